@@ -1,0 +1,108 @@
+// Dynamic per-token activation quantisation (INT8 / FP8), one CTA per row.
+// Arithmetic contract: gemlite/quant_utils.py:268-305 -- fp32 absmax / qmax, clamp 1e-6, x / s with
+// the same div.full.f32 the reference's Triton `/` lowers to, clamp to [min, max], INT8 rounds half
+// away from zero (libdevice.round, :255-257), FP8 converts round-to-nearest-even (saturating).
+// HBM-bound: the row is read once with 128-bit loads into registers, reduced, and written once.
+#include "gl_common.cuh"
+
+namespace glb {
+namespace {
+
+constexpr int AQ_THREADS = 256;
+constexpr int AQ_MAX_PER_THREAD = 64;  // register-resident up to K = 16384
+
+template <typename XT> __device__ __forceinline__ float x_to_float(XT v);
+template <> __device__ __forceinline__ float x_to_float<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float x_to_float<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float x_to_float<float>(float v) { return v; }
+
+template <int QD> __device__ __forceinline__ uint8_t quant_one(float v, float s, float lo, float hi) {
+  float t = div_full(v, s);
+  t = fminf(fmaxf(t, lo), hi);
+  if (QD == GLB_INT8) return (uint8_t)(int8_t)(int)roundf(t);   // half away from zero
+  if (QD == GLB_FP8E4) return float_to_fp8e4(t);
+  return float_to_fp8e5(t);
+}
+
+template <typename XT, int QD>
+__global__ void __launch_bounds__(AQ_THREADS) act_quant_kernel(const XT* __restrict__ x, uint8_t* __restrict__ q,
+                                                               float* __restrict__ s_out, int64_t K, float qmax,
+                                                               float lo, float hi) {
+  __shared__ float red[AQ_THREADS / 32];
+  __shared__ float s_sh;
+  const int64_t row = blockIdx.x;
+  const XT* xr = x + row * K;
+  uint8_t* qr = q + row * K;
+  pdl_wait_prior_grids();
+  // pass 1: absmax (values stay in registers when the row is short enough; otherwise re-read from L2)
+  float vals[AQ_MAX_PER_THREAD];
+  const bool in_regs = K <= (int64_t)AQ_THREADS * AQ_MAX_PER_THREAD;
+  float amax = 0.f;
+  if (in_regs) {
+#pragma unroll
+    for (int i = 0; i < AQ_MAX_PER_THREAD; ++i) {
+      const int64_t k = (int64_t)i * AQ_THREADS + threadIdx.x;
+      vals[i] = (k < K) ? x_to_float<XT>(xr[k]) : 0.f;
+      amax = fmaxf(amax, fabsf(vals[i]));
+    }
+  } else {
+    for (int64_t k = threadIdx.x; k < K; k += AQ_THREADS) amax = fmaxf(amax, fabsf(x_to_float<XT>(xr[k])));
+  }
+  amax = warp_max(amax);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = amax;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = (threadIdx.x < AQ_THREADS / 32) ? red[threadIdx.x] : 0.f;
+    v = warp_max(v);
+    if (threadIdx.x == 0) {
+      float s = fmaxf(div_full(v, qmax), 1e-6f);
+      s_sh = s;
+      s_out[row] = s;
+    }
+  }
+  __syncthreads();
+  const float s = s_sh;
+  pdl_launch_dependents();
+  if (in_regs) {
+#pragma unroll
+    for (int i = 0; i < AQ_MAX_PER_THREAD; ++i) {
+      const int64_t k = (int64_t)i * AQ_THREADS + threadIdx.x;
+      if (k < K) qr[k] = quant_one<QD>(vals[i], s, lo, hi);
+    }
+  } else {
+    for (int64_t k = threadIdx.x; k < K; k += AQ_THREADS) qr[k] = quant_one<QD>(x_to_float<XT>(xr[k]), s, lo, hi);
+  }
+}
+
+template <typename XT>
+int launch_aq(const void* x, int64_t M, int64_t K, int q_dtype, void* q, float* s, cudaStream_t stream) {
+  dim3 grid((unsigned)M), block(AQ_THREADS);
+  switch (q_dtype) {
+    case GLB_INT8: act_quant_kernel<XT, GLB_INT8><<<grid, block, 0, stream>>>((const XT*)x, (uint8_t*)q, s, K, 127.f, -128.f, 127.f); break;
+    case GLB_FP8E4: act_quant_kernel<XT, GLB_FP8E4><<<grid, block, 0, stream>>>((const XT*)x, (uint8_t*)q, s, K, 448.f, -448.f, 448.f); break;
+    case GLB_FP8E5: act_quant_kernel<XT, GLB_FP8E5><<<grid, block, 0, stream>>>((const XT*)x, (uint8_t*)q, s, K, 57344.f, -57344.f, 57344.f); break;
+    default: set_error("quant_act_per_token: unsupported q_dtype %d", q_dtype); return GLB_ERR_UNSUPPORTED;
+  }
+  count_launch();
+  GLB_CHECK_CUDA(cudaGetLastError());
+  return GLB_OK;
+}
+
+}  // namespace
+}  // namespace glb
+
+using namespace glb;
+
+extern "C" int glb_quant_act_per_token(const void* x, int64_t M, int64_t K, int x_dtype, int q_dtype, void* q, float* s,
+                                       void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GLB_REQUIRE(x && q && s && M > 0 && K > 0, GLB_ERR_INVALID, "quant_act_per_token: bad arguments");
+  GLB_REQUIRE(M <= 0x7fffffffLL, GLB_ERR_UNSUPPORTED, "quant_act_per_token: M too large");
+  set_kernel_name("act_quant_per_token");
+  switch (x_dtype) {
+    case GLB_FP16: return launch_aq<__half>(x, M, K, q_dtype, q, s, stream);
+    case GLB_BF16: return launch_aq<__nv_bfloat16>(x, M, K, q_dtype, q, s, stream);
+    case GLB_FP32: return launch_aq<float>(x, M, K, q_dtype, q, s, stream);
+    default: set_error("quant_act_per_token: unsupported x_dtype %d", x_dtype); return GLB_ERR_UNSUPPORTED;
+  }
+}

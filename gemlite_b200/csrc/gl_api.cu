@@ -1,0 +1,103 @@
+// C-ABI entry points + kernel-family dispatch (see include/gemlite_b200.h).
+#include <stdarg.h>
+#include <string.h>
+
+#include "gl_common.cuh"
+
+namespace glb {
+
+static thread_local char tl_error[512] = "";
+static thread_local const char* tl_kernel = "";
+static std::atomic<uint64_t> g_launches{0};
+std::atomic<int> g_pdl_enabled{1};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(tl_error, sizeof(tl_error), fmt, ap);
+  va_end(ap);
+}
+void set_kernel_name(const char* name) { tl_kernel = name; }
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+static int validate(const glb_linear* L, int64_t M) {
+  GLB_REQUIRE(L != nullptr, GLB_ERR_INVALID, "layer descriptor is NULL");
+  GLB_REQUIRE(L->W_q != nullptr && L->K > 0 && L->N > 0, GLB_ERR_INVALID, "layer has no weights");
+  GLB_REQUIRE(M > 0, GLB_ERR_INVALID, "M must be positive (got %lld)", (long long)M);
+  GLB_REQUIRE(L->elements_per_sample >= 1, GLB_ERR_INVALID, "elements_per_sample must be >= 1");
+  GLB_REQUIRE(L->wq_rows * L->elements_per_sample == L->K && L->wq_cols == L->N, GLB_ERR_INVALID,
+              "W_q shape (%lld, %lld) does not match K=%lld N=%lld eps=%d", (long long)L->wq_rows,
+              (long long)L->wq_cols, (long long)L->K, (long long)L->N, L->elements_per_sample);
+  GLB_REQUIRE(L->W_group_mode >= 0 && L->W_group_mode <= 4, GLB_ERR_INVALID, "bad W_group_mode %d", L->W_group_mode);
+  GLB_REQUIRE(L->channel_scale_mode >= 0 && L->channel_scale_mode <= 4, GLB_ERR_INVALID, "bad channel_scale_mode %d",
+              L->channel_scale_mode);
+  if (!is_mx(L->input_dtype)) {
+    GLB_REQUIRE(L->channel_scale_mode != 4, GLB_ERR_UNSUPPORTED, "channel_scale_mode 4 needs an MX input dtype");
+    if (L->W_group_mode >= 2) GLB_REQUIRE(L->scales_numel > 0, GLB_ERR_INVALID, "W_group_mode %d needs scales", L->W_group_mode);
+    if (L->W_group_mode == 1 || L->W_group_mode >= 3)
+      GLB_REQUIRE(L->zeros_numel > 0, GLB_ERR_INVALID, "W_group_mode %d needs zeros", L->W_group_mode);
+    if (L->channel_scale_mode == 1 || L->channel_scale_mode == 3)
+      GLB_REQUIRE(L->scales_numel == L->N, GLB_ERR_INVALID, "channel-wise scaling needs N scales");
+  } else {
+    GLB_REQUIRE(L->scales_numel > 0 && L->group_size > 0, GLB_ERR_INVALID, "MX layer needs group scales");
+    GLB_REQUIRE(L->channel_scale_mode == 0, GLB_ERR_UNSUPPORTED,
+                "MX activation quantisation (channel_scale_mode %d) is not implemented yet", L->channel_scale_mode);
+  }
+  return GLB_OK;
+}
+
+// reference dispatch: core.py:100-114
+static int pick_matmul_type(const glb_linear& L, int64_t M) {
+  if (M > 64) return GLB_MM_GEMM;
+  if (M > 1) return GLB_MM_GEMM_SPLITK;
+  if (is_mx(L.input_dtype)) return GLB_MM_GEMM_SPLITK;
+  return (L.W_nbits < 8) ? GLB_MM_GEMV_REVSPLITK : GLB_MM_GEMV_SPLITK;
+}
+
+}  // namespace glb
+
+using namespace glb;
+
+extern "C" int glb_version(void) { return GLB_ABI_VERSION; }
+extern "C" const char* glb_last_error(void) { return tl_error; }
+extern "C" const char* glb_last_kernel(void) { return tl_kernel; }
+extern "C" uint64_t glb_launch_count(void) { return g_launches.load(); }
+extern "C" void glb_set_pdl(int enabled) { g_pdl_enabled.store(enabled ? 1 : 0); }
+extern "C" int glb_get_pdl(void) { return g_pdl_enabled.load(); }
+
+extern "C" size_t glb_workspace_bytes(const glb_linear* L, int64_t M, int matmul_type) {
+  if (!L || M <= 0) return 0;
+  if (matmul_type == GLB_MM_AUTO) matmul_type = pick_matmul_type(*L, M);
+  if (gemm_tc_supported(*L, M) && !(gemv_supported(*L, M) && matmul_type <= GLB_MM_GEMV_SPLITK))
+    return gemm_tc_workspace(*L, M);
+  return 0;
+}
+
+extern "C" int glb_matmul(const glb_linear* L, const void* x, const void* scales_x, void* y, int64_t M, int matmul_type,
+                          void* workspace, size_t workspace_bytes, const void* bias, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int rc = validate(L, M);
+  if (rc != GLB_OK) return rc;
+  GLB_REQUIRE(x && y, GLB_ERR_INVALID, "x / y is NULL");
+  GLB_REQUIRE(matmul_type >= GLB_MM_AUTO && matmul_type <= GLB_MM_GEMM, GLB_ERR_INVALID, "bad matmul_type %d", matmul_type);
+  if (L->channel_scale_mode == 2 || L->channel_scale_mode == 3)
+    GLB_REQUIRE(scales_x != nullptr, GLB_ERR_INVALID, "channel_scale_mode %d needs activation scales", L->channel_scale_mode);
+  if (matmul_type == GLB_MM_AUTO) matmul_type = pick_matmul_type(*L, M);
+  const bool gemv_name = (matmul_type <= GLB_MM_GEMV_SPLITK);
+  // the GEMV names are M == 1 kernels in the reference (tests skip them for M > 1)
+  GLB_REQUIRE(!(gemv_name && M > 16), GLB_ERR_UNSUPPORTED, "GEMV kernels take at most 16 rows (got %lld)", (long long)M);
+  const float* sx = reinterpret_cast<const float*>(scales_x);
+
+  // 1. decode kernel: small M, packed 4-bit (M == 1 .. 16)
+  if (gemv_supported(*L, M) && (gemv_name || !gemm_tc_supported(*L, M)))
+    return launch_gemv(*L, x, sx, y, M, bias, stream);
+  // 2. tcgen05 tensor-core kernel
+  if (gemm_tc_supported(*L, M)) {
+    const size_t need = gemm_tc_workspace(*L, M);
+    GLB_REQUIRE(need == 0 || (workspace && workspace_bytes >= need), GLB_ERR_WORKSPACE,
+                "workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+    return launch_gemm_tc(*L, x, sx, y, M, workspace, workspace_bytes, bias, stream);
+  }
+  // 3. general-case CUDA-core kernel
+  return launch_generic(*L, x, sx, y, M, bias, stream);
+}

@@ -1,0 +1,107 @@
+"""CPU: the C-ABI library builds, loads and exports exactly what include/gemlite_b200.h declares;
+host-side logic (validation, mode resolution inputs, dispatch table) behaves like the reference."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+import torch
+
+import gemlite_b200
+from gemlite_b200 import DType, GemLiteLinear, _cabi, get_matmul_type
+from gemlite_b200.build import build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_builds_and_exports_header_symbols():
+    lib_path = build()
+    assert os.path.exists(lib_path)
+    header = open(os.path.join(ROOT, "include", "gemlite_b200.h")).read()
+    declared = sorted(set(re.findall(r"GLB_API\s+[\w\s\*]+?\b(glb_\w+)\s*\(", header)))
+    assert declared == sorted(_cabi.EXPORTS)
+    out = subprocess.run(["nm", "-D", "--defined-only", lib_path], capture_output=True, text=True).stdout
+    exported = sorted(l.split()[-1] for l in out.splitlines() if " T " in l)
+    assert exported == declared, (exported, declared)
+    lib = _cabi.load()
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.glb_version() == 1
+
+
+def test_struct_layout_matches_header():
+    src = '#include "%s/include/gemlite_b200.h"\n#include <stdio.h>\n#include <stddef.h>\nint main(){printf("%%zu %%zu %%zu %%zu\\n", sizeof(glb_linear), offsetof(glb_linear, scales), offsetof(glb_linear, K), offsetof(glb_linear, W_group_mode));}' % ROOT
+    exe = "/tmp/_glb_sz"
+    subprocess.run(["gcc", "-x", "c", "-", "-o", exe], input=src, text=True, check=True)
+    size, o_scales, o_k, o_wgm = map(int, subprocess.run([exe], capture_output=True, text=True).stdout.split())
+    assert size == ctypes.sizeof(_cabi.GlbLinear)
+    assert o_scales == _cabi.GlbLinear.scales.offset
+    assert o_k == _cabi.GlbLinear.K.offset
+    assert o_wgm == _cabi.GlbLinear.W_group_mode.offset
+
+
+def test_dtype_enum_wire_values():
+    want = dict(FP32=0, FP16=1, BF16=2, FP8=3, INT8=4, UINT8=5, INT32=6, UINT32=7, FP8e5=8, INT16=9, UINT16=10,
+                INT64=11, FP8e4nuz=12, FP8e5nuz=13, MXFP16=14, MXBF16=15, MXFP8=16, MXFP4=17, NVFP4=18, E8M0=19)
+    for k, v in want.items():
+        assert DType[k].value == v
+
+
+def test_dispatch_table_matches_reference():
+    # core.py:100-114
+    assert get_matmul_type(1, 4) == "GEMV_REVSPLITK"
+    assert get_matmul_type(1, 8) == "GEMV_SPLITK"
+    assert get_matmul_type(1, 4, True) == "GEMM_SPLITK"
+    assert get_matmul_type(2, 4) == "GEMM_SPLITK" and get_matmul_type(64, 4) == "GEMM_SPLITK"
+    assert get_matmul_type(65, 4) == "GEMM"
+    assert gemlite_b200.GEMLITE_MATMUL_TYPES == ["GEMV", "GEMV_REVSPLITK", "GEMV_SPLITK", "GEMM_SPLITK", "GEMM"]
+
+
+def test_constructor_validation_like_reference():
+    with pytest.raises(NotImplementedError):
+        GemLiteLinear(W_nbits=3, group_size=64, in_features=256, out_features=64)
+    with pytest.raises(NotImplementedError):
+        GemLiteLinear(W_nbits=4, group_size=64, in_features=250, out_features=64)
+    with pytest.raises(NotImplementedError):
+        GemLiteLinear(W_nbits=4, group_size=8, in_features=256, out_features=64)
+    with pytest.raises(NotImplementedError):
+        GemLiteLinear(W_nbits=4, group_size=48, in_features=256, out_features=64)
+    layer = GemLiteLinear(W_nbits=4, group_size=None, in_features=256, out_features=64)
+    assert layer.group_size == 1 and layer.unpack_mask == 15
+    # fp16 inputs never get dynamic activation scaling (core.py:293-296)
+    assert GemLiteLinear(4, 64, 256, 64, DType.FP16, DType.FP16, scaled_activations=True).scaled_activations is False
+    assert GemLiteLinear(8, 256, 256, 64, DType.INT8, DType.FP16, scaled_activations=True).scaled_activations is True
+    assert GemLiteLinear(8, 256, 256, 64, DType.INT8, DType.FP16).acc_dtype == DType.INT32
+
+
+def test_no_cpu_fallback():
+    """The product must fail loudly off-GPU instead of computing on the host."""
+    layer = GemLiteLinear(4, 64, 256, 64, DType.FP16, DType.FP16)
+    W_q = torch.randint(0, 16, (64, 256), dtype=torch.uint8)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        layer.pack(W_q, torch.ones(256, 1, dtype=torch.float16), torch.ones(256, 1, dtype=torch.float16))
+
+
+def test_product_does_not_import_oracle():
+    import ast
+    pkg = os.path.join(ROOT, "gemlite_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            tree = ast.parse(open(os.path.join(pkg, fn)).read())
+            for node in ast.walk(tree):
+                names = []
+                if isinstance(node, ast.Import):
+                    names = [a.name for a in node.names]
+                elif isinstance(node, ast.ImportFrom):
+                    names = [node.module or ""]
+                assert not any(n.split(".")[0] == "oracle" for n in names), fn
+
+
+def test_matmul_rejects_bad_descriptor_without_gpu():
+    lib = _cabi.load()
+    d = _cabi.GlbLinear()
+    rc = lib.glb_matmul(ctypes.byref(d), None, None, None, 1, -1, None, 0, None, None)
+    assert rc == -1 and b"no weights" in lib.glb_last_error()
+    assert lib.glb_pack_cols(None, 4, 64, 3, 32, None, 1, None) == -1
+    assert b"nbits" in lib.glb_last_error()

@@ -1,0 +1,337 @@
+"""GPU parity: the CUDA path (through the public API -> C ABI) against (a) the golden fixtures written
+by the reference itself and (b) the CPU oracle on seeded inputs.  Integer / byte work is bit-exact;
+floating point uses the tolerances stated next to each check."""
+import numpy as np
+import pytest
+import torch
+
+import gemlite_b200
+from gemlite_b200 import DType, GemLiteLinear, _cabi
+from gemlite_b200 import bitpack as B
+from gemlite_b200.helper import (A16W8_INT8, A16W4_HQQ_INT, A16W8_FP8, A8W8_INT8_dynamic, A8W8_FP8_dynamic,
+                                 A16W4_MXFP, A16W8_MXFP, A16W158_INT)
+from gemlite_b200.quant_utils import scale_activations_per_token
+from oracle import gemlite_oracle as O
+from oracle import recipes as R
+from golden_io import from_bits, layer_cases, load, tdtype
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+# |y_cuda - y_oracle| <= REL * max|y_oracle|: one output ulp of headroom plus fp32 summation-order noise
+REL = {torch.float16: 2.0e-3, torch.bfloat16: 1.6e-2, torch.float32: 2e-5}
+# the decode kernel factors scale/zero per group (y += s*sum(x q) + z'*sum(x)) instead of rounding every
+# dequantised weight to fp16 first; that differs from the oracle by weight-rounding noise (<= 2^-11 rel.
+# per weight, averaging out over K) -- bound stated against max|y|:
+REL_DECODE = {torch.float16: 3.0e-3, torch.bfloat16: 2.0e-2}
+
+
+def relerr(y, yref):
+    y, yref = y.double().cpu(), yref.double().cpu()
+    return ((y - yref).abs().max() / (yref.abs().max() + 1e-30)).item()
+
+
+def gen_int(N, K, nbits, gs, dtype, seed):
+    g = torch.Generator().manual_seed(seed)
+    W_q = torch.randint(0, 2 ** nbits, (N, K), generator=g, dtype=torch.int32).to(torch.uint8)
+    ng = N * K // gs
+    scales = (torch.rand(ng, 1, generator=g) * 0.01 + 0.001).to(dtype)
+    zeros = (torch.rand(ng, 1, generator=g) * (2 ** nbits - 1)).to(dtype)
+    return W_q, scales, zeros
+
+
+def xgen(M, K, dtype, seed):
+    return (torch.randn(M, K, generator=torch.Generator().manual_seed(seed)) / 10.0).to(dtype)
+
+
+# ------------------------------------------------------------------------------------------------
+def test_native_library_is_loaded():
+    lib = _cabi.load()
+    assert lib.glb_version() == 1
+    assert "libgemlite_b200.so" in open("/proc/self/maps").read()
+
+
+@pytest.mark.parametrize("nbits", [8, 4, 2, 1])
+@pytest.mark.parametrize("pw", [8, 16, 32, 64])
+def test_pack_unpack_bit_exact(nbits, pw):
+    if pw < nbits:
+        pytest.skip("word narrower than a code")
+    g = torch.Generator().manual_seed(nbits * 100 + pw)
+    for (rows, cols) in [(16, 128), (96, 4096), (33, 256)]:
+        W_q = torch.randint(0, 2 ** nbits, (rows, cols), generator=g, dtype=torch.int32).to(torch.uint8)
+        for tr in (True, False):
+            ref, eps = O.pack_over_cols(W_q.numpy(), nbits, pw, tr)
+            out, eps2 = B.pack_weights_over_cols(W_q.to(DEV), nbits, pw, tr)
+            assert eps == eps2 and tuple(out.shape) == ref.shape
+            assert np.array_equal(out.cpu().numpy(), np.ascontiguousarray(ref)), (nbits, pw, tr, rows, cols)
+            back = B.unpack_over_cols(out, nbits, cols, transpose=tr)
+            assert torch.equal(back.cpu(), W_q)
+
+
+def test_pack_matches_reference_fixture():
+    z, _ = load("bitpack")
+    for nbits in (8, 4, 2, 1):
+        W_q = torch.from_numpy(z[f"in_b{nbits}"]).to(DEV)
+        for pw in (8, 16, 32, 64):
+            if pw < nbits:
+                continue
+            for tr in (1, 0):
+                out, _ = B.pack_weights_over_cols(W_q, nbits, pw, bool(tr))
+                key = f"triton_b{nbits}_w{pw}_t{tr}"
+                ref = z[key] if key in z.files else z[f"torch_b{nbits}_w{pw}_t{tr}"]
+                assert np.array_equal(out.cpu().numpy(), ref), key
+
+
+# ------------------------------------------------------------------------------------------------
+def build_gpu_layer(name, z, info):
+    """Same construction as tests/golden/make_golden.py, on the GPU with gemlite_b200."""
+    if name.startswith("a16w") and "in_W_q" in z.files:
+        parts = name.split("_")
+        nbits = int(parts[0][4:])
+        dtype = torch.bfloat16 if "bf16" in name else torch.float16
+        gs = 256 if "channelwise" in name else int([p for p in parts if p.startswith("gs")][0][2:])
+        W_q = torch.from_numpy(z["in_W_q"]).to(DEV)
+        scales = from_bits(z["in_scales"], dtype).to(DEV)
+        zeros = from_bits(z["in_zeros"], dtype).to(DEV)
+        bias = from_bits(z["in_bias"], dtype).to(DEV) if "in_bias" in z.files else None
+        N, K = W_q.shape
+        gd = gemlite_b200.dtypes.TORCH_TO_DTYPE[dtype]
+        layer = GemLiteLinear(nbits, gs, K, N, gd, gd)
+        layer.pack(W_q, scales, zeros, bias, fma_mode="nofma" not in name,
+                   packing_bitwidth=8 if name.endswith("pw8") else None)
+        return layer
+    if name.startswith("a16w8_int8"):
+        W = from_bits(z["in_W"], torch.float16)
+        return A16W8_INT8(device=DEV, dtype=torch.float16, post_scale=name.endswith("postscale")).from_weights(W.clone())
+    if name == "int8_w4_scalar_zero":
+        W_q = torch.from_numpy(z["in_W_q"]).to(DEV)
+        sc = from_bits(z["in_scales"], torch.float16).to(DEV)
+        N, K = W_q.shape
+        layer = GemLiteLinear(4, K, K, N, DType.INT8, DType.FP32, scaled_activations=False)
+        layer.pack(W_q, scales=sc, zeros=7, bias=None)
+        return layer
+    if name.startswith("a8w8_"):
+        W = from_bits(z["in_W"], torch.float16)
+        proc = A8W8_FP8_dynamic(device=DEV, dtype=torch.float16) if "fp8" in name else \
+            A8W8_INT8_dynamic(device=DEV, dtype=torch.float16)
+        return proc.from_weights(W.clone())
+    if "mxfp" in name:
+        W = from_bits(z["in_W"], torch.bfloat16)
+        lin = torch.nn.Linear(W.shape[1], W.shape[0], bias=False, dtype=torch.bfloat16, device=DEV)
+        lin.weight.data = W.to(DEV)
+        proc = (A16W4_MXFP if name.startswith("a16w4") else A16W8_MXFP)(device=DEV, dtype=torch.bfloat16)
+        return proc.from_linear(lin, del_orig=False)
+    raise KeyError(name)
+
+
+@pytest.mark.parametrize("name", layer_cases())
+def test_against_reference_fixtures(name):
+    """pack() reproduces the reference's tensors/metadata bit for bit; forward() matches the reference
+    kernels' recorded outputs (where the CPU interpreter executes them faithfully) and the oracle."""
+    z, info = load(name)
+    layer = build_gpu_layer(name, z, info)
+    assert layer.get_meta_args() == [int(v) for v in z["meta_args"]]
+    assert list(layer.W_q.shape) == info["W_q_shape"]
+    assert list(layer.W_q.stride()) == [int(v) for v in z["packed_W_q_strides"]]
+    wq = layer.W_q.data.contiguous().cpu()
+    wq_bits = wq.view(torch.uint8).numpy() if wq.dtype.is_floating_point else wq.numpy()
+    assert np.array_equal(wq_bits, z["packed_W_q"]), "packed W_q differs from the reference"
+    sdt, zdt = tdtype(info["scales_dtype"]), tdtype(info["zeros_dtype"])
+    assert layer.scales.dtype == sdt and layer.zeros.dtype == zdt
+    assert list(layer.scales.shape) == info["scales_shape"] and list(layer.zeros.shape) == info["zeros_shape"]
+    assert torch.equal(layer.scales.data.contiguous().cpu(), from_bits(z["packed_scales"], sdt).view(layer.scales.shape))
+    assert torch.equal(layer.zeros.data.contiguous().cpu(), from_bits(z["packed_zeros"], zdt).view(layer.zeros.shape))
+    assert layer.metadata.tolist() == [int(v) for v in z["metadata_param"]]
+
+    # oracle layer from the same inputs
+    from test_oracle_golden import build_oracle_layer, _interpreter_untrustworthy
+    p = build_oracle_layer(name, z, info)
+    xdt = tdtype(info["x_dtype"])
+    out_t = O.TORCH_OF[p.output_dtype]
+    i = 0
+    while f"x{i}" in z.files:
+        x = from_bits(z[f"x{i}"], xdt)
+        M = x.shape[0]
+        y_or = O.forward(p, x)
+        for mt in (["GEMV_REVSPLITK", "GEMV", "GEMV_SPLITK"] if M == 1 else []) + ["GEMM_SPLITK", "GEMM", None]:
+            y = layer.forward_manual(x.to(DEV), mt) if mt else layer(x.to(DEV))
+            assert y.dtype == out_t and tuple(y.shape) == (M, p.out_features)
+            kern = _cabi.last_kernel()
+            tol = REL_DECODE[out_t] if kern == "gemv_w4_mma" else REL[out_t]
+            if p.scaled_activations and xdt != torch.int8:
+                tol = max(tol, 2e-2)   # an activation code may round the other way (div.full.f32 vs IEEE divide)
+            e = relerr(y, y_or)
+            assert e <= tol, (name, mt, kern, e, tol)
+            # reference's own recorded output for the fp32-accumulating kernels
+            key = f"y_GEMM_SPLITK_M{M}"
+            if key in z.files and not _interpreter_untrustworthy(name, p):
+                e2 = relerr(y, from_bits(z[key], out_t))
+                assert e2 <= max(tol, 2.5e-3), (name, mt, "vs reference GEMM_SPLITK", e2)
+        i += 1
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("mode", ["fma", "nofma", "sym"])
+@pytest.mark.parametrize("gs", [32, 64, 128])
+def test_a16w4_decode_and_small_batch_vs_oracle(dtype, mode, gs):
+    N, K = 256, 1024
+    W_q, scales, zeros = gen_int(N, K, 4, gs, dtype, seed=gs + (7 if mode == "fma" else 11))
+    gd = gemlite_b200.dtypes.TORCH_TO_DTYPE[dtype]
+    bias = (torch.randn(N, generator=torch.Generator().manual_seed(3)) / 10).to(dtype)
+    layer = GemLiteLinear(4, gs, K, N, gd, gd)
+    z_in = None if mode == "sym" else zeros
+    layer.pack(W_q.to(DEV), scales.to(DEV), None if z_in is None else z_in.to(DEV), bias.to(DEV), fma_mode=(mode == "fma"))
+    p = O.prepare(W_q, scales, z_in, W_nbits=4, group_size=gs, in_features=K, out_features=N,
+                  input_dtype=O.DTYPE_OF[dtype], output_dtype=O.DTYPE_OF[dtype], bias=bias, fma_mode=(mode == "fma"))
+    assert layer.W_group_mode == p.W_group_mode == {"fma": 4, "nofma": 3, "sym": 2}[mode]
+    for M in (1, 2, 5, 8, 16, 33):
+        x = xgen(M, K, dtype, 50 + M)
+        y = layer(x.to(DEV))
+        kern = _cabi.last_kernel()
+        tol = REL_DECODE[dtype] if kern == "gemv_w4_mma" else REL[dtype]
+        e = relerr(y, O.forward(p, x))
+        assert e <= tol, (dtype, mode, gs, M, kern, e)
+    assert layer(xgen(1, K, dtype, 1).to(DEV)).shape == (1, N)
+    # leading batch dims are preserved (core.py:151-152)
+    assert layer(xgen(6, K, dtype, 2).view(2, 3, K).to(DEV)).shape == (2, 3, N)
+
+
+def test_decode_kernel_is_used_for_the_headline_shape():
+    N = K = 4096
+    W_q, scales, zeros = gen_int(N, K, 4, 128, torch.float16, seed=0)
+    layer = A16W4_HQQ_INT(device=DEV, dtype=torch.float16).from_weights(W_q, scales, zeros)
+    assert (layer.W_group_mode, layer.channel_scale_mode, layer.elements_per_sample) == (4, 0, 8)
+    assert tuple(layer.W_q.shape) == (512, 4096) and layer.W_q.dtype == torch.int32 and layer.W_q.is_contiguous()
+    x = xgen(1, K, torch.float16, 5).to(DEV)
+    before = _cabi.launch_count()
+    y = layer(x)
+    assert _cabi.last_kernel() == "gemv_w4_mma" and _cabi.launch_count() == before + 1
+    # full-size check against a torch fp32 dequant + matmul on the device (tolerance: REL_DECODE)
+    Wd = ((W_q.to(DEV).view(-1, 128).float() - zeros.to(DEV).float()) * scales.to(DEV).float()).view(N, K)
+    yref = x.float() @ Wd.t()
+    assert relerr(y, yref) <= REL_DECODE[torch.float16]
+    # linearity in x (size-independent property): y(2x) == 2 y(x) exactly in fp16 (power-of-two scaling)
+    assert torch.equal(layer(2 * x), 2 * y)
+    # determinism: no atomics anywhere on the path
+    assert torch.equal(layer(x), y)
+
+
+def test_per_token_activation_quant_vs_oracle():
+    for dtype in (torch.float16, torch.bfloat16, torch.float32):
+        for wdt in (torch.int8, torch.float8_e4m3fn):
+            x = xgen(37, 4096, dtype, 99)
+            q, s = scale_activations_per_token(x.to(DEV), wdt)
+            qo, so = O.quantize_activations_per_token(x, wdt)
+            assert s.shape == (37, 1) and q.shape == x.shape and q.dtype == wdt
+            # scale: div.full.f32 (<= 2 ulp) vs IEEE divide
+            assert torch.allclose(s.cpu(), so, rtol=3e-7, atol=0)
+            if wdt == torch.int8:
+                d = (q.cpu().int() - qo.int()).abs()
+                assert d.max().item() <= 1 and (d > 0).float().mean().item() < 2e-3
+            else:
+                mism = (q.cpu().view(torch.uint8) != qo.view(torch.uint8)).float().mean().item()
+                assert mism < 2e-3
+    # empty and single-row inputs
+    q, s = scale_activations_per_token(torch.zeros(1, 64, dtype=torch.float16, device=DEV), torch.int8)
+    assert s.item() == pytest.approx(1e-6) and int(q.abs().max()) == 0
+
+
+def test_int8_matmul_bit_exact():
+    """INT8 x INT8 -> INT32 is exact; with the activation codes/scales the GPU produced, the fp16 output
+    must equal the oracle's bit for bit at every batch size (epilogue cvt.rn.f32.s32 * (sa*sb) -> fp16)."""
+    N = K = 1024
+    W = (torch.randn(N, K, generator=torch.Generator().manual_seed(8)) / 10).half()
+    layer = A8W8_INT8_dynamic(device=DEV, dtype=torch.float16).from_weights(W.clone())
+    p = R.a8w8_dynamic(W, torch.float16)
+    assert torch.equal(layer.W_q.data.cpu(), p.W_q) and torch.equal(layer.scales.data.cpu(), p.scales)
+    for M in (1, 3, 16, 64, 65, 200):
+        x = xgen(M, K, torch.float16, M)
+        xq, sx = scale_activations_per_token(x.to(DEV), torch.int8)
+        y = layer(x.to(DEV))
+        y_or = O.forward(p, xq.cpu(), scales_x=sx.cpu())
+        assert torch.equal(y.cpu(), y_or), (M, relerr(y, y_or))
+        # raw int32 accumulator through an unscaled layer
+    acc_layer = GemLiteLinear(8, None, K, N, DType.INT8, DType.INT32)
+    Wi = torch.randint(-128, 128, (N, K), generator=torch.Generator().manual_seed(1), dtype=torch.int32).to(torch.int8)
+    acc_layer.pack(Wi.to(DEV), None, None)
+    xi = torch.randint(-128, 128, (9, K), generator=torch.Generator().manual_seed(2), dtype=torch.int32).to(torch.int8)
+    got = acc_layer(xi.to(DEV))
+    assert got.dtype == torch.int32 and torch.equal(got.cpu(), xi.int() @ Wi.int().t())
+
+
+def test_fp8_dynamic_and_weight_only_paths():
+    N = K = 512
+    W = (torch.randn(N, K, generator=torch.Generator().manual_seed(18)) / 10).half()
+    layer = A8W8_FP8_dynamic(device=DEV, dtype=torch.float16).from_weights(W.clone())
+    p = R.a8w8_dynamic(W, torch.float16, fp8=torch.float8_e4m3fn)
+    for M in (1, 4, 70):
+        x = xgen(M, K, torch.float16, 40 + M)
+        xq, sx = scale_activations_per_token(x.to(DEV), torch.float8_e4m3fn)
+        y = layer(x.to(DEV))
+        assert relerr(y, O.forward(p, xq.cpu(), scales_x=sx.cpu())) <= REL[torch.float16]
+    wl = A16W8_FP8(device=DEV, dtype=torch.float16).from_weights(W.clone())
+    pw = R.a16w8(W, torch.float16, fp8=torch.float8_e4m3fn)
+    x = xgen(3, K, torch.float16, 77)
+    assert relerr(wl(x.to(DEV)), O.forward(pw, x)) <= REL[torch.float16]
+
+
+def test_mxfp_weight_only_vs_oracle_and_unquantised():
+    torch.manual_seed(0)
+    N, K = 512, 1024
+    for nbits, tol_q in ((4, 7e-4), (8, 2e-4)):   # the reference's own bars vs the unquantised layer (test_mxfp.py:50,57)
+        W = (torch.randn(N, K) / 10).to(torch.bfloat16) / 10
+        lin = torch.nn.Linear(K, N, bias=False, dtype=torch.bfloat16, device=DEV)
+        lin.weight.data = W.to(DEV)
+        proc = (A16W4_MXFP if nbits == 4 else A16W8_MXFP)(device=DEV, dtype=torch.bfloat16)
+        layer = proc.from_linear(lin, del_orig=False)
+        assert layer.W_q.numel() * layer.W_q.itemsize == N * K * nbits // 8 and not layer.scaled_activations
+        p, codes, sc = R.a16wn_mxfp(W, nbits, torch.bfloat16)
+        assert torch.equal(layer.scales.data.cpu(), p.scales) and list(layer.W_q.stride()) == list(p.W_q.stride())
+        assert torch.equal(layer.W_q.data.cpu().contiguous().view(torch.uint8), p.W_q.contiguous().view(torch.uint8))
+        for M in (1, 4, 16):
+            x = (torch.randn(M, K) / 10).to(torch.bfloat16)
+            y = layer(x.to(DEV))
+            assert relerr(y, O.forward(p, x)) <= REL[torch.bfloat16]
+            assert (lin(x.to(DEV)) - y).abs().mean().item() < tol_q
+
+
+def test_bitnet_and_state_dict_roundtrip(tmp_path):
+    N, K = 128, 512
+    g = torch.Generator().manual_seed(4)
+    Wt = torch.randint(-1, 2, (N, K), generator=g).half()
+    layer = A16W158_INT(device=DEV, dtype=torch.float16).from_weights(Wt, torch.tensor(0.02))
+    assert (layer.W_group_mode, layer.channel_scale_mode, layer.W_nbits) == (1, 1, 2)
+    x = xgen(2, K, torch.float16, 6)
+    yref = (x.float() @ (Wt.float() * 0.02).t())
+    assert relerr(layer(x.to(DEV)), yref) <= 3e-3
+
+    W_q, scales, zeros = gen_int(N, K, 4, 64, torch.float16, seed=21)
+    l1 = GemLiteLinear(4, 64, K, N, DType.FP16, DType.FP16).pack(W_q.to(DEV), scales.to(DEV), zeros.to(DEV), None)
+    keys = set(l1.state_dict().keys())
+    assert keys == {"W_q", "scales", "zeros", "metadata", "orig_shape"}      # core.py:502-517 (bias absent)
+    f = tmp_path / "layer.pt"
+    torch.save(l1.state_dict(), f)
+    l2 = GemLiteLinear()
+    l2.load_state_dict(torch.load(f))
+    assert l1.get_meta_args() == l2.get_meta_args()
+    for a, b in zip(l1.get_tensor_args(), l2.get_tensor_args()):
+        assert torch.equal(a, b)
+    for M in (1, 4):
+        xx = xgen(M, K, torch.float16, M).to(DEV)
+        assert (l1.forward_manual(xx, "GEMM") - l2.forward_manual(xx, "GEMM")).abs().mean().item() < 1e-7
+
+
+def test_error_behaviour():
+    layer = GemLiteLinear(4, 64, 256, 64, DType.FP16, DType.FP16)
+    W_q, scales, zeros = gen_int(64, 256, 4, 64, torch.float16, seed=1)
+    layer.pack(W_q.to(DEV), scales.to(DEV), zeros.to(DEV))
+    with pytest.raises(TypeError):
+        layer(torch.zeros(1, 256, dtype=torch.bfloat16, device=DEV))
+    with pytest.raises(KeyError):
+        layer.forward_manual(torch.zeros(1, 256, dtype=torch.float16, device=DEV), "NOPE")
+    with pytest.raises(Exception, match="INT8 inputs is not compatible"):
+        GemLiteLinear(4, 64, 256, 64, DType.INT8, DType.FP16).pack(W_q.to(DEV), scales.to(DEV), zeros.to(DEV) + 0.5)
+    with pytest.raises(AssertionError):
+        B.pack_weights_over_cols(W_q.to(DEV), 3, 32, True)
+    assert layer(torch.zeros(0, 256, dtype=torch.float16, device=DEV)).shape == (0, 64)
