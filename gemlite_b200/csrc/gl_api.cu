@@ -68,8 +68,7 @@ extern "C" int glb_get_pdl(void) { return g_pdl_enabled.load(); }
 extern "C" size_t glb_workspace_bytes(const glb_linear* L, int64_t M, int matmul_type) {
   if (!L || M <= 0) return 0;
   if (matmul_type == GLB_MM_AUTO) matmul_type = pick_matmul_type(*L, M);
-  if (gemm_tc_supported(*L, M) && !(gemv_supported(*L, M) && matmul_type <= GLB_MM_GEMV_SPLITK))
-    return gemm_tc_workspace(*L, M);
+  if (gemm_tc_supported(*L, M)) return gemm_tc_workspace(*L, M);
   return 0;
 }
 
@@ -82,17 +81,20 @@ extern "C" int glb_matmul(const glb_linear* L, const void* x, const void* scales
   GLB_REQUIRE(matmul_type >= GLB_MM_AUTO && matmul_type <= GLB_MM_GEMM, GLB_ERR_INVALID, "bad matmul_type %d", matmul_type);
   if (L->channel_scale_mode == 2 || L->channel_scale_mode == 3)
     GLB_REQUIRE(scales_x != nullptr, GLB_ERR_INVALID, "channel_scale_mode %d needs activation scales", L->channel_scale_mode);
-  if (matmul_type == GLB_MM_AUTO) matmul_type = pick_matmul_type(*L, M);
+  const bool was_auto = (matmul_type == GLB_MM_AUTO);
+  if (was_auto) matmul_type = pick_matmul_type(*L, M);
   const bool gemv_name = (matmul_type <= GLB_MM_GEMV_SPLITK);
   // the GEMV names are M == 1 kernels in the reference (tests skip them for M > 1)
   GLB_REQUIRE(!(gemv_name && M > 16), GLB_ERR_UNSUPPORTED, "GEMV kernels take at most 16 rows (got %lld)", (long long)M);
   const float* sx = reinterpret_cast<const float*>(scales_x);
+  const bool can_gemv = gemv_supported(*L, M), can_tc = gemm_tc_supported(*L, M);
 
-  // 1. decode kernel: small M, packed 4-bit (M == 1 .. 16)
-  if (gemv_supported(*L, M) && (gemv_name || !gemm_tc_supported(*L, M)))
-    return launch_gemv(*L, x, sx, y, M, bias, stream);
-  // 2. tcgen05 tensor-core kernel
-  if (gemm_tc_supported(*L, M)) {
+  // 1. decode kernel (M <= 16, packed 4-bit): the automatic choice for small batches, and what the
+  //    GEMV names select; 2. tcgen05 kernel: the automatic choice above that, and what the GEMM
+  //    names select whenever the layer qualifies.
+  const bool prefer_gemv = can_gemv && (gemv_name || (was_auto && M <= 16) || !can_tc);
+  if (prefer_gemv) return launch_gemv(*L, x, sx, y, M, bias, stream);
+  if (can_tc) {
     const size_t need = gemm_tc_workspace(*L, M);
     GLB_REQUIRE(need == 0 || (workspace && workspace_bytes >= need), GLB_ERR_WORKSPACE,
                 "workspace too small: need %zu bytes, got %zu", need, workspace_bytes);

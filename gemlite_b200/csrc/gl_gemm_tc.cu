@@ -1,10 +1,385 @@
-// tcgen05 tensor-core GEMM (placeholder until the kernel lands; keeps the link closed).
+// tcgen05 tensor-core GEMM with fused unpack + dequant (A16W4 packed int32) -- the prefill path.
+//
+// Replaces gemlite/triton_kernels/gemm_kernels.py (gemm_INT_kernel, :248-413) and, for 16 < M <= 64,
+// gemm_splitK_kernels.py.  Arithmetic contract: the dequantised weight tile is bit-identical to the
+// reference's dequantize() (utils.py:57-89: fp16/bf16 fma / sub-mul in the scale dtype), products are
+// accumulated in fp32 by the tensor core (tl.dot(..., out_dtype=fp32), gemm_kernels.py:384).
+//
+// Mapping (B200-first, not the reference's):
+//   * the WEIGHTS are the MMA "A" operand: a CTA tile is 128 output features x BT tokens; the
+//     accumulator D[feature, token] lives in TMEM (128 lanes x BT fp32 columns, double buffered).
+//     Per FLOP this needs half the dequant work of the transposed mapping and lets BT shrink to 32/64
+//     for small batches without wasting the dequant/HBM pipeline.
+//   * warp roles (384 threads): w0 TMA producer, w1 MMA issuer (one elected lane), w2 TMEM allocator,
+//     w4-7 dequant (thread = one feature row), w8-11 epilogue (TMEM -> registers -> global).
+//   * per 64-wide k-block and stage s: TMA brings the token tile x[BT,64] (128B-swizzled, K-major)
+//     and the packed weight tile Wq[8 words,128 features] (4 KB) into shared memory; dequant warps
+//     turn the 4 KB into a 16 KB fp16/bf16 K-major SW128 tile (conflict-free 128-bit stores);
+//     the MMA lane issues 4 x tcgen05.mma (K=16) and commits to the stage's "empty" barrier.
+//   * persistent: grid = #SMs, tiles are walked token-block-fastest so CTAs running together share
+//     the same weight tile in L2.
+#include <mutex>
+#include <unordered_map>
+
 #include "gl_common.cuh"
+#include "gl_ptx.cuh"
+
 namespace glb {
-bool gemm_tc_supported(const glb_linear&, int64_t) { return false; }
-size_t gemm_tc_workspace(const glb_linear&, int64_t) { return 0; }
-int launch_gemm_tc(const glb_linear&, const void*, const float*, void*, int64_t, void*, size_t, const void*, cudaStream_t) {
-  set_error("tcgen05 GEMM not built");
-  return GLB_ERR_UNSUPPORTED;
+namespace {
+
+constexpr int TC_BM = 128;            // features per tile (UMMA M)
+constexpr int TC_BK = 64;             // k per stage (128 bytes of fp16 -> one swizzle atom row)
+constexpr int TC_THREADS = 384;
+constexpr int TC_DEQ_WARP0 = 4;       // warps 4..7
+constexpr int TC_EPI_WARP0 = 8;       // warps 8..11
+
+struct TcParams {
+  const void* scales;     // (G, N)
+  const void* zeros;      // (G, N) or null
+  void* y;                // (M, N)
+  const void* bias;       // (N) or null
+  int M, N, K;
+  int group_size;
+  int mode;               // 2, 3, 4
+  int tiles_m;            // token blocks
+  int tiles_n;            // feature blocks
+};
+
+template <int BT> struct TcSmem {
+  static constexpr int X_BYTES = BT * TC_BK * 2;          // token tile
+  static constexpr int P_BYTES = (TC_BK / 8) * TC_BM * 4;  // packed words
+  static constexpr int A_BYTES = TC_BM * TC_BK * 2;        // dequantised weights
+  static constexpr int STAGE = X_BYTES + P_BYTES + A_BYTES;
+  static constexpr int STAGES = (BT >= 256) ? 4 : ((BT >= 128) ? 5 : 6);
+  static constexpr int BAR_BYTES = 1024;
+  static constexpr int TOTAL = STAGES * STAGE + BAR_BYTES + 1024 /* alignment slack */;
+};
+
+// 8 nibbles -> 8 exact small integers in memory order k0..k7, as 4 packed 16-bit pairs
+template <bool BF16> __device__ __forceinline__ void unpack8(uint32_t q, uint32_t (&o)[4]) {
+  uint32_t h[4];
+  if (!BF16) {
+    const uint32_t t = q >> 8;
+    uint32_t m0, m1, m2, m3;
+    asm("lop3.b32 %0, %1, 0x000F000F, 0x64006400, 0xEA;" : "=r"(m0) : "r"(q));
+    asm("lop3.b32 %0, %1, 0x00F000F0, 0x64006400, 0xEA;" : "=r"(m1) : "r"(q));
+    asm("lop3.b32 %0, %1, 0x000F000F, 0x64006400, 0xEA;" : "=r"(m2) : "r"(t));
+    asm("lop3.b32 %0, %1, 0x00F000F0, 0x64006400, 0xEA;" : "=r"(m3) : "r"(t));
+    const __half2 k1024 = __half2half2(__ushort_as_half((unsigned short)0x6400));
+    const __half2 k16th = __half2half2(__ushort_as_half((unsigned short)0x2C00));
+    const __half2 km64 = __half2half2(__ushort_as_half((unsigned short)0xD400));
+    __half2 r0 = __hsub2(*reinterpret_cast<__half2*>(&m0), k1024);           // (k0,k4)
+    __half2 r1 = __hfma2(*reinterpret_cast<__half2*>(&m1), k16th, km64);      // (k1,k5)
+    __half2 r2 = __hsub2(*reinterpret_cast<__half2*>(&m2), k1024);           // (k2,k6)
+    __half2 r3 = __hfma2(*reinterpret_cast<__half2*>(&m3), k16th, km64);      // (k3,k7)
+    h[0] = *reinterpret_cast<uint32_t*>(&r0); h[1] = *reinterpret_cast<uint32_t*>(&r1);
+    h[2] = *reinterpret_cast<uint32_t*>(&r2); h[3] = *reinterpret_cast<uint32_t*>(&r3);
+  } else {
+    const __nv_bfloat162 k128 = __bfloat162bfloat162(__ushort_as_bfloat16((unsigned short)0x4300));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint32_t v;
+      asm("lop3.b32 %0, %1, 0x000F000F, 0x43004300, 0xEA;" : "=r"(v) : "r"(q >> (4 * i)));
+      __nv_bfloat162 r = __hsub2(*reinterpret_cast<__nv_bfloat162*>(&v), k128);   // (k_i, k_{i+4})
+      h[i] = *reinterpret_cast<uint32_t*>(&r);
+    }
+  }
+  o[0] = __byte_perm(h[0], h[1], 0x5410);   // (k0,k1)
+  o[1] = __byte_perm(h[2], h[3], 0x5410);   // (k2,k3)
+  o[2] = __byte_perm(h[0], h[1], 0x7632);   // (k4,k5)
+  o[3] = __byte_perm(h[2], h[3], 0x7632);   // (k6,k7)
 }
+
+// reference dequantize() on a pair, in the scale dtype (one rounding per op, fma fused for mode 4)
+template <bool BF16> __device__ __forceinline__ uint32_t dequant2(uint32_t q2, uint32_t s2, uint32_t z2, int mode) {
+  if (!BF16) {
+    const __half2 q = *reinterpret_cast<__half2*>(&q2), s = *reinterpret_cast<__half2*>(&s2), z = *reinterpret_cast<__half2*>(&z2);
+    __half2 r = (mode == 4) ? __hfma2(q, s, z) : ((mode == 3) ? __hmul2(__hsub2(q, z), s) : __hmul2(q, s));
+    return *reinterpret_cast<uint32_t*>(&r);
+  } else {
+    const __nv_bfloat162 q = *reinterpret_cast<__nv_bfloat162*>(&q2), s = *reinterpret_cast<__nv_bfloat162*>(&s2),
+                         z = *reinterpret_cast<__nv_bfloat162*>(&z2);
+    __nv_bfloat162 r = (mode == 4) ? __hfma2(q, s, z) : ((mode == 3) ? __hmul2(__hsub2(q, z), s) : __hmul2(q, s));
+    return *reinterpret_cast<uint32_t*>(&r);
+  }
+}
+
+template <bool BF16, int BT>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_a16w4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const TcParams P) {
+  using S = TcSmem<BT>;
+  extern __shared__ unsigned char smem_raw[];
+  // 1024-byte alignment for the 128B swizzle atoms
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* stage_base = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::STAGES * S::STAGE);
+  uint64_t* full = bars;                       // [STAGES]  TMA landed (x + packed)
+  uint64_t* aready = bars + S::STAGES;         // [STAGES]  dequant wrote the A tile
+  uint64_t* empty = bars + 2 * S::STAGES;      // [STAGES]  MMAs reading the stage completed
+  uint64_t* tfull = bars + 3 * S::STAGES;      // [2]       accumulator buffer complete
+  uint64_t* tempty = bars + 3 * S::STAGES + 2; // [2]       accumulator buffer drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S::STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kblocks = P.K / TC_BK;
+  const int ntiles = P.tiles_m * P.tiles_n;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_x);
+    ptx::prefetch_tmap(&tmap_w);
+    for (int s = 0; s < S::STAGES; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&aready[s], 4);     // one arrival per dequant warp
+      ptx::mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(&tfull[b], 1);
+      ptx::mbar_init(&tempty[b], 4);     // one arrival per epilogue warp
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) ptx::tmem_alloc(tmem_slot, 2 * BT);
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int tm = t % P.tiles_m, tn = t / P.tiles_m;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          ptx::mbar_wait(&empty[s], ph ^ 1);
+          unsigned char* st = stage_base + s * S::STAGE;
+          ptx::mbar_arrive_expect_tx(&full[s], S::X_BYTES + S::P_BYTES);
+          ptx::tma_load_2d(st, &tmap_x, &full[s], kb * TC_BK, tm * BT);
+          ptx::tma_load_2d(st + S::X_BYTES, &tmap_w, &full[s], tn * TC_BM, kb * (TC_BK / 8));
+          if (++s == S::STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    constexpr uint32_t idesc = ptx::make_idesc(1u, BF16 ? 1u : 0u, BF16 ? 1u : 0u, TC_BM, BT);
+    int s = 0; uint32_t ph = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t bph = (it >> 1) & 1;
+      ptx::mbar_wait(&tempty[buf], bph ^ 1);
+      ptx::tc_fence_after_sync();
+      const uint32_t d_tmem = tmem_base + buf * BT;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        ptx::mbar_wait(&full[s], ph);
+        ptx::mbar_wait(&aready[s], ph);
+        ptx::tc_fence_after_sync();
+        if (ptx::elect_one()) {
+          unsigned char* st = stage_base + s * S::STAGE;
+          const uint64_t bdesc = ptx::make_sw128_kmajor_desc(ptx::smem_u32(st));
+          const uint64_t adesc = ptx::make_sw128_kmajor_desc(ptx::smem_u32(st + S::X_BYTES + S::P_BYTES));
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k)   // +32 bytes per K=16 step inside the swizzle atom
+            ptx::mma_f16_ss(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+          ptx::mma_commit(&empty[s]);
+          if (kb == kblocks - 1) ptx::mma_commit(&tfull[buf]);
+        }
+        __syncwarp();
+        if (++s == S::STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp >= TC_DEQ_WARP0 && warp < TC_DEQ_WARP0 + 4) {
+    // ================= dequant: thread = feature row =================
+    const int row = threadIdx.x - TC_DEQ_WARP0 * 32;     // 0..127
+    int s = 0; uint32_t ph = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      const int tn = t / P.tiles_m;
+      const int n = tn * TC_BM + row;
+      int cur_g = -1;
+      uint32_t s2 = 0, z2 = 0;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        ptx::mbar_wait(&full[s], ph);
+        unsigned char* st = stage_base + s * S::STAGE;
+        const uint32_t* pk = reinterpret_cast<const uint32_t*>(st + S::X_BYTES);
+        unsigned char* arow = st + S::X_BYTES + S::P_BYTES + (row >> 3) * 1024 + (row & 7) * 128;
+#pragma unroll
+        for (int c = 0; c < TC_BK / 8; ++c) {
+          const int g = (kb * TC_BK + c * 8) / P.group_size;
+          if (g != cur_g) {
+            cur_g = g;
+            const int64_t mi = (int64_t)g * P.N + n;
+            const uint16_t sv = reinterpret_cast<const uint16_t*>(P.scales)[mi];
+            const uint16_t zv = (P.mode != 2) ? reinterpret_cast<const uint16_t*>(P.zeros)[mi] : (uint16_t)0;
+            s2 = (uint32_t)sv | ((uint32_t)sv << 16);
+            z2 = (uint32_t)zv | ((uint32_t)zv << 16);
+          }
+          uint32_t q[4];
+          unpack8<BF16>(pk[c * TC_BM + row], q);
+          uint4 o;
+          o.x = dequant2<BF16>(q[0], s2, z2, P.mode);
+          o.y = dequant2<BF16>(q[1], s2, z2, P.mode);
+          o.z = dequant2<BF16>(q[2], s2, z2, P.mode);
+          o.w = dequant2<BF16>(q[3], s2, z2, P.mode);
+          *reinterpret_cast<uint4*>(arow + ((c ^ (row & 7)) << 4)) = o;      // 128B swizzle: chunk ^= row % 8
+        }
+        ptx::fence_proxy_async_smem();    // generic-proxy stores -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&aready[s]);
+        if (++s == S::STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp >= TC_EPI_WARP0) {
+    // ================= epilogue: TMEM -> registers -> global =================
+    const int q4 = warp - TC_EPI_WARP0;                 // TMEM lane quarter (== warp % 4)
+    const int row = q4 * 32 + lane;                     // feature row inside the tile
+    int it = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+      const int tm = t % P.tiles_m, tn = t / P.tiles_m;
+      const int buf = it & 1;
+      const uint32_t bph = (it >> 1) & 1;
+      const int n = tn * TC_BM + row;
+      float bv = 0.f;
+      if (P.bias) bv = BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(P.bias)[n])
+                            : __half2float(reinterpret_cast<const __half*>(P.bias)[n]);
+      ptx::mbar_wait(&tfull[buf], bph);
+      ptx::tc_fence_after_sync();
+#pragma unroll 1
+      for (int c0 = 0; c0 < BT; c0 += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * BT + c0), r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int m = tm * BT + c0 + j;
+          if (m < P.M) {
+            float v = __uint_as_float(r[j]);
+            if (BF16) {
+              if (P.bias) v = __bfloat162float(__float2bfloat16_rn(v)) + bv;
+              reinterpret_cast<__nv_bfloat16*>(P.y)[(int64_t)m * P.N + n] = __float2bfloat16_rn(v);
+            } else {
+              if (P.bias) v = __half2float(__float2half_rn(v)) + bv;
+              reinterpret_cast<__half*>(P.y)[(int64_t)m * P.N + n] = __float2half_rn(v);
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tempty[buf]);
+    }
+  }
+
+  // ---- teardown ----
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  if (warp == 2) ptx::tmem_dealloc(tmem_base, 2 * BT);
+}
+
+// ---------------------------------------------------------------------------------------------- host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, []() {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int make_tmap_2d(CUtensorMap* out, CUtensorMapDataType dt, const void* base, uint64_t inner, uint64_t outer,
+                 uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle sw) {
+  EncodeTiledFn fn = get_encode_fn();
+  GLB_REQUIRE(fn != nullptr, GLB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  GLB_REQUIRE(r == CUDA_SUCCESS, GLB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return GLB_OK;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <bool BF16, int BT>
+int launch_tc(const glb_linear& L, const void* x, void* y, int64_t M, const void* bias, cudaStream_t stream) {
+  using S = TcSmem<BT>;
+  CUtensorMap tx, tw;
+  int rc = make_tmap_2d(&tx, BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, x, (uint64_t)L.K,
+                        (uint64_t)M, (uint64_t)L.K * 2, TC_BK, BT, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc != GLB_OK) return rc;
+  rc = make_tmap_2d(&tw, CU_TENSOR_MAP_DATA_TYPE_INT32, L.W_q, (uint64_t)L.N, (uint64_t)(L.K / 8), (uint64_t)L.N * 4, TC_BM,
+                    TC_BK / 8, CU_TENSOR_MAP_SWIZZLE_NONE);
+  if (rc != GLB_OK) return rc;
+  TcParams P;
+  P.scales = L.scales; P.zeros = (L.W_group_mode == 2) ? nullptr : L.zeros;
+  P.y = y; P.bias = bias; P.M = (int)M; P.N = (int)L.N; P.K = (int)L.K;
+  P.group_size = L.group_size; P.mode = L.W_group_mode;
+  P.tiles_m = (int)((M + BT - 1) / BT); P.tiles_n = (int)(L.N / TC_BM);
+  auto kern = gemm_a16w4_tc_kernel<BF16, BT>;
+  static thread_local bool configured = false;
+  if (!configured) {
+    GLB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    configured = true;
+  }
+  const int grid = std::min(num_sms(), P.tiles_m * P.tiles_n);
+  kern<<<grid, TC_THREADS, S::TOTAL, stream>>>(tx, tw, P);
+  count_launch();
+  GLB_CHECK_CUDA(cudaGetLastError());
+  return GLB_OK;
+}
+
+}  // namespace
+
+bool gemm_tc_supported(const glb_linear& L, int64_t M) {
+  if (M < 1 || M > (1 << 24)) return false;
+  if (!(L.input_dtype == GLB_FP16 || L.input_dtype == GLB_BF16)) return false;
+  if (L.output_dtype != L.input_dtype || L.meta_dtype != L.input_dtype) return false;
+  if (L.W_nbits != 4 || L.elements_per_sample != 8 || L.wq_dtype != GLB_INT32) return false;
+  if (L.wq_stride1 != 1 || L.wq_stride0 != L.N) return false;
+  if (L.channel_scale_mode != 0) return false;
+  if (!(L.W_group_mode == 2 || L.W_group_mode == 3 || L.W_group_mode == 4)) return false;
+  if (L.W_group_mode != 2 && (L.zeros_numel != L.scales_numel || L.zeros_dtype != L.scales_dtype)) return false;
+  if (L.group_size < 8 || L.group_size % 8 != 0 || L.K % L.group_size != 0) return false;
+  if (L.scales_numel != (L.K / L.group_size) * L.N || L.s_stride1 != 1 || L.s_stride0 != L.N) return false;
+  if (L.W_group_mode != 2 && (L.z_stride1 != 1 || L.z_stride0 != L.N)) return false;
+  if (L.N % TC_BM != 0 || L.K % TC_BK != 0) return false;
+  if (reinterpret_cast<uintptr_t>(L.W_q) & 15) return false;
+  return true;
+}
+
+size_t gemm_tc_workspace(const glb_linear&, int64_t) { return 0; }
+
+int launch_gemm_tc(const glb_linear& L, const void* x, const float* scales_x, void* y, int64_t M, void* workspace,
+                   size_t ws_bytes, const void* bias, cudaStream_t stream) {
+  (void)scales_x; (void)workspace; (void)ws_bytes;
+  GLB_REQUIRE(gemm_tc_supported(L, M), GLB_ERR_UNSUPPORTED, "tcgen05 GEMM: unsupported layer configuration");
+  GLB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, GLB_ERR_INVALID, "tcgen05 GEMM: x must be 16-byte aligned");
+  const bool bf = (L.input_dtype == GLB_BF16);
+  set_kernel_name("gemm_a16w4_tcgen05");
+  if (M <= 32) return bf ? launch_tc<true, 32>(L, x, y, M, bias, stream) : launch_tc<false, 32>(L, x, y, M, bias, stream);
+  if (M <= 64) return bf ? launch_tc<true, 64>(L, x, y, M, bias, stream) : launch_tc<false, 64>(L, x, y, M, bias, stream);
+  if (M <= 128) return bf ? launch_tc<true, 128>(L, x, y, M, bias, stream) : launch_tc<false, 128>(L, x, y, M, bias, stream);
+  return bf ? launch_tc<true, 256>(L, x, y, M, bias, stream) : launch_tc<false, 256>(L, x, y, M, bias, stream);
+}
+
 }  // namespace glb

@@ -7,21 +7,22 @@
 // word (r, n) holds codes k = 8r .. 8r+7 of column n in nibbles 0..7; scales / zeros (K/gs, N).
 //
 // Design for B200 (148 SMs, ~6.5 TB/s measured => ~23 B/clk/SM => ~46 four-bit weights/clk/SM):
-//  * one CTA per 32-column slab, full K, 8 warps; a warp-load is 4 packed rows x 128 contiguous
-//    bytes (uint4 per lane, ld.global.nc.L1::no_allocate); every lane issues ALL of its weight
-//    loads (16 x 128-bit for K=4096) before it consumes anything, so the whole slab (64 KB) is in
-//    flight at once -- the bandwidth-delay product of the chip is about the size of the matrix;
-//  * weights do not depend on the previous layer: they are requested BEFORE griddepcontrol.wait,
-//    x (which does) after it => with programmatic dependent launch the next layer's HBM traffic
-//    overlaps this layer's tail;
+//  * a 32-column slab of the weight matrix is owned by a CLUSTER of KSPLIT (1 or 2) CTAs that split
+//    K; partial sums meet in the leader's shared memory through DSMEM (no atomics, no memset,
+//    deterministic). N=4096 => 256 CTAs of 8 warps: two CTAs per SM, every SM busy;
+//  * a warp-load is 4 packed rows x 128 contiguous bytes (uint4 per lane, ld.global.nc no-allocate);
+//    every lane issues ALL its weight loads (8 x 128-bit per batch) and the scale / zero vectors of
+//    its groups before it consumes anything;
+//  * weights and metadata do not depend on the previous layer: they are requested BEFORE
+//    griddepcontrol.wait, x (which does) after it => with programmatic dependent launch the next
+//    layer's HBM traffic overlaps this layer's tail;
 //  * the multiply-accumulate is issue-bound on CUDA cores at this bandwidth (>= 1.9 issue slots per
 //    weight for lop3 + sub + fma + flush), so the dot products run on the tensor pipe instead:
 //    nibbles -> fp16 integers by the 0x6400 magic (1 shift + 4 lop3 per 8 weights), exact
 //    (h - 1024) / (h/16 - 64), then mma.sync.m16n8k16 with fp32 accumulation; the k order inside a
-//    word is permuted consistently on the x side, so no shuffles are needed;
+//    word is permuted consistently on the x side at staging time, so no shuffles are needed;
 //  * per group g:  y += s_g * sum_k x_k q_k  +  z'_g * sum_k x_k   (mode 4; modes 2/3 analogous) --
-//    the group-wise factorisation of sum_k x_k * fma(q_k, s_g, z'_g), applied in fp32;
-//  * deterministic: no atomics, no memset; cross-warp reduction through shared memory; bias fused.
+//    the group-wise factorisation of sum_k x_k * fma(q_k, s_g, z'_g), applied in fp32; bias fused.
 // The same kernel handles 1 <= M <= 16 rows of x (rows of the MMA A operand).
 #include "gl_common.cuh"
 
@@ -30,8 +31,11 @@ namespace {
 
 constexpr int GV_THREADS = 256;
 constexpr int GV_WARPS = 8;
-constexpr int GV_COLS = 32;        // columns per CTA
-constexpr int GV_MAXR = 16;        // packed rows (uint4 loads) a lane keeps in flight per batch
+constexpr int GV_COLS = 32;        // columns per cluster
+constexpr int GV_R = 8;            // uint4 loads a lane keeps in flight per batch
+#ifndef GLB_GEMV_FAST
+#define GLB_GEMV_FAST 0            // 1: offset-carrying nibble unpack (no subtract), fp16 only
+#endif
 
 struct GemvParams {
   const uint32_t* W;     // (K/8, N) int32
@@ -41,9 +45,8 @@ struct GemvParams {
   void* y;               // (M, N)
   const void* bias;      // (N) or null
   int K, N, M;
-  int group_size;        // multiple of 32
+  int group_size;        // 32 * RPG
   int mode;              // 2, 3, 4
-  int rows_total;        // K / 8
 };
 
 template <bool BF16> __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -64,15 +67,19 @@ __device__ __forceinline__ uint32_t lop3_and_or(uint32_t a, uint32_t mask, uint3
   return r;
 }
 
-// 8 nibbles of one word -> 4 registers of exact small integers as fp16x2 / bf16x2.
+// 8 nibbles of one word -> 4 registers of fp16x2 / bf16x2 values.
 // Pairing: h[0] = (k0,k4), h[1] = (k1,k5), h[2] = (k2,k6), h[3] = (k3,k7).
-template <bool BF16> __device__ __forceinline__ void nibbles_to_f16x2(uint32_t q, uint32_t (&h)[4]) {
+//   exact form : the integers n themselves (magic 0x6400 = 1024, then h-1024 resp. h/16-64)
+//   FAST form  : fp16 only -- the raw magic values 1024+n (h[0],h[2]) and 1024+16n (h[1],h[3]); the x side
+//                carries x/16 in the (k1,k5),(k3,k7) slots and 1024*sum(x') is subtracted per group.
+template <bool BF16, bool FAST> __device__ __forceinline__ void nibbles_to_f16x2(uint32_t q, uint32_t (&h)[4]) {
   if (!BF16) {
     const uint32_t t = q >> 8;
     const uint32_t h0 = lop3_and_or(q, 0x000F000Fu, 0x64006400u);   // 1024 + n
     const uint32_t h1 = lop3_and_or(q, 0x00F000F0u, 0x64006400u);   // 1024 + 16 n
     const uint32_t h2 = lop3_and_or(t, 0x000F000Fu, 0x64006400u);
     const uint32_t h3 = lop3_and_or(t, 0x00F000F0u, 0x64006400u);
+    if (FAST) { h[0] = h0; h[1] = h1; h[2] = h2; h[3] = h3; return; }
     const __half2 k1024 = __half2half2(__ushort_as_half((unsigned short)0x6400));
     const __half2 k16th = __half2half2(__ushort_as_half((unsigned short)0x2C00));   // 1/16
     const __half2 km64 = __half2half2(__ushort_as_half((unsigned short)0xD400));    // -64
@@ -94,9 +101,9 @@ template <bool BF16> __device__ __forceinline__ void nibbles_to_f16x2(uint32_t q
   }
 }
 
-template <bool BF16> __device__ __forceinline__ float ld_meta(const void* p, int64_t i) {
-  if (BF16) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
-  return __half2float(reinterpret_cast<const __half*>(p)[i]);
+template <bool BF16> __device__ __forceinline__ float cvt_meta(uint16_t raw) {
+  if (BF16) return __bfloat162float(__ushort_as_bfloat16(raw));
+  return __half2float(__ushort_as_half(raw));
 }
 template <bool BF16> __device__ __forceinline__ void st_out(void* p, int64_t i, float v) {
   if (BF16) reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
@@ -107,179 +114,230 @@ template <bool BF16> __device__ __forceinline__ float rnd_out(float v) {
   return __half2float(__float2half_rn(v));
 }
 
-// Shared memory: xs[MT][K] permuted 16-bit activations | sx[MT][G] fp32 group sums | red[8][MT][32] fp32
-template <bool BF16, int MT>
-__global__ void __launch_bounds__(GV_THREADS) gemv_w4_mma_kernel(const GemvParams P) {
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void st_cluster_f32(float* local_smem_ptr, uint32_t rank, float v) {
+  uint32_t a = (uint32_t)__cvta_generic_to_shared(local_smem_ptr), ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
+}
+
+// Shared memory (per CTA, Kc = K / KSPLIT):
+//   xs[MT][Kc] permuted 16-bit activations | zero[4] (16 B of zeros)
+//   | red[8][MT][32] fp32 per-warp partials | peer[MT][32] fp32 partials of the other cluster rank
+template <bool BF16, int MT, int RPG /*4-row runs per group = gs/32*/, int KSPLIT, bool FAST>
+__global__ void __launch_bounds__(GV_THREADS, 2) gemv_w4_mma_kernel(const GemvParams P) {
+  static_assert(!(BF16 && FAST), "the offset-carrying unpack needs fp16's 10-bit mantissa");
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int K = P.K, N = P.N, G = K / P.group_size;
+  constexpr int GPB = (GV_R / RPG) > 0 ? (GV_R / RPG) : 1;   // groups a warp covers per batch
+  constexpr int RUNS = GPB * RPG;                            // uint4 loads per batch
+  constexpr bool HI = (MT > 8);                              // MMA rows 8..15 carry tokens
+  const int K = P.K, N = P.N;
+  const int G = K / P.group_size;
+  const int Kc = K / KSPLIT, Gc = G / KSPLIT;
+  const uint32_t rank = (KSPLIT > 1) ? cluster_ctarank() : 0u;
+  const int slab = (KSPLIT > 1) ? (blockIdx.x / KSPLIT) : blockIdx.x;
+  const int kbeg = (int)rank * Kc, gbeg = (int)rank * Gc;
+
   uint16_t* xs = reinterpret_cast<uint16_t*>(smem_raw);
-  float* sx = reinterpret_cast<float*>(smem_raw + (size_t)MT * K * 2);
-  float* red = sx + (size_t)MT * G;
+  uint32_t* zero16 = reinterpret_cast<uint32_t*>(smem_raw + (size_t)MT * Kc * 2);
+  float* red = reinterpret_cast<float*>(smem_raw + (size_t)MT * Kc * 2 + 16);
+  float* peer = red + GV_WARPS * MT * GV_COLS;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g8 = lane >> 2, t4 = lane & 3;        // mma lane coordinates
-  const int col0 = blockIdx.x * GV_COLS;
-  const int rpg = P.group_size >> 3;               // packed rows per group (multiple of 4)
-  const int runs_per_group = rpg >> 2;             // 4-row runs per group
+  const int col0 = slab * GV_COLS;
+  constexpr int rpg = RPG * 4;                     // packed rows per group
+  const int nbatches = (Gc + GV_WARPS * GPB - 1) / (GV_WARPS * GPB);
 
-  // ---- work split: warp w owns groups w, w+8, ...; inside a group the warp walks runs of 4 rows;
-  //      lane (g8, t4) loads row (run*4 + t4), columns col0 + 4*g8 .. +3
-  // Issue every weight load of the first batch before anything else.
-  const uint32_t* wbase = P.W + (size_t)col0 + 4 * g8;
-  uint4 q[GV_MAXR];
-  int nq = 0;                       // loads held
-  int grp = warp, run = 0;          // cursor of the next (group, run) to load
-  auto issue_batch = [&]() {
-    nq = 0;
+  // ---- 1. everything that does not depend on the previous kernel: weights + scale/zero vectors ----
+  // lane (g8, t4) loads row (run*4 + t4), columns col0 + 4*g8 .. +3 ; it later owns the outputs of
+  // columns col0 + 8*t4 .. +7 (rows g8, g8+8), whose scales/zeros are one 16-byte vector per group.
+  const uint32_t* wbase = P.W + (size_t)col0 + 4 * g8 + (size_t)t4 * N;
+  const uint16_t* sbase = reinterpret_cast<const uint16_t*>(P.scales) + col0 + 8 * t4;
+  const uint16_t* zbase = reinterpret_cast<const uint16_t*>(P.zeros) + col0 + 8 * t4;
+  uint4 q[RUNS];
+  uint4 sv[GPB], zv[GPB];
+  auto issue = [&](int batch) {
+    const int gl0 = (batch * GV_WARPS + warp) * GPB;           // first group (CTA-local) of this warp in the batch
+    if (gl0 < Gc) {
+      const uint32_t* wp = wbase + (size_t)(gbeg + gl0) * rpg * N;
 #pragma unroll
-    for (int i = 0; i < GV_MAXR; ++i) {
-      if (grp < G) {
-        const int row = grp * rpg + run * 4 + t4;
-        q[i] = ldg_nc_v4(wbase + (size_t)row * N);
-        ++nq;
-        if (++run == runs_per_group) { run = 0; grp += GV_WARPS; }
+      for (int i = 0; i < RUNS; ++i) q[i] = ldg_nc_v4(wp + (size_t)(i * 4) * N);   // consecutive 4-row runs
+#pragma unroll
+      for (int j = 0; j < GPB; ++j) {
+        sv[j] = ldg_nc_v4(sbase + (size_t)(gbeg + gl0 + j) * N);
+        if (P.mode != 2) zv[j] = ldg_nc_v4(zbase + (size_t)(gbeg + gl0 + j) * N);
       }
     }
   };
-  issue_batch();
+  issue(0);
 
-  // ---- x depends on the previous kernel: wait for it only now (PDL), then stage it permuted ----
+  // ---- 2. x depends on the previous kernel: wait for it only now (PDL), then stage it permuted ----
   pdl_wait_prior_grids();
   {
     // word r of row m: source k = 8r + j -> slot order [0,4,1,5,2,6,3,7] so that an LDS.128 yields
     // {(k0,k4), (k1,k5), (k2,k6), (k3,k7)} = the A-fragment pairs matching nibbles_to_f16x2
-    const uint16_t* xg = reinterpret_cast<const uint16_t*>(P.x);
-    const int words = K >> 3;
+    const uint16_t* xg = reinterpret_cast<const uint16_t*>(P.x) + kbeg;
+    const int words = Kc >> 3;
     for (int i = threadIdx.x; i < MT * words; i += GV_THREADS) {
-      const int m = i / words, r = i - m * words;
+      const int m = (MT == 1) ? 0 : (i / words), r = (MT == 1) ? i : (i - m * words);
       uint4 o = make_uint4(0u, 0u, 0u, 0u);
       if (m < P.M) {
         const uint4 v = *reinterpret_cast<const uint4*>(xg + (size_t)m * K + (size_t)r * 8);
-        // v.x = (k0,k1) v.y = (k2,k3) v.z = (k4,k5) v.w = (k6,k7)
         o.x = __byte_perm(v.x, v.z, 0x5410);   // (k0,k4)
         o.y = __byte_perm(v.x, v.z, 0x7632);   // (k1,k5)
         o.z = __byte_perm(v.y, v.w, 0x5410);   // (k2,k6)
         o.w = __byte_perm(v.y, v.w, 0x7632);   // (k3,k7)
+        if (FAST) {                            // the 1024+16n slots see x/16 (exact unless subnormal)
+          const __half2 k16th = __half2half2(__ushort_as_half((unsigned short)0x2C00));
+          __half2 a = __hmul2(*reinterpret_cast<__half2*>(&o.y), k16th), b = __hmul2(*reinterpret_cast<__half2*>(&o.w), k16th);
+          o.y = *reinterpret_cast<uint32_t*>(&a); o.w = *reinterpret_cast<uint32_t*>(&b);
+        }
       }
-      *reinterpret_cast<uint4*>(xs + (size_t)m * K + (size_t)r * 8) = o;
+      *reinterpret_cast<uint4*>(xs + (size_t)m * Kc + (size_t)r * 8) = o;
     }
+    if (threadIdx.x < 4) zero16[threadIdx.x] = 0u;
   }
   __syncthreads();
-  if (P.mode != 2) {   // group sums of x (fp32) for the zero-point term
-    for (int i = warp; i < MT * G; i += GV_WARPS) {
-      const int m = i / G, g = i - m * G;
-      float s = 0.f;
-      for (int k = lane; k < P.group_size; k += 32) {
-        const uint16_t raw = xs[(size_t)m * K + (size_t)g * P.group_size + k];
-        s += BF16 ? __bfloat162float(__ushort_as_bfloat16(raw)) : __half2float(__ushort_as_half(raw));
-      }
-      s = warp_sum(s);
-      if (lane == 0) sx[i] = s;
-    }
-    __syncthreads();
-  }
   pdl_launch_dependents();
 
-  // ---- main loop ----
-  // out[c][0..3]: D fragment of column set c (columns col0 + 4*n' + c, n' = mma n index)
+  // ---- 3. main loop ----
+  // out[c][0..3]: rows (g8, g8+8) x columns col0 + 8*t4 + c (regs 0,2) and col0 + 8*t4 + 4 + c (regs 1,3)
   float out[4][4];
 #pragma unroll
   for (int c = 0; c < 4; ++c) { out[c][0] = out[c][1] = out[c][2] = out[c][3] = 0.f; }
-  float dacc[4][4];
-#pragma unroll
-  for (int c = 0; c < 4; ++c) { dacc[c][0] = dacc[c][1] = dacc[c][2] = dacc[c][3] = 0.f; }
+  const bool a_lo = (g8 < MT), a_hi = HI && (g8 + 8 < MT);
+  // A-fragment source: this lane's x row; lanes whose MMA row does not exist read 16 bytes of zeros (stride 0)
+  const unsigned char* xa_lo = a_lo ? reinterpret_cast<const unsigned char*>(xs + (size_t)g8 * Kc) + t4 * 16
+                                    : reinterpret_cast<const unsigned char*>(zero16);
+  const unsigned char* xa_hi = a_hi ? reinterpret_cast<const unsigned char*>(xs + (size_t)(g8 + 8) * Kc) + t4 * 16
+                                    : reinterpret_cast<const unsigned char*>(zero16);
+  const int st_lo = a_lo ? 64 : 0, st_hi = a_hi ? 64 : 0;      // bytes per 4-row run
+  // "ones" B fragment: one extra MMA per A fragment yields the group sums of x in the accumulator layout:
+  //   even n' : sum_k x_k            (slots carrying x/16 are weighted by 16 in FAST mode)
+  //   odd  n' : sum_k x'_k           (FAST only: what the 1024 offset multiplies)
+  const uint32_t one2 = BF16 ? 0x3F803F80u : 0x3C003C00u;
+  const uint32_t ones_b0 = one2;
+  const uint32_t ones_b1 = (FAST && !(g8 & 1)) ? 0x4C004C00u /* (16,16) */ : one2;
 
-  int cgrp = warp, crun = 0;        // cursor of the (group, run) being consumed
-  const bool a_lo = (g8 < MT), a_hi = (g8 + 8 < MT);
-  while (nq > 0) {
+  for (int batch = 0; batch < nbatches; ++batch) {
+    const int gl0 = (batch * GV_WARPS + warp) * GPB;
+    if (gl0 < Gc) {
 #pragma unroll
-    for (int i = 0; i < GV_MAXR; ++i) {
-      if (i < nq) {
-        const int row = cgrp * rpg + crun * 4 + t4;
-        // A fragments: rows g8 / g8+8 of x, k-slots of packed row `row`
-        uint32_t a1[4] = {0u, 0u, 0u, 0u}, a2[4] = {0u, 0u, 0u, 0u};
-        if (a_lo) {
-          const uint4 v = *reinterpret_cast<const uint4*>(xs + (size_t)g8 * K + (size_t)row * 8);
-          a1[0] = v.x; a1[2] = v.y; a2[0] = v.z; a2[2] = v.w;
+      for (int j = 0; j < GPB; ++j) {
+        float dacc[4][4], dsum[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { dacc[c][0] = dacc[c][1] = dacc[c][2] = dacc[c][3] = 0.f; }
+        dsum[0] = dsum[1] = dsum[2] = dsum[3] = 0.f;
+#pragma unroll
+        for (int r = 0; r < RPG; ++r) {
+          const int i = j * RPG + r;
+          const int run = (gl0 + j) * RPG + r;                           // 4-row run inside this CTA's K range
+          const uint4 vlo = *reinterpret_cast<const uint4*>(xa_lo + (size_t)run * st_lo);
+          uint4 vhi = make_uint4(0u, 0u, 0u, 0u);
+          if (HI) vhi = *reinterpret_cast<const uint4*>(xa_hi + (size_t)run * st_hi);
+          const uint32_t a1[4] = {vlo.x, vhi.x, vlo.y, vhi.y};
+          const uint32_t a2[4] = {vlo.z, vhi.z, vlo.w, vhi.w};
+          const uint32_t w4[4] = {q[i].x, q[i].y, q[i].z, q[i].w};
+          uint32_t h[4][4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) nibbles_to_f16x2<BF16, FAST>(w4[c], h[c]);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) mma16816<BF16>(dacc[c], a1, h[c][0], h[c][1]);
+          mma16816<BF16>(dsum, a1, ones_b0, ones_b1);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) mma16816<BF16>(dacc[c], a2, h[c][2], h[c][3]);
+          mma16816<BF16>(dsum, a2, ones_b0, ones_b1);
         }
-        if (MT > 8 && a_hi) {
-          const uint4 v = *reinterpret_cast<const uint4*>(xs + (size_t)(g8 + 8) * K + (size_t)row * 8);
-          a1[1] = v.x; a1[3] = v.y; a2[1] = v.z; a2[3] = v.w;
-        }
-        const uint32_t w4[4] = {q[i].x, q[i].y, q[i].z, q[i].w};
+        // ---- end of group: y += s * sum(x q) + z' * sum(x), z' = zeros (mode 4) | -zeros*s (mode 3) | 0 (mode 2)
+        // dsum[0] / [2]: even n' -> sum x (rows g8 / g8+8); dsum[1] / [3]: odd n' -> sum x' (FAST) else sum x
+        const float sx_lo = dsum[0], sx_hi = dsum[2];
+        const float off_lo = FAST ? 1024.f * dsum[1] : 0.f, off_hi = FAST ? 1024.f * dsum[3] : 0.f;
+        const uint32_t sw[4] = {sv[j].x, sv[j].y, sv[j].z, sv[j].w};
+        const uint32_t zw[4] = {zv[j].x, zv[j].y, zv[j].z, zv[j].w};
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          uint32_t h[4];
-          nibbles_to_f16x2<BF16>(w4[c], h);
-          mma16816<BF16>(dacc[c], a1, h[0], h[1]);
-          mma16816<BF16>(dacc[c], a2, h[2], h[3]);
-        }
-        if (++crun == runs_per_group) {
-          // ---- end of group: apply scale / zero in fp32 ----
-          // this lane holds rows (g8, g8+8) x n' = (2*t4, 2*t4+1) -> columns col0 + 8*t4 + {0..7}
-          const int64_t mo = (int64_t)cgrp * N + col0 + 8 * t4;
-          float sc[8], zc[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            sc[j] = ld_meta<BF16>(P.scales, mo + j);
-            zc[j] = (P.mode != 2) ? ld_meta<BF16>(P.zeros, mo + j) : 0.f;
+          // column 8*t4 + c -> element c of the vector ; column 8*t4 + 4 + c -> element 4 + c
+          const float s0 = cvt_meta<BF16>((uint16_t)((c & 1) ? (sw[c >> 1] >> 16) : (sw[c >> 1] & 0xffffu)));
+          const float s1 = cvt_meta<BF16>((uint16_t)((c & 1) ? (sw[2 + (c >> 1)] >> 16) : (sw[2 + (c >> 1)] & 0xffffu)));
+          float z0 = 0.f, z1 = 0.f;
+          if (P.mode != 2) {
+            z0 = cvt_meta<BF16>((uint16_t)((c & 1) ? (zw[c >> 1] >> 16) : (zw[c >> 1] & 0xffffu)));
+            z1 = cvt_meta<BF16>((uint16_t)((c & 1) ? (zw[2 + (c >> 1)] >> 16) : (zw[2 + (c >> 1)] & 0xffffu)));
+            if (P.mode == 3) { z0 = -z0 * s0; z1 = -z1 * s1; }
           }
-          const float sx_lo = (P.mode != 2 && a_lo) ? sx[g8 * G + cgrp] : 0.f;
-          const float sx_hi = (P.mode != 2 && MT > 8 && a_hi) ? sx[(g8 + 8) * G + cgrp] : 0.f;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            // dacc[c][0]: (row g8, n'=2t4) -> column 8*t4 + c ; [1]: n'=2t4+1 -> column 8*t4 + 4 + c
-            const float s0 = sc[c], s1 = sc[4 + c], z0 = zc[c], z1 = zc[4 + c];
-            if (P.mode == 4) {
-              out[c][0] += s0 * dacc[c][0] + z0 * sx_lo;  out[c][1] += s1 * dacc[c][1] + z1 * sx_lo;
-              out[c][2] += s0 * dacc[c][2] + z0 * sx_hi;  out[c][3] += s1 * dacc[c][3] + z1 * sx_hi;
-            } else if (P.mode == 3) {
-              out[c][0] += s0 * (dacc[c][0] - z0 * sx_lo);  out[c][1] += s1 * (dacc[c][1] - z1 * sx_lo);
-              out[c][2] += s0 * (dacc[c][2] - z0 * sx_hi);  out[c][3] += s1 * (dacc[c][3] - z1 * sx_hi);
-            } else {
-              out[c][0] += s0 * dacc[c][0];  out[c][1] += s1 * dacc[c][1];
-              out[c][2] += s0 * dacc[c][2];  out[c][3] += s1 * dacc[c][3];
-            }
-            dacc[c][0] = dacc[c][1] = dacc[c][2] = dacc[c][3] = 0.f;
+          out[c][0] = fmaf(s0, dacc[c][0] - off_lo, fmaf(z0, sx_lo, out[c][0]));
+          out[c][1] = fmaf(s1, dacc[c][1] - off_lo, fmaf(z1, sx_lo, out[c][1]));
+          if (HI) {
+            out[c][2] = fmaf(s0, dacc[c][2] - off_hi, fmaf(z0, sx_hi, out[c][2]));
+            out[c][3] = fmaf(s1, dacc[c][3] - off_hi, fmaf(z1, sx_hi, out[c][3]));
           }
-          crun = 0; cgrp += GV_WARPS;
         }
       }
     }
-    issue_batch();   // K larger than one batch: next set of loads
+    if (batch + 1 < nbatches) issue(batch + 1);
   }
 
-  // ---- cross-warp reduction + epilogue ----
-  // red[warp][m][col]: lane writes rows g8 (+8), columns 8*t4 + c and 8*t4 + 4 + c
+  // ---- 4. cross-warp reduction, cluster (split-K) reduction through DSMEM, epilogue ----
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
-    if (g8 < MT) {
+    if (a_lo) {
       red[(warp * MT + g8) * GV_COLS + 8 * t4 + c] = out[c][0];
       red[(warp * MT + g8) * GV_COLS + 8 * t4 + 4 + c] = out[c][1];
     }
-    if (MT > 8 && g8 + 8 < MT) {
+    if (a_hi) {
       red[(warp * MT + g8 + 8) * GV_COLS + 8 * t4 + c] = out[c][2];
       red[(warp * MT + g8 + 8) * GV_COLS + 8 * t4 + 4 + c] = out[c][3];
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < MT * GV_COLS; i += GV_THREADS) {
-    const int m = i / GV_COLS, c = i - m * GV_COLS;
-    if (m < P.M && col0 + c < N) {
-      float v = 0.f;
+  float part[(MT * GV_COLS + GV_THREADS - 1) / GV_THREADS];
+#pragma unroll
+  for (int u = 0; u < (MT * GV_COLS + GV_THREADS - 1) / GV_THREADS; ++u) {
+    const int i = u * GV_THREADS + threadIdx.x;
+    float v = 0.f;
+    if (i < MT * GV_COLS) {
+      const int m = i / GV_COLS, c = i - m * GV_COLS;
 #pragma unroll
       for (int w = 0; w < GV_WARPS; ++w) v += red[(w * MT + m) * GV_COLS + c];
-      if (P.bias) v = rnd_out<BF16>(v) + ld_meta<BF16>(P.bias, col0 + c);
-      st_out<BF16>(P.y, (int64_t)m * N + col0 + c, v);
+      if (KSPLIT > 1 && rank != 0) st_cluster_f32(&peer[i], 0u, v);
+    }
+    part[u] = v;
+  }
+  if (KSPLIT > 1) cluster_sync_all();
+  if (rank == 0) {
+#pragma unroll
+    for (int u = 0; u < (MT * GV_COLS + GV_THREADS - 1) / GV_THREADS; ++u) {
+      const int i = u * GV_THREADS + threadIdx.x;
+      if (i < MT * GV_COLS) {
+        const int m = i / GV_COLS, c = i - m * GV_COLS;
+        if (m < P.M) {
+          float v = part[u];
+          if (KSPLIT > 1) v += peer[i];
+          if (P.bias) v = rnd_out<BF16>(v) + cvt_meta<BF16>(reinterpret_cast<const uint16_t*>(P.bias)[col0 + c]);
+          st_out<BF16>(P.y, (int64_t)m * N + col0 + c, v);
+        }
+      }
     }
   }
 }
 
-template <bool BF16, int MT>
+template <int MT, int KSPLIT> size_t gemv_smem_bytes(int K) {
+  const int Kc = K / KSPLIT;
+  return (size_t)MT * Kc * 2 + 16 + (size_t)GV_WARPS * MT * GV_COLS * 4 + (size_t)MT * GV_COLS * 4;
+}
+
+template <bool BF16, int MT, int RPG, int KSPLIT, bool FAST>
 int launch_w4(const GemvParams& P, cudaStream_t stream) {
-  const int G = P.K / P.group_size;
-  const size_t smem = (size_t)MT * P.K * 2 + (size_t)MT * G * 4 + (size_t)GV_WARPS * MT * GV_COLS * 4;
-  auto kern = gemv_w4_mma_kernel<BF16, MT>;
+  const size_t smem = gemv_smem_bytes<MT, KSPLIT>(P.K);
+  auto kern = gemv_w4_mma_kernel<BF16, MT, RPG, KSPLIT, FAST>;
   if (smem > 48 * 1024) {
     static thread_local size_t configured = 0;
     if (configured < smem) {
@@ -288,18 +346,51 @@ int launch_w4(const GemvParams& P, cudaStream_t stream) {
     }
   }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(P.N / GV_COLS));
+  cfg.gridDim = dim3((unsigned)(P.N / GV_COLS) * KSPLIT);
   cfg.blockDim = dim3(GV_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (KSPLIT > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = KSPLIT; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (g_pdl_enabled.load()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = g_pdl_enabled.load() ? 1 : 0;
+  cfg.numAttrs = na;
   GLB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, P));
   count_launch();
   return GLB_OK;
+}
+
+template <bool BF16, int MT>
+int dispatch_w4(const GemvParams& P, cudaStream_t stream) {
+  const int G = P.K / P.group_size;
+  const int rpgi = P.group_size / 32;
+  // split K over a 2-CTA cluster when that still leaves whole groups per warp-batch
+#define GLB_GV(RPG)                                                                                   \
+  {                                                                                                   \
+    constexpr int GPB = (GV_R / RPG) > 0 ? (GV_R / RPG) : 1;                                          \
+    constexpr bool F = !BF16 && GLB_GEMV_FAST;                                                        \
+    if (G % (2 * GPB) == 0 && P.N / GV_COLS < 296) return launch_w4<BF16, MT, RPG, 2, F>(P, stream);  \
+    return launch_w4<BF16, MT, RPG, 1, F>(P, stream);                                                 \
+  }
+  switch (rpgi) {
+    case 1: GLB_GV(1)
+    case 2: GLB_GV(2)
+    case 4: GLB_GV(4)
+    case 8: GLB_GV(8)
+    default: break;
+  }
+#undef GLB_GV
+  set_error("decode kernel: unsupported group_size %d", P.group_size);
+  return GLB_ERR_UNSUPPORTED;
 }
 
 }  // namespace
@@ -314,13 +405,17 @@ bool gemv_supported(const glb_linear& L, int64_t M) {
   if (L.channel_scale_mode != 0) return false;
   if (!(L.W_group_mode == 2 || L.W_group_mode == 3 || L.W_group_mode == 4)) return false;
   if (L.W_group_mode != 2 && (L.zeros_numel != L.scales_numel || L.zeros_dtype != L.scales_dtype)) return false;
-  if (L.group_size < 32 || L.group_size % 32 != 0 || L.K % L.group_size != 0) return false;
-  if (L.scales_numel != (L.K / L.group_size) * L.N || L.s_stride1 != 1 || L.s_stride0 != L.N) return false;
+  const int gs = L.group_size;
+  if (!(gs == 32 || gs == 64 || gs == 128 || gs == 256) || L.K % gs != 0) return false;
+  const int rpg = gs / 32, gpb = (GV_R / rpg) > 0 ? (GV_R / rpg) : 1;
+  if ((L.K / gs) % gpb != 0) return false;
+  if (L.scales_numel != (L.K / gs) * L.N || L.s_stride1 != 1 || L.s_stride0 != L.N) return false;
   if (L.W_group_mode != 2 && (L.z_stride1 != 1 || L.z_stride0 != L.N)) return false;
   if (L.N % GV_COLS != 0 || L.K % 8 != 0) return false;
-  if ((reinterpret_cast<uintptr_t>(L.W_q) & 15) || (reinterpret_cast<uintptr_t>(L.scales) & 1)) return false;
+  if ((reinterpret_cast<uintptr_t>(L.W_q) & 15) || (reinterpret_cast<uintptr_t>(L.scales) & 15)) return false;
+  if (L.W_group_mode != 2 && (reinterpret_cast<uintptr_t>(L.zeros) & 15)) return false;
   const int mt = (M == 1) ? 1 : (M <= 8 ? 8 : 16);
-  const size_t smem = (size_t)mt * L.K * 2 + (size_t)mt * (L.K / L.group_size) * 4 + (size_t)GV_WARPS * mt * GV_COLS * 4;
+  const size_t smem = (size_t)mt * L.K * 2 + (size_t)mt * (L.K / gs) * 4 + (size_t)(GV_WARPS + 1) * mt * GV_COLS * 4 + 16;
   if (smem > 200 * 1024) return false;
   return true;
 }
@@ -335,12 +430,12 @@ int launch_gemv(const glb_linear& L, const void* x, const float* scales_x, void*
   P.scales = L.scales; P.zeros = (L.W_group_mode == 2) ? nullptr : L.zeros;
   P.x = x; P.y = y; P.bias = bias;
   P.K = (int)L.K; P.N = (int)L.N; P.M = (int)M;
-  P.group_size = L.group_size; P.mode = L.W_group_mode; P.rows_total = (int)(L.K / 8);
+  P.group_size = L.group_size; P.mode = L.W_group_mode;
   const bool bf = (L.input_dtype == GLB_BF16);
   set_kernel_name("gemv_w4_mma");
-  if (M == 1) return bf ? launch_w4<true, 1>(P, stream) : launch_w4<false, 1>(P, stream);
-  if (M <= 8) return bf ? launch_w4<true, 8>(P, stream) : launch_w4<false, 8>(P, stream);
-  return bf ? launch_w4<true, 16>(P, stream) : launch_w4<false, 16>(P, stream);
+  if (M == 1) return bf ? dispatch_w4<true, 1>(P, stream) : dispatch_w4<false, 1>(P, stream);
+  if (M <= 8) return bf ? dispatch_w4<true, 8>(P, stream) : dispatch_w4<false, 8>(P, stream);
+  return bf ? dispatch_w4<true, 16>(P, stream) : dispatch_w4<false, 16>(P, stream);
 }
 
 }  // namespace glb

@@ -56,6 +56,7 @@ struct GenParams {
   const void* bias;
   int64_t M;
   int act_dtype;     // storage dtype of x
+  int out_dtype;     // storage dtype of y (MX tags resolved)
 };
 
 __device__ __forceinline__ float load_act(const void* x, int dt, int64_t i) {
@@ -246,20 +247,20 @@ __global__ void __launch_bounds__(GEN_COLS) generic_kernel(const GenParams P) {
       out = __fmul_rn(a_m, __fmul_rn(sa, sb));
     }
     const int64_t oi = (m0 + r) * L.N + n;
-    if (INT_ACC && csm == 0 && KIND != 2 && L.output_dtype == GLB_INT32 && !P.bias) {
+    if (INT_ACC && csm == 0 && KIND != 2 && P.out_dtype == GLB_INT32 && !P.bias) {
       reinterpret_cast<int32_t*>(P.y)[oi] = acci[r];   // raw accumulator, exact
       continue;
     }
     if (P.bias) {
       float b;
-      switch (L.output_dtype) {
+      switch (P.out_dtype) {
         case GLB_FP16: b = __half2float(reinterpret_cast<const __half*>(P.bias)[n]); break;
         case GLB_BF16: b = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(P.bias)[n]); break;
         default: b = reinterpret_cast<const float*>(P.bias)[n]; break;
       }
-      out = __fadd_rn(round_out(out, L.output_dtype), b);
+      out = __fadd_rn(round_out(out, P.out_dtype), b);
     }
-    store_out(P.y, L.output_dtype, oi, out);
+    store_out(P.y, P.out_dtype, oi, out);
   }
 }
 
@@ -270,6 +271,7 @@ int launch_generic(const glb_linear& L, const void* x, const float* scales_x, vo
   GenParams P;
   P.L = L; P.x = x; P.scales_x = scales_x; P.y = y; P.bias = bias; P.M = M;
   P.act_dtype = act_storage_dtype(L.input_dtype);
+  P.out_dtype = act_storage_dtype(L.output_dtype);
   if (L.zeros_numel == 1)
     GLB_REQUIRE(L.zeros_dtype == GLB_INT32, GLB_ERR_UNSUPPORTED, "scalar zero-point must be int32");
   const bool mx = is_mx(L.input_dtype);
