@@ -10,8 +10,8 @@
 //     accumulator D[feature, token] lives in TMEM (128 lanes x BT fp32 columns, double buffered).
 //     Per FLOP this needs half the dequant work of the transposed mapping and lets BT shrink to 32/64
 //     for small batches without wasting the dequant/HBM pipeline.
-//   * warp roles (384 threads): w0 TMA producer, w1 MMA issuer (one elected lane), w2 TMEM allocator,
-//     w4-7 dequant (thread = one feature row), w8-11 epilogue (TMEM -> registers -> global).
+//   * warp roles (512 threads): w0 TMA producer, w1 MMA issuer (one elected lane), w2 TMEM allocator,
+//     w4-11 dequant (two threads per feature row), w12-15 epilogue (TMEM -> registers -> global).
 //   * per 64-wide k-block and stage s: TMA brings the token tile x[BT,64] (128B-swizzled, K-major)
 //     and the packed weight tile Wq[8 words,128 features] (4 KB) into shared memory; dequant warps
 //     turn the 4 KB into a 16 KB fp16/bf16 K-major SW128 tile (conflict-free 128-bit stores);
@@ -29,9 +29,10 @@ namespace {
 
 constexpr int TC_BM = 128;            // features per tile (UMMA M)
 constexpr int TC_BK = 64;             // k per stage (128 bytes of fp16 -> one swizzle atom row)
-constexpr int TC_THREADS = 384;
-constexpr int TC_DEQ_WARP0 = 4;       // warps 4..7
-constexpr int TC_EPI_WARP0 = 8;       // warps 8..11
+constexpr int TC_THREADS = 512;
+constexpr int TC_DEQ_WARP0 = 4;       // warps 4..11 (two threads per feature row, 4 words each)
+constexpr int TC_DEQ_WARPS = 8;
+constexpr int TC_EPI_WARP0 = 12;      // warps 12..15 (warp % 4 == TMEM lane quarter)
 
 struct TcParams {
   const void* scales;     // (G, N)
@@ -129,7 +130,7 @@ gemm_a16w4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     ptx::prefetch_tmap(&tmap_w);
     for (int s = 0; s < S::STAGES; ++s) {
       ptx::mbar_init(&full[s], 1);
-      ptx::mbar_init(&aready[s], 4);     // one arrival per dequant warp
+      ptx::mbar_init(&aready[s], TC_DEQ_WARPS);     // one arrival per dequant warp
       ptx::mbar_init(&empty[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -189,38 +190,59 @@ gemm_a16w4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         if (++s == S::STAGES) { s = 0; ph ^= 1; }
       }
     }
-  } else if (warp >= TC_DEQ_WARP0 && warp < TC_DEQ_WARP0 + 4) {
-    // ================= dequant: thread = feature row =================
-    const int row = threadIdx.x - TC_DEQ_WARP0 * 32;     // 0..127
+  } else if (warp >= TC_DEQ_WARP0 && warp < TC_DEQ_WARP0 + TC_DEQ_WARPS) {
+    // ================= dequant: two threads per feature row, 4 packed words (32 k) each =================
+    const int dt = threadIdx.x - TC_DEQ_WARP0 * 32;      // 0..255
+    const int row = dt & (TC_BM - 1);                    // feature row inside the tile
+    const int half = dt >> 7;                            // which 32-k half of the 64-k block
+    const uint16_t* sc_g = reinterpret_cast<const uint16_t*>(P.scales);
+    const uint16_t* zr_g = reinterpret_cast<const uint16_t*>(P.zeros);
     int s = 0; uint32_t ph = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
       const int tn = t / P.tiles_m;
       const int n = tn * TC_BM + row;
-      int cur_g = -1;
-      uint32_t s2 = 0, z2 = 0;
+      int cur_g = -1, pre_g = -1;
+      uint32_t s2 = 0, z2 = 0, ps2 = 0, pz2 = 0;
+      auto fetch = [&](int g, uint32_t& S2, uint32_t& Z2) {   // scale / zero of (group g, feature n), duplicated into a pair
+        const int64_t mi = (int64_t)g * P.N + n;
+        const uint32_t sv = sc_g[mi];
+        const uint32_t zv = (P.mode != 2) ? (uint32_t)zr_g[mi] : 0u;
+        S2 = sv | (sv << 16);
+        Z2 = zv | (zv << 16);
+      };
       for (int kb = 0; kb < kblocks; ++kb) {
+        const int k0 = kb * TC_BK + half * 32;
+        const int g = k0 / P.group_size;
+        if (g != cur_g) {
+          if (g == pre_g) { s2 = ps2; z2 = pz2; } else fetch(g, s2, z2);
+          cur_g = g;
+        }
+        if (kb + 1 < kblocks) {                            // prefetch the next block's metadata before blocking
+          const int gn = (k0 + TC_BK) / P.group_size;
+          if (gn != cur_g && gn != pre_g) { fetch(gn, ps2, pz2); pre_g = gn; }
+        }
         ptx::mbar_wait(&full[s], ph);
         unsigned char* st = stage_base + s * S::STAGE;
         const uint32_t* pk = reinterpret_cast<const uint32_t*>(st + S::X_BYTES);
         unsigned char* arow = st + S::X_BYTES + S::P_BYTES + (row >> 3) * 1024 + (row & 7) * 128;
+        uint32_t w[4];
 #pragma unroll
-        for (int c = 0; c < TC_BK / 8; ++c) {
-          const int g = (kb * TC_BK + c * 8) / P.group_size;
-          if (g != cur_g) {
-            cur_g = g;
-            const int64_t mi = (int64_t)g * P.N + n;
-            const uint16_t sv = reinterpret_cast<const uint16_t*>(P.scales)[mi];
-            const uint16_t zv = (P.mode != 2) ? reinterpret_cast<const uint16_t*>(P.zeros)[mi] : (uint16_t)0;
-            s2 = (uint32_t)sv | ((uint32_t)sv << 16);
-            z2 = (uint32_t)zv | ((uint32_t)zv << 16);
+        for (int cc = 0; cc < 4; ++cc) w[cc] = pk[(half * 4 + cc) * TC_BM + row];
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          const int c = half * 4 + cc;
+          uint32_t ls2 = s2, lz2 = z2;
+          if (P.group_size < 32) {                         // a 32-k span may cross groups only for gs = 8 / 16 / 24
+            const int gg = (k0 + cc * 8) / P.group_size;
+            if (gg != cur_g) fetch(gg, ls2, lz2);
           }
           uint32_t q[4];
-          unpack8<BF16>(pk[c * TC_BM + row], q);
+          unpack8<BF16>(w[cc], q);
           uint4 o;
-          o.x = dequant2<BF16>(q[0], s2, z2, P.mode);
-          o.y = dequant2<BF16>(q[1], s2, z2, P.mode);
-          o.z = dequant2<BF16>(q[2], s2, z2, P.mode);
-          o.w = dequant2<BF16>(q[3], s2, z2, P.mode);
+          o.x = dequant2<BF16>(q[0], ls2, lz2, P.mode);
+          o.y = dequant2<BF16>(q[1], ls2, lz2, P.mode);
+          o.z = dequant2<BF16>(q[2], ls2, lz2, P.mode);
+          o.w = dequant2<BF16>(q[3], ls2, lz2, P.mode);
           *reinterpret_cast<uint4*>(arow + ((c ^ (row & 7)) << 4)) = o;      // 128B swizzle: chunk ^= row % 8
         }
         ptx::fence_proxy_async_smem();    // generic-proxy stores -> visible to the tensor core (async proxy)
@@ -271,6 +293,171 @@ gemm_a16w4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
   }
 
   // ---- teardown ----
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  if (warp == 2) ptx::tmem_dealloc(tmem_base, 2 * BT);
+}
+
+
+// =================================================================================================
+// A8W8: 8-bit activations x 8-bit weights, no dequant (W_group_mode 0) -- rows a9/a10 for config C4.
+// Both operands are K-major byte matrices and go straight from TMA (128B swizzle) to the tensor core:
+//   int8 x int8 -> int32 (kind::i8, exact)   |   fp8 x fp8 -> fp32 (kind::f8f6f4)
+// Epilogue = the reference's channel-scale modes (gemm_kernels.py:392-406) with fp32 metadata:
+//   out = float(acc) * (scales_x[m] * scales_w[n])   (mode 3; modes 0/1/2 analogous), then bias.
+// =================================================================================================
+constexpr int T8_BK = 128;            // bytes == elements per stage row
+constexpr int T8_THREADS = 256;       // w0 TMA, w1 MMA, w2 TMEM alloc, w4-7 epilogue
+
+struct T8Params {
+  const float* scales_w;   // (N) or null
+  const float* scales_x;   // (M) or null
+  void* y;
+  const void* bias;
+  int M, N, K;
+  int csm;                 // channel_scale_mode 0..3
+  int out_dtype;           // GLB_FP16 / BF16 / FP32 / INT32
+  int tiles_m, tiles_n;
+};
+
+template <int BT> struct T8Smem {
+  static constexpr int X_BYTES = BT * T8_BK;
+  static constexpr int W_BYTES = TC_BM * T8_BK;
+  static constexpr int STAGE = X_BYTES + W_BYTES;
+  static constexpr int STAGES = (BT >= 256) ? 4 : ((BT >= 128) ? 6 : 8);
+  static constexpr int TOTAL = STAGES * STAGE + 1024 + 1024;
+};
+
+template <bool IS_INT, int BT>
+__global__ void __launch_bounds__(T8_THREADS, 1)
+gemm_a8w8_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const T8Params P,
+                    const uint32_t idesc) {
+  using S = T8Smem<BT>;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::STAGES * S::STAGE);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + S::STAGES;
+  uint64_t* tfull = bars + 2 * S::STAGES;
+  uint64_t* tempty = bars + 2 * S::STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S::STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kblocks = P.K / T8_BK;
+  const int ntiles = P.tiles_m * P.tiles_n;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_x);
+    ptx::prefetch_tmap(&tmap_w);
+    for (int s = 0; s < S::STAGES; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { ptx::mbar_init(&tfull[b], 1); ptx::mbar_init(&tempty[b], 4); }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) ptx::tmem_alloc(tmem_slot, 2 * BT);
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int tm = t % P.tiles_m, tn = t / P.tiles_m;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          ptx::mbar_wait(&empty[s], ph ^ 1);
+          unsigned char* st = smem + s * S::STAGE;
+          ptx::mbar_arrive_expect_tx(&full[s], S::X_BYTES + S::W_BYTES);
+          ptx::tma_load_2d(st, &tmap_x, &full[s], kb * T8_BK, tm * BT);
+          ptx::tma_load_2d(st + S::X_BYTES, &tmap_w, &full[s], kb * T8_BK, tn * TC_BM);
+          if (++s == S::STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    int s = 0; uint32_t ph = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t bph = (it >> 1) & 1;
+      ptx::mbar_wait(&tempty[buf], bph ^ 1);
+      ptx::tc_fence_after_sync();
+      const uint32_t d_tmem = tmem_base + buf * BT;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        ptx::mbar_wait(&full[s], ph);
+        ptx::tc_fence_after_sync();
+        if (ptx::elect_one()) {
+          unsigned char* st = smem + s * S::STAGE;
+          const uint64_t bdesc = ptx::make_sw128_kmajor_desc(ptx::smem_u32(st));
+          const uint64_t adesc = ptx::make_sw128_kmajor_desc(ptx::smem_u32(st + S::X_BYTES));
+#pragma unroll
+          for (int k = 0; k < T8_BK / 32; ++k) {     // K = 32 bytes per instruction
+            if (IS_INT) ptx::mma_i8_ss(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+            else ptx::mma_f8_ss(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+          }
+          ptx::mma_commit(&empty[s]);
+          if (kb == kblocks - 1) ptx::mma_commit(&tfull[buf]);
+        }
+        __syncwarp();
+        if (++s == S::STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    const int q4 = warp - 4;
+    const int row = q4 * 32 + lane;
+    int it = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+      const int tm = t % P.tiles_m, tn = t / P.tiles_m;
+      const int buf = it & 1;
+      const uint32_t bph = (it >> 1) & 1;
+      const int n = tn * TC_BM + row;
+      const float sb = (P.csm == 1 || P.csm == 3) ? P.scales_w[n] : 1.f;
+      float bv = 0.f;
+      if (P.bias) {
+        if (P.out_dtype == GLB_FP16) bv = __half2float(reinterpret_cast<const __half*>(P.bias)[n]);
+        else if (P.out_dtype == GLB_BF16) bv = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(P.bias)[n]);
+        else bv = reinterpret_cast<const float*>(P.bias)[n];
+      }
+      ptx::mbar_wait(&tfull[buf], bph);
+      ptx::tc_fence_after_sync();
+#pragma unroll 1
+      for (int c0 = 0; c0 < BT; c0 += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * BT + c0), r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int m = tm * BT + c0 + j;
+          if (m < P.M) {
+            const int64_t oi = (int64_t)m * P.N + n;
+            if (IS_INT && P.out_dtype == GLB_INT32 && P.csm == 0 && !P.bias) {
+              reinterpret_cast<int32_t*>(P.y)[oi] = (int32_t)r[j];
+              continue;
+            }
+            float v = IS_INT ? (float)(int32_t)r[j] : __uint_as_float(r[j]);     // cvt.rn.f32.s32
+            if (P.csm == 1) v = __fmul_rn(v, sb);
+            else if (P.csm == 2) v = __fmul_rn(v, P.scales_x[m]);
+            else if (P.csm == 3) v = __fmul_rn(v, __fmul_rn(P.scales_x[m], sb));
+            if (P.out_dtype == GLB_FP16) {
+              if (P.bias) v = __half2float(__float2half_rn(v)) + bv;
+              reinterpret_cast<__half*>(P.y)[oi] = __float2half_rn(v);
+            } else if (P.out_dtype == GLB_BF16) {
+              if (P.bias) v = __bfloat162float(__float2bfloat16_rn(v)) + bv;
+              reinterpret_cast<__nv_bfloat16*>(P.y)[oi] = __float2bfloat16_rn(v);
+            } else if (P.out_dtype == GLB_FP32) {
+              reinterpret_cast<float*>(P.y)[oi] = v + bv;
+            } else {
+              reinterpret_cast<int32_t*>(P.y)[oi] = (int32_t)(v + bv);
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tempty[buf]);
+    }
+  }
   ptx::tc_fence_before_sync();
   __syncthreads();
   ptx::tc_fence_after_sync();
@@ -348,9 +535,67 @@ int launch_tc(const glb_linear& L, const void* x, void* y, int64_t M, const void
   return GLB_OK;
 }
 
+
+template <bool IS_INT, int BT>
+int launch_t8(const glb_linear& L, const void* x, const float* scales_x, void* y, int64_t M, const void* bias, cudaStream_t stream) {
+  using S = T8Smem<BT>;
+  CUtensorMap tx, tw;
+  int rc = make_tmap_2d(&tx, CU_TENSOR_MAP_DATA_TYPE_UINT8, x, (uint64_t)L.K, (uint64_t)M, (uint64_t)L.K, T8_BK, BT,
+                        CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc != GLB_OK) return rc;
+  // W_q is the (K, N) view with strides (1, K) of an (N, K) row-major byte matrix
+  rc = make_tmap_2d(&tw, CU_TENSOR_MAP_DATA_TYPE_UINT8, L.W_q, (uint64_t)L.K, (uint64_t)L.N, (uint64_t)L.K, T8_BK, TC_BM,
+                    CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc != GLB_OK) return rc;
+  T8Params P;
+  P.scales_w = (L.channel_scale_mode == 1 || L.channel_scale_mode == 3) ? reinterpret_cast<const float*>(L.scales) : nullptr;
+  P.scales_x = scales_x; P.y = y; P.bias = bias;
+  P.M = (int)M; P.N = (int)L.N; P.K = (int)L.K; P.csm = L.channel_scale_mode; P.out_dtype = L.output_dtype;
+  P.tiles_m = (int)((M + BT - 1) / BT); P.tiles_n = (int)(L.N / TC_BM);
+  uint32_t idesc;
+  if (IS_INT) idesc = ptx::make_idesc(2u, 1u, 1u, TC_BM, BT);                         // s32 accumulate, signed 8-bit A/B
+  else {
+    const uint32_t wf = (L.wq_dtype == GLB_FP8E5) ? 1u : 0u, xf = (act_storage_dtype(L.input_dtype) == GLB_FP8E5) ? 1u : 0u;
+    idesc = ptx::make_idesc(1u, wf, xf, TC_BM, BT);                                    // f32 accumulate, e4m3 = 0 / e5m2 = 1
+  }
+  auto kern = gemm_a8w8_tc_kernel<IS_INT, BT>;
+  static thread_local bool configured = false;
+  if (!configured) {
+    GLB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    configured = true;
+  }
+  const int grid = std::min(num_sms(), P.tiles_m * P.tiles_n);
+  kern<<<grid, T8_THREADS, S::TOTAL, stream>>>(tx, tw, P, idesc);
+  count_launch();
+  GLB_CHECK_CUDA(cudaGetLastError());
+  return GLB_OK;
+}
+
+bool a8w8_tc_supported(const glb_linear& L, int64_t M) {
+  if (M < 1 || M > (1 << 24)) return false;
+  const int xd = act_storage_dtype(L.input_dtype);
+  const bool is_int = (xd == GLB_INT8), is_f8 = (xd == GLB_FP8E4 || xd == GLB_FP8E5);
+  if (!is_int && !is_f8) return false;
+  if (is_mx(L.input_dtype)) return false;
+  if (L.W_group_mode != 0 || L.elements_per_sample != 1) return false;
+  if (is_int && L.wq_dtype != GLB_INT8) return false;
+  if (is_f8 && !(L.wq_dtype == GLB_FP8E4 || L.wq_dtype == GLB_FP8E5)) return false;
+  if (L.wq_stride0 != 1 || L.wq_stride1 != L.K) return false;            // K-contiguous weights
+  if (L.channel_scale_mode < 0 || L.channel_scale_mode > 3) return false;
+  if ((L.channel_scale_mode == 1 || L.channel_scale_mode == 3) && (L.scales_dtype != GLB_FP32 || L.scales_numel != L.N)) return false;
+  if (L.channel_scale_mode >= 1 && L.meta_dtype != GLB_FP32) return false;
+  if (!(L.output_dtype == GLB_FP16 || L.output_dtype == GLB_BF16 || L.output_dtype == GLB_FP32 ||
+        (is_int && L.output_dtype == GLB_INT32)))
+    return false;
+  if (L.N % TC_BM != 0 || L.K % T8_BK != 0) return false;
+  if (reinterpret_cast<uintptr_t>(L.W_q) & 15) return false;
+  return true;
+}
+
 }  // namespace
 
 bool gemm_tc_supported(const glb_linear& L, int64_t M) {
+  if (a8w8_tc_supported(L, M)) return true;
   if (M < 1 || M > (1 << 24)) return false;
   if (!(L.input_dtype == GLB_FP16 || L.input_dtype == GLB_BF16)) return false;
   if (L.output_dtype != L.input_dtype || L.meta_dtype != L.input_dtype) return false;
@@ -371,9 +616,19 @@ size_t gemm_tc_workspace(const glb_linear&, int64_t) { return 0; }
 
 int launch_gemm_tc(const glb_linear& L, const void* x, const float* scales_x, void* y, int64_t M, void* workspace,
                    size_t ws_bytes, const void* bias, cudaStream_t stream) {
-  (void)scales_x; (void)workspace; (void)ws_bytes;
+  (void)workspace; (void)ws_bytes;
   GLB_REQUIRE(gemm_tc_supported(L, M), GLB_ERR_UNSUPPORTED, "tcgen05 GEMM: unsupported layer configuration");
   GLB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, GLB_ERR_INVALID, "tcgen05 GEMM: x must be 16-byte aligned");
+  if (a8w8_tc_supported(L, M)) {
+    const bool is_int = (act_storage_dtype(L.input_dtype) == GLB_INT8);
+    set_kernel_name(is_int ? "gemm_a8w8_int8_tcgen05" : "gemm_a8w8_fp8_tcgen05");
+#define GLB_T8(BT) (is_int ? launch_t8<true, BT>(L, x, scales_x, y, M, bias, stream) : launch_t8<false, BT>(L, x, scales_x, y, M, bias, stream))
+    if (M <= 32) return GLB_T8(32);
+    if (M <= 64) return GLB_T8(64);
+    if (M <= 128) return GLB_T8(128);
+    return GLB_T8(256);
+#undef GLB_T8
+  }
   const bool bf = (L.input_dtype == GLB_BF16);
   set_kernel_name("gemm_a16w4_tcgen05");
   if (M <= 32) return bf ? launch_tc<true, 32>(L, x, y, M, bias, stream) : launch_tc<false, 32>(L, x, y, M, bias, stream);

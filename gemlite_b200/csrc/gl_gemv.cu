@@ -34,7 +34,7 @@ constexpr int GV_WARPS = 8;
 constexpr int GV_COLS = 32;        // columns per cluster
 constexpr int GV_R = 8;            // uint4 loads a lane keeps in flight per batch
 #ifndef GLB_GEMV_FAST
-#define GLB_GEMV_FAST 0            // 1: offset-carrying nibble unpack (no subtract), fp16 only
+#define GLB_GEMV_FAST 1            // 1: offset-carrying nibble unpack (no subtract), fp16 only
 #endif
 
 struct GemvParams {
@@ -131,13 +131,20 @@ __device__ __forceinline__ void st_cluster_f32(float* local_smem_ptr, uint32_t r
 // Shared memory (per CTA, Kc = K / KSPLIT):
 //   xs[MT][Kc] permuted 16-bit activations | zero[4] (16 B of zeros)
 //   | red[8][MT][32] fp32 per-warp partials | peer[MT][32] fp32 partials of the other cluster rank
+//
+// MMA mapping (mma.sync.m16n8k16, D[16x8] = A[16x16] B[16x8]):
+//   A = weights^T : rows 0-7 <-> column col0+4g+cA, rows 8-15 <-> column col0+4g+cB of lane group g
+//                   (one MMA consumes TWO of the lane's four words -> 256 weights per instruction);
+//   B = x^T       : column j <-> token j (8 tokens per MMA; NB = 2 token blocks for M <= 16);
+//   k slots (2t,2t+1 | 2t+8,2t+9) of lane t <-> nibble pairs of ITS packed row (run*4 + t), the same
+//   permutation being applied to x when it is staged, so no data ever moves between lanes.
 template <bool BF16, int MT, int RPG /*4-row runs per group = gs/32*/, int KSPLIT, bool FAST>
 __global__ void __launch_bounds__(GV_THREADS, 2) gemv_w4_mma_kernel(const GemvParams P) {
   static_assert(!(BF16 && FAST), "the offset-carrying unpack needs fp16's 10-bit mantissa");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int GPB = (GV_R / RPG) > 0 ? (GV_R / RPG) : 1;   // groups a warp covers per batch
   constexpr int RUNS = GPB * RPG;                            // uint4 loads per batch
-  constexpr bool HI = (MT > 8);                              // MMA rows 8..15 carry tokens
+  constexpr int NB = (MT > 8) ? 2 : 1;                       // token blocks of 8
   const int K = P.K, N = P.N;
   const int G = K / P.group_size;
   const int Kc = K / KSPLIT, Gc = G / KSPLIT;
@@ -157,13 +164,13 @@ __global__ void __launch_bounds__(GV_THREADS, 2) gemv_w4_mma_kernel(const GemvPa
   const int nbatches = (Gc + GV_WARPS * GPB - 1) / (GV_WARPS * GPB);
 
   // ---- 1. everything that does not depend on the previous kernel: weights + scale/zero vectors ----
-  // lane (g8, t4) loads row (run*4 + t4), columns col0 + 4*g8 .. +3 ; it later owns the outputs of
-  // columns col0 + 8*t4 .. +7 (rows g8, g8+8), whose scales/zeros are one 16-byte vector per group.
+  // lane (g8, t4) loads packed row (run*4 + t4), columns col0 + 4*g8 .. +3, and owns the outputs of exactly
+  // those four columns (tokens 2*t4, 2*t4+1 of each token block): their scales/zeros are one 8-byte vector.
   const uint32_t* wbase = P.W + (size_t)col0 + 4 * g8 + (size_t)t4 * N;
-  const uint16_t* sbase = reinterpret_cast<const uint16_t*>(P.scales) + col0 + 8 * t4;
-  const uint16_t* zbase = reinterpret_cast<const uint16_t*>(P.zeros) + col0 + 8 * t4;
+  const uint16_t* sbase = reinterpret_cast<const uint16_t*>(P.scales) + col0 + 4 * g8;
+  const uint16_t* zbase = reinterpret_cast<const uint16_t*>(P.zeros) + col0 + 4 * g8;
   uint4 q[RUNS];
-  uint4 sv[GPB], zv[GPB];
+  uint2 sv[GPB], zv[GPB];
   auto issue = [&](int batch) {
     const int gl0 = (batch * GV_WARPS + warp) * GPB;           // first group (CTA-local) of this warp in the batch
     if (gl0 < Gc) {
@@ -172,8 +179,8 @@ __global__ void __launch_bounds__(GV_THREADS, 2) gemv_w4_mma_kernel(const GemvPa
       for (int i = 0; i < RUNS; ++i) q[i] = ldg_nc_v4(wp + (size_t)(i * 4) * N);   // consecutive 4-row runs
 #pragma unroll
       for (int j = 0; j < GPB; ++j) {
-        sv[j] = ldg_nc_v4(sbase + (size_t)(gbeg + gl0 + j) * N);
-        if (P.mode != 2) zv[j] = ldg_nc_v4(zbase + (size_t)(gbeg + gl0 + j) * N);
+        sv[j] = __ldg(reinterpret_cast<const uint2*>(sbase + (size_t)(gbeg + gl0 + j) * N));
+        if (P.mode != 2) zv[j] = __ldg(reinterpret_cast<const uint2*>(zbase + (size_t)(gbeg + gl0 + j) * N));
       }
     }
   };
@@ -183,7 +190,7 @@ __global__ void __launch_bounds__(GV_THREADS, 2) gemv_w4_mma_kernel(const GemvPa
   pdl_wait_prior_grids();
   {
     // word r of row m: source k = 8r + j -> slot order [0,4,1,5,2,6,3,7] so that an LDS.128 yields
-    // {(k0,k4), (k1,k5), (k2,k6), (k3,k7)} = the A-fragment pairs matching nibbles_to_f16x2
+    // {(k0,k4), (k1,k5), (k2,k6), (k3,k7)} = the B-fragment pairs matching nibbles_to_f16x2
     const uint16_t* xg = reinterpret_cast<const uint16_t*>(P.x) + kbeg;
     const int words = Kc >> 3;
     for (int i = threadIdx.x; i < MT * words; i += GV_THREADS) {
@@ -197,8 +204,8 @@ __global__ void __launch_bounds__(GV_THREADS, 2) gemv_w4_mma_kernel(const GemvPa
         o.w = __byte_perm(v.y, v.w, 0x7632);   // (k3,k7)
         if (FAST) {                            // the 1024+16n slots see x/16 (exact unless subnormal)
           const __half2 k16th = __half2half2(__ushort_as_half((unsigned short)0x2C00));
-          __half2 a = __hmul2(*reinterpret_cast<__half2*>(&o.y), k16th), b = __hmul2(*reinterpret_cast<__half2*>(&o.w), k16th);
-          o.y = *reinterpret_cast<uint32_t*>(&a); o.w = *reinterpret_cast<uint32_t*>(&b);
+          __half2 a = __hmul2(*reinterpret_cast<__half2*>(&o.y), k16th), b2 = __hmul2(*reinterpret_cast<__half2*>(&o.w), k16th);
+          o.y = *reinterpret_cast<uint32_t*>(&a); o.w = *reinterpret_cast<uint32_t*>(&b2);
         }
       }
       *reinterpret_cast<uint4*>(xs + (size_t)m * Kc + (size_t)r * 8) = o;
@@ -209,75 +216,88 @@ __global__ void __launch_bounds__(GV_THREADS, 2) gemv_w4_mma_kernel(const GemvPa
   pdl_launch_dependents();
 
   // ---- 3. main loop ----
-  // out[c][0..3]: rows (g8, g8+8) x columns col0 + 8*t4 + c (regs 0,2) and col0 + 8*t4 + 4 + c (regs 1,3)
-  float out[4][4];
+  // out[nb][c][tk]: column col0 + 4*g8 + c, token nb*8 + 2*t4 + tk
+  float out[NB][4][2];
 #pragma unroll
-  for (int c = 0; c < 4; ++c) { out[c][0] = out[c][1] = out[c][2] = out[c][3] = 0.f; }
-  const bool a_lo = (g8 < MT), a_hi = HI && (g8 + 8 < MT);
-  // A-fragment source: this lane's x row; lanes whose MMA row does not exist read 16 bytes of zeros (stride 0)
-  const unsigned char* xa_lo = a_lo ? reinterpret_cast<const unsigned char*>(xs + (size_t)g8 * Kc) + t4 * 16
-                                    : reinterpret_cast<const unsigned char*>(zero16);
-  const unsigned char* xa_hi = a_hi ? reinterpret_cast<const unsigned char*>(xs + (size_t)(g8 + 8) * Kc) + t4 * 16
-                                    : reinterpret_cast<const unsigned char*>(zero16);
-  const int st_lo = a_lo ? 64 : 0, st_hi = a_hi ? 64 : 0;      // bytes per 4-row run
-  // "ones" B fragment: one extra MMA per A fragment yields the group sums of x in the accumulator layout:
-  //   even n' : sum_k x_k            (slots carrying x/16 are weighted by 16 in FAST mode)
-  //   odd  n' : sum_k x'_k           (FAST only: what the 1024 offset multiplies)
+  for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) out[nb][c][0] = out[nb][c][1] = 0.f;
+  // B-fragment source: x row of token (nb*8 + g8); lanes whose token does not exist read 16 bytes of zeros (stride 0)
+  const unsigned char* xb[NB];
+  int xst[NB];
+#pragma unroll
+  for (int nb = 0; nb < NB; ++nb) {
+    const bool ok = (nb * 8 + g8) < MT;
+    xb[nb] = ok ? reinterpret_cast<const unsigned char*>(xs + (size_t)(nb * 8 + g8) * Kc) + t4 * 16
+                : reinterpret_cast<const unsigned char*>(zero16);
+    xst[nb] = ok ? 64 : 0;                                        // bytes per 4-row run
+  }
+  // "ones" A operand: one extra MMA per B fragment yields the group sums of x in the accumulator layout:
+  //   rows 0-7  (d0,d1): sum_k x_k   (in FAST mode the slots that carry x/16 are weighted by 16)
+  //   rows 8-15 (d2,d3): sum_k x'_k  (FAST only: what the 1024 offset multiplies)
   const uint32_t one2 = BF16 ? 0x3F803F80u : 0x3C003C00u;
-  const uint32_t ones_b0 = one2;
-  const uint32_t ones_b1 = (FAST && !(g8 & 1)) ? 0x4C004C00u /* (16,16) */ : one2;
+  const uint32_t ones_a[4] = {one2, one2, FAST ? 0x4C004C00u /* (16,16) */ : one2, one2};
 
   for (int batch = 0; batch < nbatches; ++batch) {
     const int gl0 = (batch * GV_WARPS + warp) * GPB;
     if (gl0 < Gc) {
 #pragma unroll
       for (int j = 0; j < GPB; ++j) {
-        float dacc[4][4], dsum[4];
+        float dacc[NB][2][4], dsum[NB][4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) { dacc[c][0] = dacc[c][1] = dacc[c][2] = dacc[c][3] = 0.f; }
-        dsum[0] = dsum[1] = dsum[2] = dsum[3] = 0.f;
+        for (int nb = 0; nb < NB; ++nb) {
+#pragma unroll
+          for (int pr = 0; pr < 2; ++pr) dacc[nb][pr][0] = dacc[nb][pr][1] = dacc[nb][pr][2] = dacc[nb][pr][3] = 0.f;
+          dsum[nb][0] = dsum[nb][1] = dsum[nb][2] = dsum[nb][3] = 0.f;
+        }
 #pragma unroll
         for (int r = 0; r < RPG; ++r) {
           const int i = j * RPG + r;
           const int run = (gl0 + j) * RPG + r;                           // 4-row run inside this CTA's K range
-          const uint4 vlo = *reinterpret_cast<const uint4*>(xa_lo + (size_t)run * st_lo);
-          uint4 vhi = make_uint4(0u, 0u, 0u, 0u);
-          if (HI) vhi = *reinterpret_cast<const uint4*>(xa_hi + (size_t)run * st_hi);
-          const uint32_t a1[4] = {vlo.x, vhi.x, vlo.y, vhi.y};
-          const uint32_t a2[4] = {vlo.z, vhi.z, vlo.w, vhi.w};
-          const uint32_t w4[4] = {q[i].x, q[i].y, q[i].z, q[i].w};
           uint32_t h[4][4];
+          nibbles_to_f16x2<BF16, FAST>(q[i].x, h[0]);
+          nibbles_to_f16x2<BF16, FAST>(q[i].y, h[1]);
+          nibbles_to_f16x2<BF16, FAST>(q[i].z, h[2]);
+          nibbles_to_f16x2<BF16, FAST>(q[i].w, h[3]);
 #pragma unroll
-          for (int c = 0; c < 4; ++c) nibbles_to_f16x2<BF16, FAST>(w4[c], h[c]);
+          for (int nb = 0; nb < NB; ++nb) {
+            const uint4 xv = *reinterpret_cast<const uint4*>(xb[nb] + (size_t)run * xst[nb]);
 #pragma unroll
-          for (int c = 0; c < 4; ++c) mma16816<BF16>(dacc[c], a1, h[c][0], h[c][1]);
-          mma16816<BF16>(dsum, a1, ones_b0, ones_b1);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) mma16816<BF16>(dacc[c], a2, h[c][2], h[c][3]);
-          mma16816<BF16>(dsum, a2, ones_b0, ones_b1);
+            for (int hh = 0; hh < 2; ++hh) {                             // hh = 0: (k0,k4),(k1,k5)   hh = 1: (k2,k6),(k3,k7)
+              const uint32_t b0 = hh ? xv.z : xv.x, b1 = hh ? xv.w : xv.y;
+              const uint32_t a01[4] = {h[0][2 * hh], h[1][2 * hh], h[0][2 * hh + 1], h[1][2 * hh + 1]};
+              const uint32_t a23[4] = {h[2][2 * hh], h[3][2 * hh], h[2][2 * hh + 1], h[3][2 * hh + 1]};
+              mma16816<BF16>(dacc[nb][0], a01, b0, b1);
+              mma16816<BF16>(dacc[nb][1], a23, b0, b1);
+              if (P.mode != 2 || FAST) mma16816<BF16>(dsum[nb], ones_a, b0, b1);
+            }
+          }
         }
         // ---- end of group: y += s * sum(x q) + z' * sum(x), z' = zeros (mode 4) | -zeros*s (mode 3) | 0 (mode 2)
-        // dsum[0] / [2]: even n' -> sum x (rows g8 / g8+8); dsum[1] / [3]: odd n' -> sum x' (FAST) else sum x
-        const float sx_lo = dsum[0], sx_hi = dsum[2];
-        const float off_lo = FAST ? 1024.f * dsum[1] : 0.f, off_hi = FAST ? 1024.f * dsum[3] : 0.f;
-        const uint32_t sw[4] = {sv[j].x, sv[j].y, sv[j].z, sv[j].w};
-        const uint32_t zw[4] = {zv[j].x, zv[j].y, zv[j].z, zv[j].w};
+        float sc[4], zc[4];
+        {
+          const uint32_t sw[2] = {sv[j].x, sv[j].y}, zw[2] = {zv[j].x, zv[j].y};
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          // column 8*t4 + c -> element c of the vector ; column 8*t4 + 4 + c -> element 4 + c
-          const float s0 = cvt_meta<BF16>((uint16_t)((c & 1) ? (sw[c >> 1] >> 16) : (sw[c >> 1] & 0xffffu)));
-          const float s1 = cvt_meta<BF16>((uint16_t)((c & 1) ? (sw[2 + (c >> 1)] >> 16) : (sw[2 + (c >> 1)] & 0xffffu)));
-          float z0 = 0.f, z1 = 0.f;
-          if (P.mode != 2) {
-            z0 = cvt_meta<BF16>((uint16_t)((c & 1) ? (zw[c >> 1] >> 16) : (zw[c >> 1] & 0xffffu)));
-            z1 = cvt_meta<BF16>((uint16_t)((c & 1) ? (zw[2 + (c >> 1)] >> 16) : (zw[2 + (c >> 1)] & 0xffffu)));
-            if (P.mode == 3) { z0 = -z0 * s0; z1 = -z1 * s1; }
+          for (int c = 0; c < 4; ++c) {
+            sc[c] = cvt_meta<BF16>((uint16_t)((c & 1) ? (sw[c >> 1] >> 16) : (sw[c >> 1] & 0xffffu)));
+            zc[c] = 0.f;
+            if (P.mode != 2) {
+              zc[c] = cvt_meta<BF16>((uint16_t)((c & 1) ? (zw[c >> 1] >> 16) : (zw[c >> 1] & 0xffffu)));
+              if (P.mode == 3) zc[c] = -zc[c] * sc[c];
+            }
           }
-          out[c][0] = fmaf(s0, dacc[c][0] - off_lo, fmaf(z0, sx_lo, out[c][0]));
-          out[c][1] = fmaf(s1, dacc[c][1] - off_lo, fmaf(z1, sx_lo, out[c][1]));
-          if (HI) {
-            out[c][2] = fmaf(s0, dacc[c][2] - off_hi, fmaf(z0, sx_hi, out[c][2]));
-            out[c][3] = fmaf(s1, dacc[c][3] - off_hi, fmaf(z1, sx_hi, out[c][3]));
+        }
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) {
+#pragma unroll
+          for (int tk = 0; tk < 2; ++tk) {
+            const float sx = dsum[nb][tk];
+            const float off = FAST ? 1024.f * dsum[nb][2 + tk] : 0.f;
+            // pair 0 = columns (c0 rows 0-7 -> d0,d1 ; c1 rows 8-15 -> d2,d3), pair 1 = (c2, c3)
+            out[nb][0][tk] = fmaf(sc[0], dacc[nb][0][tk] - off, fmaf(zc[0], sx, out[nb][0][tk]));
+            out[nb][1][tk] = fmaf(sc[1], dacc[nb][0][2 + tk] - off, fmaf(zc[1], sx, out[nb][1][tk]));
+            out[nb][2][tk] = fmaf(sc[2], dacc[nb][1][tk] - off, fmaf(zc[2], sx, out[nb][2][tk]));
+            out[nb][3][tk] = fmaf(sc[3], dacc[nb][1][2 + tk] - off, fmaf(zc[3], sx, out[nb][3][tk]));
           }
         }
       }
@@ -287,16 +307,15 @@ __global__ void __launch_bounds__(GV_THREADS, 2) gemv_w4_mma_kernel(const GemvPa
 
   // ---- 4. cross-warp reduction, cluster (split-K) reduction through DSMEM, epilogue ----
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    if (a_lo) {
-      red[(warp * MT + g8) * GV_COLS + 8 * t4 + c] = out[c][0];
-      red[(warp * MT + g8) * GV_COLS + 8 * t4 + 4 + c] = out[c][1];
+  for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+    for (int tk = 0; tk < 2; ++tk) {
+      const int m = nb * 8 + 2 * t4 + tk;
+      if (m < MT) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) red[(warp * MT + m) * GV_COLS + 4 * g8 + c] = out[nb][c][tk];
+      }
     }
-    if (a_hi) {
-      red[(warp * MT + g8 + 8) * GV_COLS + 8 * t4 + c] = out[c][2];
-      red[(warp * MT + g8 + 8) * GV_COLS + 8 * t4 + 4 + c] = out[c][3];
-    }
-  }
   __syncthreads();
   float part[(MT * GV_COLS + GV_THREADS - 1) / GV_THREADS];
 #pragma unroll
@@ -412,8 +431,8 @@ bool gemv_supported(const glb_linear& L, int64_t M) {
   if (L.scales_numel != (L.K / gs) * L.N || L.s_stride1 != 1 || L.s_stride0 != L.N) return false;
   if (L.W_group_mode != 2 && (L.z_stride1 != 1 || L.z_stride0 != L.N)) return false;
   if (L.N % GV_COLS != 0 || L.K % 8 != 0) return false;
-  if ((reinterpret_cast<uintptr_t>(L.W_q) & 15) || (reinterpret_cast<uintptr_t>(L.scales) & 15)) return false;
-  if (L.W_group_mode != 2 && (reinterpret_cast<uintptr_t>(L.zeros) & 15)) return false;
+  if ((reinterpret_cast<uintptr_t>(L.W_q) & 15) || (reinterpret_cast<uintptr_t>(L.scales) & 7)) return false;
+  if (L.W_group_mode != 2 && (reinterpret_cast<uintptr_t>(L.zeros) & 7)) return false;
   const int mt = (M == 1) ? 1 : (M <= 8 ? 8 : 16);
   const size_t smem = (size_t)mt * L.K * 2 + (size_t)mt * (L.K / gs) * 4 + (size_t)(GV_WARPS + 1) * mt * GV_COLS * 4 + 16;
   if (smem > 200 * 1024) return false;

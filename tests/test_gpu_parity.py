@@ -280,9 +280,11 @@ def test_mxfp_weight_only_vs_oracle_and_unquantised():
     torch.manual_seed(0)
     N, K = 512, 1024
     for nbits, tol_q in ((4, 7e-4), (8, 2e-4)):   # the reference's own bars vs the unquantised layer (test_mxfp.py:50,57)
-        W = (torch.randn(N, K) / 10).to(torch.bfloat16) / 10
+        # same data recipe as the reference test (test_mxfp.py:22-33): default Linear init / 10, x = randn / 10
         lin = torch.nn.Linear(K, N, bias=False, dtype=torch.bfloat16, device=DEV)
-        lin.weight.data = W.to(DEV)
+        lin.weight.data /= 10.0
+        lin.weight.requires_grad = False
+        W = lin.weight.data.cpu()
         proc = (A16W4_MXFP if nbits == 4 else A16W8_MXFP)(device=DEV, dtype=torch.bfloat16)
         layer = proc.from_linear(lin, del_orig=False)
         assert layer.W_q.numel() * layer.W_q.itemsize == N * K * nbits // 8 and not layer.scaled_activations

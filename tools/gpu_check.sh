@@ -4,7 +4,7 @@
 set -u
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > gpurun_out/gpu.csv 2>&1
-echo "== pytest" ; timeout 1200 python -m pytest tests -m gpu -q --timeout=300 2>&1 | tail -60 | tee gpurun_out/pytest_gpu.log
+echo "== pytest" ; timeout 1200 python -m pytest tests -m gpu -q --timeout=300 --tb=short > gpurun_out/pytest_gpu_full.log 2>&1; grep -E "^(FAILED|ERROR|E  )|passed|failed" gpurun_out/pytest_gpu_full.log | cut -c1-300 | head -80 | tee gpurun_out/pytest_gpu.log
 echo "== smoke" ; timeout 300 python __graft_entry__.py --smoke 2>&1 | tail -8 | tee gpurun_out/smoke.log
 echo "== bench" ; timeout 600 python bench.py --steps 30 --warmup 5 2>&1 | tail -3 | tee gpurun_out/bench.log
 echo "== bench nopdl" ; GLB_PDL=0 timeout 600 python bench.py --steps 30 --warmup 5 2>&1 | tail -1 | tee gpurun_out/bench_nopdl.log
