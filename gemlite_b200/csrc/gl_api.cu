@@ -2,6 +2,9 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <cuda.h>
+#include <mutex>
+
 #include "gl_common.cuh"
 
 namespace glb {
@@ -19,6 +22,57 @@ void set_error(const char* fmt, ...) {
 }
 void set_kernel_name(const char* name) { tl_kernel = name; }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// ---- TMA descriptors: cuTensorMapEncodeTiled is fetched from the driver at run time (no libcuda link) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, []() {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int make_tmap_2d(void* out_tmap, int dt, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                 uint32_t box_inner, uint32_t box_outer, int swizzle128) {
+  EncodeTiledFn fn = get_encode_fn();
+  GLB_REQUIRE(fn != nullptr, GLB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  CUtensorMapDataType cdt;
+  switch (dt) {
+    case GLB_FP16: cdt = CU_TENSOR_MAP_DATA_TYPE_FLOAT16; break;
+    case GLB_BF16: cdt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16; break;
+    case GLB_INT32: cdt = CU_TENSOR_MAP_DATA_TYPE_INT32; break;
+    case GLB_FP32: cdt = CU_TENSOR_MAP_DATA_TYPE_FLOAT32; break;
+    default: cdt = CU_TENSOR_MAP_DATA_TYPE_UINT8; break;
+  }
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(reinterpret_cast<CUtensorMap*>(out_tmap), cdt, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  GLB_REQUIRE(r == CUDA_SUCCESS, GLB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return GLB_OK;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
 
 static int validate(const glb_linear* L, int64_t M) {
   GLB_REQUIRE(L != nullptr, GLB_ERR_INVALID, "layer descriptor is NULL");

@@ -55,6 +55,11 @@ inline int dtype_bytes(int dt) {
   }
 }
 
+// host helpers shared by the TMA-based kernels (defined in gl_api.cu)
+int make_tmap_2d(void* out_tmap /*CUtensorMap*/, int glb_elem_dtype, const void* base, uint64_t inner, uint64_t outer,
+                 uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer, int swizzle128);
+int num_sms();
+
 // sub-kernel entry points (one translation unit each)
 int launch_generic(const glb_linear& L, const void* x, const float* scales_x, void* y, int64_t M,
                    const void* bias, cudaStream_t stream);

@@ -465,57 +465,13 @@ gemm_a8w8_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
 }
 
 // ---------------------------------------------------------------------------------------------- host
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, []() {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  });
-  return fn;
-}
-
-int make_tmap_2d(CUtensorMap* out, CUtensorMapDataType dt, const void* base, uint64_t inner, uint64_t outer,
-                 uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle sw) {
-  EncodeTiledFn fn = get_encode_fn();
-  GLB_REQUIRE(fn != nullptr, GLB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
-  cuuint64_t dims[2] = {inner, outer};
-  cuuint64_t strides[1] = {row_stride_bytes};
-  cuuint32_t box[2] = {box_inner, box_outer};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(out, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  GLB_REQUIRE(r == CUDA_SUCCESS, GLB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
-  return GLB_OK;
-}
-
-int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
-
 template <bool BF16, int BT>
 int launch_tc(const glb_linear& L, const void* x, void* y, int64_t M, const void* bias, cudaStream_t stream) {
   using S = TcSmem<BT>;
   CUtensorMap tx, tw;
-  int rc = make_tmap_2d(&tx, BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, x, (uint64_t)L.K,
-                        (uint64_t)M, (uint64_t)L.K * 2, TC_BK, BT, CU_TENSOR_MAP_SWIZZLE_128B);
+  int rc = make_tmap_2d(&tx, BF16 ? GLB_BF16 : GLB_FP16, x, (uint64_t)L.K, (uint64_t)M, (uint64_t)L.K * 2, TC_BK, BT, 1);
   if (rc != GLB_OK) return rc;
-  rc = make_tmap_2d(&tw, CU_TENSOR_MAP_DATA_TYPE_INT32, L.W_q, (uint64_t)L.N, (uint64_t)(L.K / 8), (uint64_t)L.N * 4, TC_BM,
-                    TC_BK / 8, CU_TENSOR_MAP_SWIZZLE_NONE);
+  rc = make_tmap_2d(&tw, GLB_INT32, L.W_q, (uint64_t)L.N, (uint64_t)(L.K / 8), (uint64_t)L.N * 4, TC_BM, TC_BK / 8, 0);
   if (rc != GLB_OK) return rc;
   TcParams P;
   P.scales = L.scales; P.zeros = (L.W_group_mode == 2) ? nullptr : L.zeros;
@@ -540,12 +496,10 @@ template <bool IS_INT, int BT>
 int launch_t8(const glb_linear& L, const void* x, const float* scales_x, void* y, int64_t M, const void* bias, cudaStream_t stream) {
   using S = T8Smem<BT>;
   CUtensorMap tx, tw;
-  int rc = make_tmap_2d(&tx, CU_TENSOR_MAP_DATA_TYPE_UINT8, x, (uint64_t)L.K, (uint64_t)M, (uint64_t)L.K, T8_BK, BT,
-                        CU_TENSOR_MAP_SWIZZLE_128B);
+  int rc = make_tmap_2d(&tx, GLB_UINT8, x, (uint64_t)L.K, (uint64_t)M, (uint64_t)L.K, T8_BK, BT, 1);
   if (rc != GLB_OK) return rc;
   // W_q is the (K, N) view with strides (1, K) of an (N, K) row-major byte matrix
-  rc = make_tmap_2d(&tw, CU_TENSOR_MAP_DATA_TYPE_UINT8, L.W_q, (uint64_t)L.K, (uint64_t)L.N, (uint64_t)L.K, T8_BK, TC_BM,
-                    CU_TENSOR_MAP_SWIZZLE_128B);
+  rc = make_tmap_2d(&tw, GLB_UINT8, L.W_q, (uint64_t)L.K, (uint64_t)L.N, (uint64_t)L.K, T8_BK, TC_BM, 1);
   if (rc != GLB_OK) return rc;
   T8Params P;
   P.scales_w = (L.channel_scale_mode == 1 || L.channel_scale_mode == 3) ? reinterpret_cast<const float*>(L.scales) : nullptr;

@@ -24,7 +24,10 @@
 //  * per group g:  y += s_g * sum_k x_k q_k  +  z'_g * sum_k x_k   (mode 4; modes 2/3 analogous) --
 //    the group-wise factorisation of sum_k x_k * fma(q_k, s_g, z'_g), applied in fp32; bias fused.
 // The same kernel handles 1 <= M <= 16 rows of x (rows of the MMA A operand).
+#include <cuda.h>
+
 #include "gl_common.cuh"
+#include "gl_ptx.cuh"
 
 namespace glb {
 namespace {
@@ -35,6 +38,9 @@ constexpr int GV_COLS = 32;        // columns per cluster
 constexpr int GV_R = 8;            // uint4 loads a lane keeps in flight per batch
 #ifndef GLB_GEMV_FAST
 #define GLB_GEMV_FAST 1            // 1: offset-carrying nibble unpack (no subtract), fp16 only
+#endif
+#ifndef GLB_GEMV_TMA
+#define GLB_GEMV_TMA 1             // 1: weights via TMA into shared memory (co-resident layers under PDL)
 #endif
 
 struct GemvParams {
@@ -388,8 +394,257 @@ int launch_w4(const GemvParams& P, cudaStream_t stream) {
   return GLB_OK;
 }
 
+
+// =================================================================================================
+// Decode kernel, TMA flavour (the default for M <= 8): same arithmetic and MMA mapping as
+// gemv_w4_mma_kernel above, but the weights / scales / zeros of the CTA are pulled into SHARED MEMORY
+// by TMA (cp.async.bulk.tensor) right at kernel start -- before griddepcontrol.wait -- instead of into
+// registers.  With <= 64 registers per thread four CTAs fit on an SM, so under programmatic dependent
+// launch the CTAs of layer i+1 are resident (their 32 KB of weights landing in shared memory) while
+// layer i is still computing: HBM streaming of the next layer overlaps the dependent x -> y chain.
+// =================================================================================================
+constexpr int GT_NCH = 4;   // weight chunks, one mbarrier each
+
+struct GemvTmaParams {
+  const void* x; void* y; const void* bias;
+  int K, N, M, group_size, mode;
+};
+
+template <bool BF16, int MT, int RPG, int KSPLIT, bool FAST>
+__global__ void __launch_bounds__(GV_THREADS, 4)
+gemv_w4_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_s,
+                   const __grid_constant__ CUtensorMap tmap_z, const GemvTmaParams P) {
+  static_assert(MT <= 8, "one token block");
+  static_assert(!(BF16 && FAST), "the offset-carrying unpack needs fp16's 10-bit mantissa");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int rpg = RPG * 4;                     // packed rows per group
+  const int K = P.K, N = P.N;
+  const int G = K / P.group_size;
+  const int Kc = K / KSPLIT, Gc = G / KSPLIT, rows_c = Kc >> 3;
+  const uint32_t rank = (KSPLIT > 1) ? cluster_ctarank() : 0u;
+  const int slab = (KSPLIT > 1) ? (blockIdx.x / KSPLIT) : blockIdx.x;
+  const int kbeg = (int)rank * Kc, gbeg = (int)rank * Gc;
+  const int col0 = slab * GV_COLS;
+  const int nch = (rows_c % (GT_NCH * rpg) == 0) ? GT_NCH : 1;
+  const int chunk_rows = rows_c / nch;
+
+  // shared memory carve-up (all TMA destinations 128-byte aligned)
+  unsigned char* wbuf = smem_raw;                                        // rows_c x 128 B
+  unsigned char* sbuf = wbuf + (size_t)rows_c * 128;                     // Gc x 64 B (padded to 128)
+  unsigned char* zbuf = sbuf + (((size_t)Gc * 64 + 127) & ~(size_t)127);
+  uint16_t* xs = reinterpret_cast<uint16_t*>(zbuf + (((size_t)Gc * 64 + 127) & ~(size_t)127));
+  uint32_t* zero16 = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(xs) + (size_t)MT * Kc * 2);
+  float* red = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(zero16) + 16);
+  float* peer = red + GV_WARPS * MT * GV_COLS;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(peer + MT * GV_COLS);     // [GT_NCH] weights, [GT_NCH] metadata
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g8 = lane >> 2, t4 = lane & 3;
+
+  // ---- 1. weights + metadata -> shared memory by TMA (independent of the previous kernel) ----
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tmap(&tmap_w);
+    ptx::prefetch_tmap(&tmap_s);
+    for (int c = 0; c <= GT_NCH; ++c) ptx::mbar_init(&bars[c], 1);
+    ptx::fence_mbar_init();
+    const uint32_t meta_bytes = (uint32_t)Gc * 64u * (P.mode != 2 ? 2u : 1u);
+    ptx::mbar_arrive_expect_tx(&bars[GT_NCH], meta_bytes);
+    ptx::tma_load_2d(sbuf, &tmap_s, &bars[GT_NCH], col0, gbeg);
+    if (P.mode != 2) ptx::tma_load_2d(zbuf, &tmap_z, &bars[GT_NCH], col0, gbeg);
+    for (int c = 0; c < nch; ++c) {
+      ptx::mbar_arrive_expect_tx(&bars[c], (uint32_t)chunk_rows * 128u);
+      ptx::tma_load_2d(wbuf + (size_t)c * chunk_rows * 128, &tmap_w, &bars[c], col0, (kbeg >> 3) + c * chunk_rows);
+    }
+  }
+  pdl_launch_dependents();      // everything this CTA can do ahead of its input has been issued
+
+  // ---- 2. x depends on the previous kernel: wait for it only now, then stage it permuted ----
+  pdl_wait_prior_grids();
+  {
+    const uint16_t* xg = reinterpret_cast<const uint16_t*>(P.x) + kbeg;
+    const int words = Kc >> 3;
+    for (int i = threadIdx.x; i < MT * words; i += GV_THREADS) {
+      const int m = (MT == 1) ? 0 : (i / words), r = (MT == 1) ? i : (i - m * words);
+      uint4 o = make_uint4(0u, 0u, 0u, 0u);
+      if (m < P.M) {
+        const uint4 v = *reinterpret_cast<const uint4*>(xg + (size_t)m * K + (size_t)r * 8);
+        o.x = __byte_perm(v.x, v.z, 0x5410);   // (k0,k4)
+        o.y = __byte_perm(v.x, v.z, 0x7632);   // (k1,k5)
+        o.z = __byte_perm(v.y, v.w, 0x5410);   // (k2,k6)
+        o.w = __byte_perm(v.y, v.w, 0x7632);   // (k3,k7)
+        if (FAST) {
+          const __half2 k16th = __half2half2(__ushort_as_half((unsigned short)0x2C00));
+          __half2 a = __hmul2(*reinterpret_cast<__half2*>(&o.y), k16th), b2 = __hmul2(*reinterpret_cast<__half2*>(&o.w), k16th);
+          o.y = *reinterpret_cast<uint32_t*>(&a); o.w = *reinterpret_cast<uint32_t*>(&b2);
+        }
+      }
+      *reinterpret_cast<uint4*>(xs + (size_t)m * Kc + (size_t)r * 8) = o;
+    }
+    if (threadIdx.x < 4) zero16[threadIdx.x] = 0u;
+  }
+  __syncthreads();              // also publishes the mbarrier initialisation to every thread
+
+  // ---- 3. main loop: warp w walks groups w, w + 8, ... of this CTA's K range ----
+  float out[4][2];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) out[c][0] = out[c][1] = 0.f;
+  const bool tok_ok = (g8 < MT);
+  const unsigned char* xb = tok_ok ? reinterpret_cast<const unsigned char*>(xs + (size_t)g8 * Kc) + t4 * 16
+                                   : reinterpret_cast<const unsigned char*>(zero16);
+  const int xst = tok_ok ? 64 : 0;
+  const unsigned char* wl = wbuf + t4 * 128 + g8 * 16;           // + run * 512
+  const uint32_t one2 = BF16 ? 0x3F803F80u : 0x3C003C00u;
+  const uint32_t ones_a[4] = {one2, one2, FAST ? 0x4C004C00u : one2, one2};
+  ptx::mbar_wait(&bars[GT_NCH], 0);                               // scales / zeros landed
+
+  for (int gl = warp; gl < Gc; gl += GV_WARPS) {
+    ptx::mbar_wait(&bars[(gl * rpg) / chunk_rows], 0);            // this group's weight chunk landed
+    float dacc[2][4], dsum[4];
+#pragma unroll
+    for (int pr = 0; pr < 2; ++pr) dacc[pr][0] = dacc[pr][1] = dacc[pr][2] = dacc[pr][3] = 0.f;
+    dsum[0] = dsum[1] = dsum[2] = dsum[3] = 0.f;
+#pragma unroll
+    for (int r = 0; r < RPG; ++r) {
+      const int run = gl * RPG + r;
+      const uint4 q = *reinterpret_cast<const uint4*>(wl + (size_t)run * 512);
+      const uint4 xv = *reinterpret_cast<const uint4*>(xb + (size_t)run * xst);
+      uint32_t ha[4], hb[4];
+      nibbles_to_f16x2<BF16, FAST>(q.x, ha);
+      nibbles_to_f16x2<BF16, FAST>(q.y, hb);
+      {
+        const uint32_t a0[4] = {ha[0], hb[0], ha[1], hb[1]}, a1[4] = {ha[2], hb[2], ha[3], hb[3]};
+        mma16816<BF16>(dacc[0], a0, xv.x, xv.y);
+        mma16816<BF16>(dacc[0], a1, xv.z, xv.w);
+      }
+      nibbles_to_f16x2<BF16, FAST>(q.z, ha);
+      nibbles_to_f16x2<BF16, FAST>(q.w, hb);
+      {
+        const uint32_t a0[4] = {ha[0], hb[0], ha[1], hb[1]}, a1[4] = {ha[2], hb[2], ha[3], hb[3]};
+        mma16816<BF16>(dacc[1], a0, xv.x, xv.y);
+        mma16816<BF16>(dacc[1], a1, xv.z, xv.w);
+      }
+      if (P.mode != 2 || FAST) {
+        mma16816<BF16>(dsum, ones_a, xv.x, xv.y);
+        mma16816<BF16>(dsum, ones_a, xv.z, xv.w);
+      }
+    }
+    // ---- end of group: y += s * sum(x q) + z' * sum(x) ----
+    const uint2 sw = *reinterpret_cast<const uint2*>(sbuf + (size_t)gl * 64 + g8 * 8);
+    uint2 zw = make_uint2(0u, 0u);
+    if (P.mode != 2) zw = *reinterpret_cast<const uint2*>(zbuf + (size_t)gl * 64 + g8 * 8);
+    const uint32_t swa[2] = {sw.x, sw.y}, zwa[2] = {zw.x, zw.y};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float sc = cvt_meta<BF16>((uint16_t)((c & 1) ? (swa[c >> 1] >> 16) : (swa[c >> 1] & 0xffffu)));
+      float zc = cvt_meta<BF16>((uint16_t)((c & 1) ? (zwa[c >> 1] >> 16) : (zwa[c >> 1] & 0xffffu)));
+      if (P.mode == 3) zc = -zc * sc;
+      const int pr = c >> 1, hi = (c & 1) * 2;        // c0,c2 -> rows 0-7 (d0,d1) ; c1,c3 -> rows 8-15 (d2,d3)
+#pragma unroll
+      for (int tk = 0; tk < 2; ++tk) {
+        const float off = FAST ? 1024.f * dsum[2 + tk] : 0.f;
+        out[c][tk] = fmaf(sc, dacc[pr][hi + tk] - off, fmaf(zc, dsum[tk], out[c][tk]));
+      }
+    }
+  }
+
+  // ---- 4. cross-warp reduction, cluster (split-K) reduction through DSMEM, epilogue ----
+#pragma unroll
+  for (int tk = 0; tk < 2; ++tk) {
+    const int m = 2 * t4 + tk;
+    if (m < MT) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) red[(warp * MT + m) * GV_COLS + 4 * g8 + c] = out[c][tk];
+    }
+  }
+  __syncthreads();
+  float part = 0.f;
+  const int i = threadIdx.x;
+  if (i < MT * GV_COLS) {
+    const int m = i / GV_COLS, c = i - m * GV_COLS;
+#pragma unroll
+    for (int w = 0; w < GV_WARPS; ++w) part += red[(w * MT + m) * GV_COLS + c];
+    if (KSPLIT > 1 && rank != 0) st_cluster_f32(&peer[i], 0u, part);
+  }
+  if (KSPLIT > 1) cluster_sync_all();
+  if (rank == 0 && i < MT * GV_COLS) {
+    const int m = i / GV_COLS, c = i - m * GV_COLS;
+    if (m < P.M) {
+      float v = part;
+      if (KSPLIT > 1) v += peer[i];
+      if (P.bias) v = rnd_out<BF16>(v) + cvt_meta<BF16>(reinterpret_cast<const uint16_t*>(P.bias)[col0 + c]);
+      st_out<BF16>(P.y, (int64_t)m * N + col0 + c, v);
+    }
+  }
+}
+
+template <int MT, int KSPLIT> size_t gemv_tma_smem_bytes(int K, int group_size) {
+  const int Kc = K / KSPLIT, Gc = K / group_size / KSPLIT;
+  const size_t meta = ((size_t)Gc * 64 + 127) & ~(size_t)127;
+  return (size_t)(Kc / 8) * 128 + 2 * meta + (size_t)MT * Kc * 2 + 16 + (size_t)GV_WARPS * MT * GV_COLS * 4 +
+         (size_t)MT * GV_COLS * 4 + (GT_NCH + 1) * 8 + 128;
+}
+
+template <bool BF16, int MT, int RPG, int KSPLIT, bool FAST>
+int launch_w4_tma(const glb_linear& L, const GemvParams& P0, cudaStream_t stream) {
+  const int Kc = P0.K / KSPLIT, Gc = P0.K / P0.group_size / KSPLIT, rows_c = Kc / 8;
+  constexpr int rpg = RPG * 4;
+  const int nch = (rows_c % (GT_NCH * rpg) == 0) ? GT_NCH : 1;
+  CUtensorMap tw, ts, tz;
+  int rc = make_tmap_2d(&tw, GLB_INT32, L.W_q, (uint64_t)L.N, (uint64_t)(L.K / 8), (uint64_t)L.N * 4, GV_COLS, rows_c / nch, 0);
+  if (rc != GLB_OK) return rc;
+  rc = make_tmap_2d(&ts, GLB_FP16, L.scales, (uint64_t)L.N, (uint64_t)(L.K / L.group_size), (uint64_t)L.N * 2, GV_COLS, Gc, 0);
+  if (rc != GLB_OK) return rc;
+  rc = make_tmap_2d(&tz, GLB_FP16, (P0.mode != 2) ? L.zeros : L.scales, (uint64_t)L.N, (uint64_t)(L.K / L.group_size),
+                    (uint64_t)L.N * 2, GV_COLS, Gc, 0);
+  if (rc != GLB_OK) return rc;
+  GemvTmaParams P;
+  P.x = P0.x; P.y = P0.y; P.bias = P0.bias; P.K = P0.K; P.N = P0.N; P.M = P0.M; P.group_size = P0.group_size; P.mode = P0.mode;
+  const size_t smem = gemv_tma_smem_bytes<MT, KSPLIT>(P0.K, P0.group_size);
+  auto kern = gemv_w4_tma_kernel<BF16, MT, RPG, KSPLIT, FAST>;
+  if (smem > 48 * 1024) {
+    static thread_local size_t configured = 0;
+    if (configured < smem) {
+      GLB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = smem;
+    }
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(P0.N / GV_COLS) * KSPLIT);
+  cfg.blockDim = dim3(GV_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (KSPLIT > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = KSPLIT; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (g_pdl_enabled.load()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  GLB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tw, ts, tz, P));
+  count_launch();
+  return GLB_OK;
+}
+
+// shapes the TMA flavour takes: <= 8 tokens, the CTA's weight slice fits 64 KB of shared memory
+bool gemv_tma_ok(const GemvParams& P, int ksplit) {
+  const int Kc = P.K / ksplit, Gc = P.K / P.group_size / ksplit;
+  if (P.M > 8) return false;
+  if ((Kc / 8) * 128 > 64 * 1024 || Gc > 256 || (Kc / 8) > 256 * GT_NCH) return false;
+  const int rows_c = Kc / 8, rpg = P.group_size / 8;
+  const int nch = (rows_c % (GT_NCH * rpg) == 0) ? GT_NCH : 1;
+  if (rows_c / nch > 256) return false;
+  return true;
+}
+
 template <bool BF16, int MT>
-int dispatch_w4(const GemvParams& P, cudaStream_t stream) {
+int dispatch_w4(const glb_linear& L, const GemvParams& P, cudaStream_t stream) {
   const int G = P.K / P.group_size;
   const int rpgi = P.group_size / 32;
   // split K over a 2-CTA cluster when that still leaves whole groups per warp-batch
@@ -397,7 +652,14 @@ int dispatch_w4(const GemvParams& P, cudaStream_t stream) {
   {                                                                                                   \
     constexpr int GPB = (GV_R / RPG) > 0 ? (GV_R / RPG) : 1;                                          \
     constexpr bool F = !BF16 && GLB_GEMV_FAST;                                                        \
-    if (G % (2 * GPB) == 0 && P.N / GV_COLS < 296) return launch_w4<BF16, MT, RPG, 2, F>(P, stream);  \
+    constexpr int MT8 = (MT <= 8) ? MT : 8;                                                           \
+    const bool split = (G % (2 * GPB) == 0 && P.N / GV_COLS < 296);                                   \
+    if (MT <= 8 && GLB_GEMV_TMA && (reinterpret_cast<uintptr_t>(L.scales) & 15) == 0 &&               \
+        (P.mode == 2 || (reinterpret_cast<uintptr_t>(L.zeros) & 15) == 0) && (P.N * 2) % 16 == 0) {   \
+      if (split && gemv_tma_ok(P, 2)) return launch_w4_tma<BF16, MT8, RPG, 2, F>(L, P, stream);       \
+      if (gemv_tma_ok(P, 1)) return launch_w4_tma<BF16, MT8, RPG, 1, F>(L, P, stream);                \
+    }                                                                                                 \
+    if (split) return launch_w4<BF16, MT, RPG, 2, F>(P, stream);                                      \
     return launch_w4<BF16, MT, RPG, 1, F>(P, stream);                                                 \
   }
   switch (rpgi) {
@@ -452,9 +714,9 @@ int launch_gemv(const glb_linear& L, const void* x, const float* scales_x, void*
   P.group_size = L.group_size; P.mode = L.W_group_mode;
   const bool bf = (L.input_dtype == GLB_BF16);
   set_kernel_name("gemv_w4_mma");
-  if (M == 1) return bf ? dispatch_w4<true, 1>(P, stream) : dispatch_w4<false, 1>(P, stream);
-  if (M <= 8) return bf ? dispatch_w4<true, 8>(P, stream) : dispatch_w4<false, 8>(P, stream);
-  return bf ? dispatch_w4<true, 16>(P, stream) : dispatch_w4<false, 16>(P, stream);
+  if (M == 1) return bf ? dispatch_w4<true, 1>(L, P, stream) : dispatch_w4<false, 1>(L, P, stream);
+  if (M <= 8) return bf ? dispatch_w4<true, 8>(L, P, stream) : dispatch_w4<false, 8>(L, P, stream);
+  return bf ? dispatch_w4<true, 16>(L, P, stream) : dispatch_w4<false, 16>(L, P, stream);
 }
 
 }  // namespace glb
