@@ -39,6 +39,8 @@ LAYERS = 64
 ALGO_BYTES = K * N // 2 + 2 * (K // GROUP) * N * 2 + 2 * K + 2 * N      # 8 929 280
 METRIC = "A16W4 gs=128 4096^2 decode M=1 HBM GB/s"
 PF_M, PF_K, PF_N = 4096, 8192, 8192
+ALIAS = os.environ.get("BENCH_ALIAS", "0") == "1"               # diagnostic: all layers share one weight buffer (L2-hot)
+INDEPENDENT = os.environ.get("BENCH_INDEPENDENT", "0") == "1"   # diagnostic: every layer reads the same x (no chain)
 
 
 def measured_peaks():
@@ -201,9 +203,11 @@ def run_ours(args, rank, world, local_rank):
     dev = torch.device(f"cuda:{local_rank}")
     torch.cuda.set_device(dev)
     layers = []
-    for (W_q, scales, zeros) in make_weights(dev, LAYERS, seed=rank):
+    for (W_q, scales, zeros) in make_weights(dev, 1 if ALIAS else LAYERS, seed=rank):
         layers.append(A16W4_HQQ_INT(device=dev, dtype=torch.float16).from_weights(W_q, scales, zeros))
         del W_q
+    if ALIAS:
+        layers = layers * LAYERS
     torch.cuda.synchronize()
     x0 = (torch.randn(1, K, device=dev, generator=torch.Generator(device=dev).manual_seed(7)) / 10).half()
 
@@ -217,7 +221,7 @@ def run_ours(args, rank, world, local_rank):
             y = layer(x)
             if world > 1:
                 outs[i].copy_(y)      # shard outputs collected for the single gather
-            else:
+            elif not INDEPENDENT:
                 x = y
         return x if world == 1 else outs
 
@@ -307,8 +311,9 @@ def run_ours(args, rank, world, local_rank):
         traffic = prof.get("dram_bytes_per_launch")
     except Exception:
         pass
-    cpu_v, cpu_calls, cpu_dt = cpu_reference_sample(os.cpu_count() or 1, seconds=12.0, max_calls=100)
-    prefill = time_prefill(dev) if world == 1 else None
+    skip = os.environ.get("BENCH_SKIP_EXTRAS", "0") == "1"     # diagnostic sweeps only
+    cpu_v, cpu_calls, cpu_dt = (0.0, 0, 0.0) if skip else cpu_reference_sample(os.cpu_count() or 1, seconds=12.0, max_calls=100)
+    prefill = time_prefill(dev) if (world == 1 and not skip) else None
     line = {
         "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
@@ -316,7 +321,7 @@ def run_ours(args, rank, world, local_rank):
         "config": {"workload": f"A16W4 gs={GROUP} decode M=1 K=N={K} fp16 (BASELINE configs[1]); step = {LAYERS} "
                                f"{'chained layers' if world == 1 else 'column shards (N_global=%d) + one NCCL all-gather' % (N * world)}",
                    "l2": f"{LAYERS} distinct layers = {LAYERS * ALGO_BYTES / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)",
-                   "launch": "CUDA graph replay, programmatic dependent launch", "parallelism": f"column-shard x{world}"},
+                   "launch": "CUDA graph replay, programmatic dependent launch", "chain": "independent layers (diagnostic)" if INDEPENDENT else "y_i feeds x_{i+1}", "parallelism": f"column-shard x{world}"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": "gemv_w4_mma_kernel", "us_per_launch": us_per_launch,
                      "algorithmic_bytes_per_launch": ALGO_BYTES,

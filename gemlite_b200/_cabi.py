@@ -38,7 +38,7 @@ class GlbLinear(ctypes.Structure):
 
 EXPORTS = [
     "glb_version", "glb_last_error", "glb_last_kernel", "glb_launch_count", "glb_pack_cols", "glb_unpack_cols",
-    "glb_quant_act_per_token", "glb_workspace_bytes", "glb_matmul", "glb_set_pdl", "glb_get_pdl",
+    "glb_quant_act_per_token", "glb_workspace_bytes", "glb_matmul", "glb_set_pdl", "glb_get_pdl", "glb_debug_timeline",
 ]
 
 
@@ -77,6 +77,8 @@ def load():
         lib.glb_set_pdl.argtypes = [i32]
         lib.glb_set_pdl.restype = None
         lib.glb_get_pdl.restype = i32
+        lib.glb_debug_timeline.argtypes = [vp, i32]
+        lib.glb_debug_timeline.restype = i32
         if os.environ.get("GLB_PDL", "1") == "0":
             lib.glb_set_pdl(0)
         _lib = lib

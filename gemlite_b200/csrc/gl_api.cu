@@ -118,6 +118,7 @@ extern "C" const char* glb_last_kernel(void) { return tl_kernel; }
 extern "C" uint64_t glb_launch_count(void) { return g_launches.load(); }
 extern "C" void glb_set_pdl(int enabled) { g_pdl_enabled.store(enabled ? 1 : 0); }
 extern "C" int glb_get_pdl(void) { return g_pdl_enabled.load(); }
+extern "C" int glb_debug_timeline(unsigned long long* out, int max_words) { return debug_read_timeline(out, max_words); }
 
 extern "C" size_t glb_workspace_bytes(const glb_linear* L, int64_t M, int matmul_type) {
   if (!L || M <= 0) return 0;

@@ -66,6 +66,7 @@ int launch_generic(const glb_linear& L, const void* x, const float* scales_x, vo
 bool gemv_supported(const glb_linear& L, int64_t M);
 int launch_gemv(const glb_linear& L, const void* x, const float* scales_x, void* y, int64_t M,
                 const void* bias, cudaStream_t stream);
+int debug_read_timeline(unsigned long long* out, int max_words);
 bool gemm_tc_supported(const glb_linear& L, int64_t M);
 size_t gemm_tc_workspace(const glb_linear& L, int64_t M);
 int launch_gemm_tc(const glb_linear& L, const void* x, const float* scales_x, void* y, int64_t M,

@@ -201,25 +201,31 @@ gemm_a16w4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
       const int tn = t / P.tiles_m;
       const int n = tn * TC_BM + row;
+      // group walk without divisions: g / rem track k0 = kb*64 + half*32 as it advances by 64 per block
+      int g = (half * 32) / P.group_size, rem = (half * 32) % P.group_size;
       int cur_g = -1, pre_g = -1;
-      uint32_t s2 = 0, z2 = 0, ps2 = 0, pz2 = 0;
-      auto fetch = [&](int g, uint32_t& S2, uint32_t& Z2) {   // scale / zero of (group g, feature n), duplicated into a pair
-        const int64_t mi = (int64_t)g * P.N + n;
-        const uint32_t sv = sc_g[mi];
-        const uint32_t zv = (P.mode != 2) ? (uint32_t)zr_g[mi] : 0u;
-        S2 = sv | (sv << 16);
-        Z2 = zv | (zv << 16);
-      };
+      uint32_t s2 = 0, z2 = 0;
+      uint16_t psv = 0, pzv = 0;                           // raw prefetched scale / zero (consumed one block later)
+      auto dup = [](uint16_t v) { return (uint32_t)v | ((uint32_t)v << 16); };
       for (int kb = 0; kb < kblocks; ++kb) {
         const int k0 = kb * TC_BK + half * 32;
-        const int g = k0 / P.group_size;
         if (g != cur_g) {
-          if (g == pre_g) { s2 = ps2; z2 = pz2; } else fetch(g, s2, z2);
+          if (g == pre_g) { s2 = dup(psv); z2 = dup(pzv); }
+          else {
+            const int64_t mi = (int64_t)g * P.N + n;
+            s2 = dup(sc_g[mi]);
+            z2 = (P.mode != 2) ? dup(zr_g[mi]) : 0u;
+          }
           cur_g = g;
         }
-        if (kb + 1 < kblocks) {                            // prefetch the next block's metadata before blocking
-          const int gn = (k0 + TC_BK) / P.group_size;
-          if (gn != cur_g && gn != pre_g) { fetch(gn, ps2, pz2); pre_g = gn; }
+        // where the next block lands; issue its metadata loads now, touch the values only next iteration
+        int gn = g, remn = rem + TC_BK;
+        while (remn >= P.group_size) { remn -= P.group_size; ++gn; }
+        if (kb + 1 < kblocks && gn != cur_g && gn != pre_g) {
+          const int64_t mi = (int64_t)gn * P.N + n;
+          psv = sc_g[mi];
+          pzv = (P.mode != 2) ? zr_g[mi] : (uint16_t)0;
+          pre_g = gn;
         }
         ptx::mbar_wait(&full[s], ph);
         unsigned char* st = stage_base + s * S::STAGE;
@@ -234,7 +240,11 @@ gemm_a16w4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
           uint32_t ls2 = s2, lz2 = z2;
           if (P.group_size < 32) {                         // a 32-k span may cross groups only for gs = 8 / 16 / 24
             const int gg = (k0 + cc * 8) / P.group_size;
-            if (gg != cur_g) fetch(gg, ls2, lz2);
+            if (gg != cur_g) {
+              const int64_t mi = (int64_t)gg * P.N + n;
+              ls2 = dup(sc_g[mi]);
+              lz2 = (P.mode != 2) ? dup(zr_g[mi]) : 0u;
+            }
           }
           uint32_t q[4];
           unpack8<BF16>(w[cc], q);
@@ -249,6 +259,7 @@ gemm_a16w4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&aready[s]);
         if (++s == S::STAGES) { s = 0; ph ^= 1; }
+        g = gn; rem = remn;
       }
     }
   } else if (warp >= TC_EPI_WARP0) {

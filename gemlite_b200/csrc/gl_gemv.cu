@@ -25,6 +25,7 @@
 //    the group-wise factorisation of sum_k x_k * fma(q_k, s_g, z'_g), applied in fp32; bias fused.
 // The same kernel handles 1 <= M <= 16 rows of x (rows of the MMA A operand).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "gl_common.cuh"
 #include "gl_ptx.cuh"
@@ -405,13 +406,27 @@ int launch_w4(const GemvParams& P, cudaStream_t stream) {
 // =================================================================================================
 constexpr int GT_NCH = 4;   // weight chunks, one mbarrier each
 
+// diagnostics: per-launch phase timestamps (ns, %globaltimer) of CTA 0 / last CTA, warp 0 -- enabled by GLB_GEMV_DEBUG bit 2
+__device__ unsigned long long g_timeline[8192];
+__device__ unsigned int g_timeline_pos;
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 struct GemvTmaParams {
   const void* x; void* y; const void* bias;
   int K, N, M, group_size, mode;
+  int late_trigger;      // dependents are signalled 0: at kernel start, 1: after the main loop, 2: right after griddepcontrol.wait
+  int bulk1d;            // 1: descriptor-free cp.async.bulk row copies instead of tensor-map TMA for the weights
+  const uint32_t* W;     // (K/8, N) int32 (for bulk1d)
+  int chunk_shift;       // log2(rows per weight chunk)
+  int debug;             // diagnostics only: bit 0 skip the main loop, bit 1 skip the weight copies
 };
 
-template <bool BF16, int MT, int RPG, int KSPLIT, bool FAST>
-__global__ void __launch_bounds__(GV_THREADS, 4)
+template <bool BF16, int MT, int RPG, int KSPLIT, bool FAST, int NW>
+__global__ void __launch_bounds__(NW * 32, (NW == 8) ? 4 : 2)
 gemv_w4_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_s,
                    const __grid_constant__ CUtensorMap tmap_z, const GemvTmaParams P) {
   static_assert(MT <= 8, "one token block");
@@ -428,19 +443,23 @@ gemv_w4_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
   const int nch = (rows_c % (GT_NCH * rpg) == 0) ? GT_NCH : 1;
   const int chunk_rows = rows_c / nch;
 
-  // shared memory carve-up (all TMA destinations 128-byte aligned)
-  unsigned char* wbuf = smem_raw;                                        // rows_c x 128 B
+  // shared memory carve-up (weight buffer 1024-byte aligned: it is written by TMA with the 128B swizzle)
+  unsigned char* wbuf = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));  // rows_c x 128 B
   unsigned char* sbuf = wbuf + (size_t)rows_c * 128;                     // Gc x 64 B (padded to 128)
   unsigned char* zbuf = sbuf + (((size_t)Gc * 64 + 127) & ~(size_t)127);
   uint16_t* xs = reinterpret_cast<uint16_t*>(zbuf + (((size_t)Gc * 64 + 127) & ~(size_t)127));
   uint32_t* zero16 = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(xs) + (size_t)MT * Kc * 2);
   float* red = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(zero16) + 16);
-  float* peer = red + GV_WARPS * MT * GV_COLS;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(peer + MT * GV_COLS);     // [GT_NCH] weights, [GT_NCH] metadata
+  float* peer = red + NW * MT * GV_COLS;
+  float* gsum = peer + MT * GV_COLS;                                     // [MT][Gc][2] group sums of x
+  uint64_t* bars = reinterpret_cast<uint64_t*>(gsum + (size_t)MT * Gc * 2);   // [GT_NCH] weights, [1] metadata
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g8 = lane >> 2, t4 = lane & 3;
 
+  unsigned long long ts[8];
+  const bool rec = (P.debug & 4) && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1);
+  if (rec) ts[0] = gtimer();
   // ---- 1. weights + metadata -> shared memory by TMA (independent of the previous kernel) ----
   if (threadIdx.x == 0) {
     ptx::prefetch_tmap(&tmap_w);
@@ -451,22 +470,44 @@ gemv_w4_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
     ptx::mbar_arrive_expect_tx(&bars[GT_NCH], meta_bytes);
     ptx::tma_load_2d(sbuf, &tmap_s, &bars[GT_NCH], col0, gbeg);
     if (P.mode != 2) ptx::tma_load_2d(zbuf, &tmap_z, &bars[GT_NCH], col0, gbeg);
-    for (int c = 0; c < nch; ++c) {
+    for (int c = 0; c < ((P.debug & 2) ? 0 : nch); ++c) {
       ptx::mbar_arrive_expect_tx(&bars[c], (uint32_t)chunk_rows * 128u);
-      ptx::tma_load_2d(wbuf + (size_t)c * chunk_rows * 128, &tmap_w, &bars[c], col0, (kbeg >> 3) + c * chunk_rows);
+      if (!P.bulk1d) ptx::tma_load_2d(wbuf + (size_t)c * chunk_rows * 128, &tmap_w, &bars[c], col0, (kbeg >> 3) + c * chunk_rows);
     }
   }
-  pdl_launch_dependents();      // everything this CTA can do ahead of its input has been issued
+  if (P.bulk1d) {
+    // one 128-byte bulk copy per packed row, issued by as many threads as there are rows (no descriptor fetch)
+    __syncthreads();                                       // barrier init + expect_tx visible before any complete_tx
+    for (int r = threadIdx.x; r < rows_c; r += NW * 32) {
+      const uint32_t* src = P.W + (size_t)((kbeg >> 3) + r) * N + col0;
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       ptx::smem_u32(wbuf + (size_t)r * 128)),
+                   "l"(src), "r"(128u), "r"(ptx::smem_u32(&bars[r / chunk_rows]))
+                   : "memory");
+    }
+  }
+  if (P.late_trigger == 0) pdl_launch_dependents();  // everything this CTA can do ahead of its input has been issued
 
   // ---- 2. x depends on the previous kernel: wait for it only now, then stage it permuted ----
+  if (rec) ts[1] = gtimer();
   pdl_wait_prior_grids();
+  if (rec) ts[2] = gtimer();
+  if (P.late_trigger == 2) pdl_launch_dependents();  // prefetch depth 1: the next layer streams while this one computes
   {
+    // Each thread stages one 8-element word: permuted to {(k0,k4),(k1,k5),(k2,k6),(k3,k7)} (the B-fragment pairs
+    // matching nibbles_to_f16x2) and, in FAST mode, with the (k1,k5),(k3,k7) slots divided by 16.  The rpg
+    // consecutive threads of one group also reduce the group sums the epilogue needs:
+    //   gsum[.][0] = sum over slots that pair with 1024+n   (plain x)
+    //   gsum[.][1] = sum over slots that pair with 1024+16n (x/16 in FAST mode, plain x otherwise)
     const uint16_t* xg = reinterpret_cast<const uint16_t*>(P.x) + kbeg;
     const int words = Kc >> 3;
-    for (int i = threadIdx.x; i < MT * words; i += GV_THREADS) {
+    const int total = MT * words;
+    for (int i0 = 0; i0 < total; i0 += NW * 32) {
+      const int i = i0 + threadIdx.x;
+      const bool live = i < total;
       const int m = (MT == 1) ? 0 : (i / words), r = (MT == 1) ? i : (i - m * words);
       uint4 o = make_uint4(0u, 0u, 0u, 0u);
-      if (m < P.M) {
+      if (live && m < P.M) {
         const uint4 v = *reinterpret_cast<const uint4*>(xg + (size_t)m * K + (size_t)r * 8);
         o.x = __byte_perm(v.x, v.z, 0x5410);   // (k0,k4)
         o.y = __byte_perm(v.x, v.z, 0x7632);   // (k1,k5)
@@ -478,61 +519,91 @@ gemv_w4_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
           o.y = *reinterpret_cast<uint32_t*>(&a); o.w = *reinterpret_cast<uint32_t*>(&b2);
         }
       }
-      *reinterpret_cast<uint4*>(xs + (size_t)m * Kc + (size_t)r * 8) = o;
+      if (live) *reinterpret_cast<uint4*>(xs + (size_t)m * Kc + (size_t)r * 8) = o;
+      if (P.mode != 2 || FAST) {
+        float slo = cvt_meta<BF16>((uint16_t)(o.x & 0xffffu)) + cvt_meta<BF16>((uint16_t)(o.x >> 16)) +
+                    cvt_meta<BF16>((uint16_t)(o.z & 0xffffu)) + cvt_meta<BF16>((uint16_t)(o.z >> 16));
+        float shi = cvt_meta<BF16>((uint16_t)(o.y & 0xffffu)) + cvt_meta<BF16>((uint16_t)(o.y >> 16)) +
+                    cvt_meta<BF16>((uint16_t)(o.w & 0xffffu)) + cvt_meta<BF16>((uint16_t)(o.w >> 16));
+#pragma unroll
+        for (int off = rpg / 2; off > 0; off >>= 1) {          // rpg (4..32) consecutive lanes hold one group
+          slo += __shfl_xor_sync(0xffffffffu, slo, off);
+          shi += __shfl_xor_sync(0xffffffffu, shi, off);
+        }
+        if (live && (r % rpg) == 0) {
+          gsum[(m * Gc + r / rpg) * 2 + 0] = slo;
+          gsum[(m * Gc + r / rpg) * 2 + 1] = shi;
+        }
+      }
     }
     if (threadIdx.x < 4) zero16[threadIdx.x] = 0u;
   }
   __syncthreads();              // also publishes the mbarrier initialisation to every thread
+  if (rec) ts[3] = gtimer();
 
-  // ---- 3. main loop: warp w walks groups w, w + 8, ... of this CTA's K range ----
+  // ---- 3. main loop: warp w walks groups w, w + NW, ... of this CTA's K range ----
   float out[4][2];
 #pragma unroll
   for (int c = 0; c < 4; ++c) out[c][0] = out[c][1] = 0.f;
+  // Row assignment inside an 8-row block (two MMA "runs" a = 0, 1): lane t4 owns packed row 2*t4 + a.  With the
+  // TMA 128-byte swizzle (16-byte chunk index ^= row % 8) the 8 lanes of every quarter-warp then read 8 different
+  // chunks {g8, g8+1} ^ {a, 2+a, 4+a, 6+a}: conflict-free 128-bit shared-memory loads.  x is staged word-per-row,
+  // so the matching B fragment of the lane is word (block*8 + 2*t4 + a) of its token's row.
   const bool tok_ok = (g8 < MT);
-  const unsigned char* xb = tok_ok ? reinterpret_cast<const unsigned char*>(xs + (size_t)g8 * Kc) + t4 * 16
-                                   : reinterpret_cast<const unsigned char*>(zero16);
-  const int xst = tok_ok ? 64 : 0;
-  const unsigned char* wl = wbuf + t4 * 128 + g8 * 16;           // + run * 512
-  const uint32_t one2 = BF16 ? 0x3F803F80u : 0x3C003C00u;
-  const uint32_t ones_a[4] = {one2, one2, FAST ? 0x4C004C00u : one2, one2};
+  const unsigned char* xb = reinterpret_cast<const unsigned char*>(xs + (size_t)(tok_ok ? g8 : 0) * Kc) + (2 * t4) * 16;
+  const unsigned char* wl = wbuf + (2 * t4) * 128;
+  const int sw0 = (g8 ^ (2 * t4)) << 4, sw1 = (g8 ^ (2 * t4 + 1)) << 4;   // swizzled chunk offsets for a = 0 / 1
   ptx::mbar_wait(&bars[GT_NCH], 0);                               // scales / zeros landed
+  if (rec) ts[4] = gtimer();
 
-  for (int gl = warp; gl < Gc; gl += GV_WARPS) {
-    ptx::mbar_wait(&bars[(gl * rpg) / chunk_rows], 0);            // this group's weight chunk landed
-    float dacc[2][4], dsum[4];
+  for (int gl = warp; gl < ((P.debug & 1) ? 0 : Gc); gl += NW) {
+    if (!(P.debug & 2)) ptx::mbar_wait(&bars[(gl * rpg) >> P.chunk_shift], 0);   // this group's weight chunk landed
+    if (rec && gl == warp) ts[5] = gtimer();
+    // four independent accumulator chains per run: [column pair][k half]
+    float dacc[2][2][4];
 #pragma unroll
-    for (int pr = 0; pr < 2; ++pr) dacc[pr][0] = dacc[pr][1] = dacc[pr][2] = dacc[pr][3] = 0.f;
-    dsum[0] = dsum[1] = dsum[2] = dsum[3] = 0.f;
+    for (int pr = 0; pr < 2; ++pr)
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) dacc[pr][hh][0] = dacc[pr][hh][1] = dacc[pr][hh][2] = dacc[pr][hh][3] = 0.f;
 #pragma unroll
     for (int r = 0; r < RPG; ++r) {
-      const int run = gl * RPG + r;
-      const uint4 q = *reinterpret_cast<const uint4*>(wl + (size_t)run * 512);
-      const uint4 xv = *reinterpret_cast<const uint4*>(xb + (size_t)run * xst);
+      const int blk = gl * (RPG / 2) + (r >> 1), a = r & 1;            // 8-row block of this CTA's slice, half-run
+      const uint4 q = *reinterpret_cast<const uint4*>(wl + (size_t)blk * 1024 + a * 128 + (a ? sw1 : sw0));
+      uint4 xv = make_uint4(0u, 0u, 0u, 0u);
+      if (tok_ok) xv = *reinterpret_cast<const uint4*>(xb + (size_t)blk * 128 + a * 16);
       uint32_t ha[4], hb[4];
       nibbles_to_f16x2<BF16, FAST>(q.x, ha);
       nibbles_to_f16x2<BF16, FAST>(q.y, hb);
       {
         const uint32_t a0[4] = {ha[0], hb[0], ha[1], hb[1]}, a1[4] = {ha[2], hb[2], ha[3], hb[3]};
-        mma16816<BF16>(dacc[0], a0, xv.x, xv.y);
-        mma16816<BF16>(dacc[0], a1, xv.z, xv.w);
+        mma16816<BF16>(dacc[0][0], a0, xv.x, xv.y);
+        mma16816<BF16>(dacc[0][1], a1, xv.z, xv.w);
       }
       nibbles_to_f16x2<BF16, FAST>(q.z, ha);
       nibbles_to_f16x2<BF16, FAST>(q.w, hb);
       {
         const uint32_t a0[4] = {ha[0], hb[0], ha[1], hb[1]}, a1[4] = {ha[2], hb[2], ha[3], hb[3]};
-        mma16816<BF16>(dacc[1], a0, xv.x, xv.y);
-        mma16816<BF16>(dacc[1], a1, xv.z, xv.w);
-      }
-      if (P.mode != 2 || FAST) {
-        mma16816<BF16>(dsum, ones_a, xv.x, xv.y);
-        mma16816<BF16>(dsum, ones_a, xv.z, xv.w);
+        mma16816<BF16>(dacc[1][0], a0, xv.x, xv.y);
+        mma16816<BF16>(dacc[1][1], a1, xv.z, xv.w);
       }
     }
-    // ---- end of group: y += s * sum(x q) + z' * sum(x) ----
+    // ---- end of group: y += s * (sum(x q)) + z' * sum(x) ----
     const uint2 sw = *reinterpret_cast<const uint2*>(sbuf + (size_t)gl * 64 + g8 * 8);
     uint2 zw = make_uint2(0u, 0u);
     if (P.mode != 2) zw = *reinterpret_cast<const uint2*>(zbuf + (size_t)gl * 64 + g8 * 8);
     const uint32_t swa[2] = {sw.x, sw.y}, zwa[2] = {zw.x, zw.y};
+    float sx[2] = {0.f, 0.f}, off[2] = {0.f, 0.f};
+    if (P.mode != 2 || FAST) {
+#pragma unroll
+      for (int tk = 0; tk < 2; ++tk) {
+        const int m = 2 * t4 + tk;
+        if (m < MT) {
+          const float2 gs2 = *reinterpret_cast<const float2*>(&gsum[(m * Gc + gl) * 2]);
+          sx[tk] = FAST ? fmaf(16.f, gs2.y, gs2.x) : (gs2.x + gs2.y);     // sum_k x_k
+          off[tk] = FAST ? 1024.f * (gs2.x + gs2.y) : 0.f;                // 1024 * sum_k x'_k
+        }
+      }
+    }
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       const float sc = cvt_meta<BF16>((uint16_t)((c & 1) ? (swa[c >> 1] >> 16) : (swa[c >> 1] & 0xffffu)));
@@ -541,12 +612,14 @@ gemv_w4_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
       const int pr = c >> 1, hi = (c & 1) * 2;        // c0,c2 -> rows 0-7 (d0,d1) ; c1,c3 -> rows 8-15 (d2,d3)
 #pragma unroll
       for (int tk = 0; tk < 2; ++tk) {
-        const float off = FAST ? 1024.f * dsum[2 + tk] : 0.f;
-        out[c][tk] = fmaf(sc, dacc[pr][hi + tk] - off, fmaf(zc, dsum[tk], out[c][tk]));
+        const float d = dacc[pr][0][hi + tk] + dacc[pr][1][hi + tk];
+        out[c][tk] = fmaf(sc, d - off[tk], fmaf(zc, sx[tk], out[c][tk]));
       }
     }
   }
 
+  if (P.late_trigger == 1) pdl_launch_dependents();
+  if (rec) ts[6] = gtimer();
   // ---- 4. cross-warp reduction, cluster (split-K) reduction through DSMEM, epilogue ----
 #pragma unroll
   for (int tk = 0; tk < 2; ++tk) {
@@ -557,12 +630,20 @@ gemv_w4_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
     }
   }
   __syncthreads();
+  if (rec) {
+    ts[7] = gtimer();
+    const unsigned int pos = atomicAdd(&g_timeline_pos, 1u);
+    if (pos < 8192 / 9) {
+      g_timeline[pos * 9] = blockIdx.x;
+      for (int k = 0; k < 8; ++k) g_timeline[pos * 9 + 1 + k] = ts[k];
+    }
+  }
   float part = 0.f;
   const int i = threadIdx.x;
   if (i < MT * GV_COLS) {
     const int m = i / GV_COLS, c = i - m * GV_COLS;
 #pragma unroll
-    for (int w = 0; w < GV_WARPS; ++w) part += red[(w * MT + m) * GV_COLS + c];
+    for (int w = 0; w < NW; ++w) part += red[(w * MT + m) * GV_COLS + c];
     if (KSPLIT > 1 && rank != 0) st_cluster_f32(&peer[i], 0u, part);
   }
   if (KSPLIT > 1) cluster_sync_all();
@@ -577,20 +658,20 @@ gemv_w4_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
   }
 }
 
-template <int MT, int KSPLIT> size_t gemv_tma_smem_bytes(int K, int group_size) {
+template <int MT, int KSPLIT, int NW> size_t gemv_tma_smem_bytes(int K, int group_size) {
   const int Kc = K / KSPLIT, Gc = K / group_size / KSPLIT;
   const size_t meta = ((size_t)Gc * 64 + 127) & ~(size_t)127;
-  return (size_t)(Kc / 8) * 128 + 2 * meta + (size_t)MT * Kc * 2 + 16 + (size_t)GV_WARPS * MT * GV_COLS * 4 +
-         (size_t)MT * GV_COLS * 4 + (GT_NCH + 1) * 8 + 128;
+  return (size_t)(Kc / 8) * 128 + 2 * meta + (size_t)MT * Kc * 2 + 16 + (size_t)NW * MT * GV_COLS * 4 +
+         (size_t)MT * GV_COLS * 4 + (size_t)MT * Gc * 8 + (GT_NCH + 1) * 8 + 128 + 1024;
 }
 
-template <bool BF16, int MT, int RPG, int KSPLIT, bool FAST>
-int launch_w4_tma(const glb_linear& L, const GemvParams& P0, cudaStream_t stream) {
+template <bool BF16, int MT, int RPG, int KSPLIT, bool FAST, int NW>
+int launch_w4_tma(const glb_linear& L, const GemvParams& P0, int late_trigger, cudaStream_t stream) {
   const int Kc = P0.K / KSPLIT, Gc = P0.K / P0.group_size / KSPLIT, rows_c = Kc / 8;
   constexpr int rpg = RPG * 4;
   const int nch = (rows_c % (GT_NCH * rpg) == 0) ? GT_NCH : 1;
   CUtensorMap tw, ts, tz;
-  int rc = make_tmap_2d(&tw, GLB_INT32, L.W_q, (uint64_t)L.N, (uint64_t)(L.K / 8), (uint64_t)L.N * 4, GV_COLS, rows_c / nch, 0);
+  int rc = make_tmap_2d(&tw, GLB_INT32, L.W_q, (uint64_t)L.N, (uint64_t)(L.K / 8), (uint64_t)L.N * 4, GV_COLS, rows_c / nch, 1);
   if (rc != GLB_OK) return rc;
   rc = make_tmap_2d(&ts, GLB_FP16, L.scales, (uint64_t)L.N, (uint64_t)(L.K / L.group_size), (uint64_t)L.N * 2, GV_COLS, Gc, 0);
   if (rc != GLB_OK) return rc;
@@ -599,8 +680,19 @@ int launch_w4_tma(const glb_linear& L, const GemvParams& P0, cudaStream_t stream
   if (rc != GLB_OK) return rc;
   GemvTmaParams P;
   P.x = P0.x; P.y = P0.y; P.bias = P0.bias; P.K = P0.K; P.N = P0.N; P.M = P0.M; P.group_size = P0.group_size; P.mode = P0.mode;
-  const size_t smem = gemv_tma_smem_bytes<MT, KSPLIT>(P0.K, P0.group_size);
-  auto kern = gemv_w4_tma_kernel<BF16, MT, RPG, KSPLIT, FAST>;
+  P.late_trigger = late_trigger % 10;
+  P.bulk1d = late_trigger / 10;
+  P.W = reinterpret_cast<const uint32_t*>(L.W_q);
+  {
+    int cr = rows_c / nch, sh = 0;
+    while ((1 << sh) < cr) ++sh;
+    P.chunk_shift = sh;
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("GLB_GEMV_DEBUG"); dbg = e ? atoi(e) : 0; }
+    P.debug = dbg;
+  }
+  const size_t smem = gemv_tma_smem_bytes<MT, KSPLIT, NW>(P0.K, P0.group_size);
+  auto kern = gemv_w4_tma_kernel<BF16, MT, RPG, KSPLIT, FAST, NW>;
   if (smem > 48 * 1024) {
     static thread_local size_t configured = 0;
     if (configured < smem) {
@@ -610,7 +702,7 @@ int launch_w4_tma(const glb_linear& L, const GemvParams& P0, cudaStream_t stream
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(P0.N / GV_COLS) * KSPLIT);
-  cfg.blockDim = dim3(GV_THREADS);
+  cfg.blockDim = dim3(NW * 32);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
@@ -632,6 +724,18 @@ int launch_w4_tma(const glb_linear& L, const GemvParams& P0, cudaStream_t stream
   return GLB_OK;
 }
 
+// Kernel flavour (GLB_GEMV_VARIANT, read once): 3 = register prefetch + 2-CTA cluster; 4 = TMA + 2-CTA cluster,
+// 256 threads (default); 41 = same with the dependent-launch trigger after the main loop; 5 / 51 = TMA, one
+// 512-thread CTA per slab over the full K (exactly two CTAs per SM), early / late trigger.
+int gemv_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GLB_GEMV_VARIANT");
+    v = e ? atoi(e) : 52;
+  }
+  return v;
+}
+
 // shapes the TMA flavour takes: <= 8 tokens, the CTA's weight slice fits 64 KB of shared memory
 bool gemv_tma_ok(const GemvParams& P, int ksplit) {
   const int Kc = P.K / ksplit, Gc = P.K / P.group_size / ksplit;
@@ -640,6 +744,9 @@ bool gemv_tma_ok(const GemvParams& P, int ksplit) {
   const int rows_c = Kc / 8, rpg = P.group_size / 8;
   const int nch = (rows_c % (GT_NCH * rpg) == 0) ? GT_NCH : 1;
   if (rows_c / nch > 256) return false;
+  const int cr = rows_c / nch;
+  if (cr & (cr - 1)) return false;                     // chunk index is a shift
+  if (rpg % 8 != 0 || cr % 8 != 0) return false;       // swizzled 8-row blocks must not straddle groups / chunks
   return true;
 }
 
@@ -654,10 +761,15 @@ int dispatch_w4(const glb_linear& L, const GemvParams& P, cudaStream_t stream) {
     constexpr bool F = !BF16 && GLB_GEMV_FAST;                                                        \
     constexpr int MT8 = (MT <= 8) ? MT : 8;                                                           \
     const bool split = (G % (2 * GPB) == 0 && P.N / GV_COLS < 296);                                   \
-    if (MT <= 8 && GLB_GEMV_TMA && (reinterpret_cast<uintptr_t>(L.scales) & 15) == 0 &&               \
+    const int variant = gemv_variant();                                                               \
+    if (MT <= 8 && variant != 3 && (reinterpret_cast<uintptr_t>(L.scales) & 15) == 0 &&               \
         (P.mode == 2 || (reinterpret_cast<uintptr_t>(L.zeros) & 15) == 0) && (P.N * 2) % 16 == 0) {   \
-      if (split && gemv_tma_ok(P, 2)) return launch_w4_tma<BF16, MT8, RPG, 2, F>(L, P, stream);       \
-      if (gemv_tma_ok(P, 1)) return launch_w4_tma<BF16, MT8, RPG, 1, F>(L, P, stream);                \
+      /* x1: late trigger, x2: trigger after wait, x3: bulk1d + trigger after wait */               \
+      const int late = (variant % 10 == 1 && variant > 10) ? 1 : ((variant % 10 == 2 && variant > 10) ? 2 : ((variant % 10 == 3 && variant > 10) ? 12 : 0)); \
+      if ((variant == 5 || variant / 10 == 5) && gemv_tma_ok(P, 1))                                   \
+        return launch_w4_tma<BF16, MT8, RPG, 1, F, 16>(L, P, late, stream);                           \
+      if (split && gemv_tma_ok(P, 2)) return launch_w4_tma<BF16, MT8, RPG, 2, F, 8>(L, P, late, stream); \
+      if (gemv_tma_ok(P, 1)) return launch_w4_tma<BF16, MT8, RPG, 1, F, 8>(L, P, late, stream);       \
     }                                                                                                 \
     if (split) return launch_w4<BF16, MT, RPG, 2, F>(P, stream);                                      \
     return launch_w4<BF16, MT, RPG, 1, F>(P, stream);                                                 \
@@ -675,6 +787,18 @@ int dispatch_w4(const glb_linear& L, const GemvParams& P, cudaStream_t stream) {
 }
 
 }  // namespace
+
+int debug_read_timeline(unsigned long long* out, int max_words) {
+  unsigned int n = 0;
+  GLB_CHECK_CUDA(cudaMemcpyFromSymbol(&n, g_timeline_pos, sizeof(n)));
+  int words = (int)n * 9;
+  if (words > max_words) words = max_words;
+  if (words > 8192) words = 8192;
+  if (words > 0) GLB_CHECK_CUDA(cudaMemcpyFromSymbol(out, g_timeline, (size_t)words * 8));
+  n = 0;
+  GLB_CHECK_CUDA(cudaMemcpyToSymbol(g_timeline_pos, &n, sizeof(n)));
+  return words;
+}
 
 bool gemv_supported(const glb_linear& L, int64_t M) {
   if (M < 1 || M > 16) return false;

@@ -148,6 +148,10 @@ GLB_API int glb_matmul(const glb_linear* layer, const void* x, const void* scale
 GLB_API void glb_set_pdl(int enabled);
 GLB_API int glb_get_pdl(void);
 
+/* Diagnostics (GLB_GEMV_DEBUG=4): copies the decode kernel's recorded phase timestamps (9 x uint64 per record:
+ * CTA index, then 8 %globaltimer stamps in ns) to host memory `out`, clears the buffer, returns the word count. */
+GLB_API int glb_debug_timeline(unsigned long long* out, int max_words);
+
 #ifdef __cplusplus
 }
 #endif
