@@ -109,9 +109,11 @@ template <bool BF16, int BT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_a16w4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const TcParams P) {
   using S = TcSmem<BT>;
-  extern __shared__ unsigned char smem_raw[];
-  // 1024-byte alignment for the 128B swizzle atoms
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment for the 128B swizzle atoms.  (No pointer round-trip through an integer here: that
+  // would lose the shared address space and turn every LDS/STS below into generic LD/ST.)
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw;
+  if ((ptx::smem_u32(smem_raw) & 1023u) != 0u) __trap();
   unsigned char* stage_base = smem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::STAGES * S::STAGE);
   uint64_t* full = bars;                       // [STAGES]  TMA landed (x + packed)
@@ -345,8 +347,9 @@ __global__ void __launch_bounds__(T8_THREADS, 1)
 gemm_a8w8_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const T8Params P,
                     const uint32_t idesc) {
   using S = T8Smem<BT>;
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw;
+  if ((ptx::smem_u32(smem_raw) & 1023u) != 0u) __trap();
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::STAGES * S::STAGE);
   uint64_t* full = bars;
   uint64_t* empty = bars + S::STAGES;

@@ -40,6 +40,9 @@ constexpr int GV_R = 8;            // uint4 loads a lane keeps in flight per bat
 #ifndef GLB_GEMV_FAST
 #define GLB_GEMV_FAST 1            // 1: offset-carrying nibble unpack (no subtract), fp16 only
 #endif
+#ifndef GLB_GEMV_TIMELINE
+#define GLB_GEMV_TIMELINE 0        // 1: record %globaltimer phase stamps (tools/decode_timeline.py)
+#endif
 #ifndef GLB_GEMV_TMA
 #define GLB_GEMV_TMA 1             // 1: weights via TMA into shared memory (co-resident layers under PDL)
 #endif
@@ -431,7 +434,7 @@ gemv_w4_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
                    const __grid_constant__ CUtensorMap tmap_z, const GemvTmaParams P) {
   static_assert(MT <= 8, "one token block");
   static_assert(!(BF16 && FAST), "the offset-carrying unpack needs fp16's 10-bit mantissa");
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
   constexpr int rpg = RPG * 4;                     // packed rows per group
   const int K = P.K, N = P.N;
   const int G = K / P.group_size;
@@ -444,7 +447,8 @@ gemv_w4_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
   const int chunk_rows = rows_c / nch;
 
   // shared memory carve-up (weight buffer 1024-byte aligned: it is written by TMA with the 128B swizzle)
-  unsigned char* wbuf = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));  // rows_c x 128 B
+  unsigned char* wbuf = smem_raw;                                        // rows_c x 128 B (no integer round-trip: keeps LDS)
+  if ((ptx::smem_u32(smem_raw) & 1023u) != 0u) __trap();
   unsigned char* sbuf = wbuf + (size_t)rows_c * 128;                     // Gc x 64 B (padded to 128)
   unsigned char* zbuf = sbuf + (((size_t)Gc * 64 + 127) & ~(size_t)127);
   uint16_t* xs = reinterpret_cast<uint16_t*>(zbuf + (((size_t)Gc * 64 + 127) & ~(size_t)127));
@@ -457,9 +461,14 @@ gemv_w4_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g8 = lane >> 2, t4 = lane & 3;
 
+#if GLB_GEMV_TIMELINE
   unsigned long long ts[8];
   const bool rec = (P.debug & 4) && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1);
-  if (rec) ts[0] = gtimer();
+#else
+  unsigned long long ts[1];
+  constexpr bool rec = false;
+#endif
+  if (rec) ts[GLB_GEMV_TIMELINE ? 0 : 0] = gtimer();
   // ---- 1. weights + metadata -> shared memory by TMA (independent of the previous kernel) ----
   if (threadIdx.x == 0) {
     ptx::prefetch_tmap(&tmap_w);
@@ -489,9 +498,9 @@ gemv_w4_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
   if (P.late_trigger == 0) pdl_launch_dependents();  // everything this CTA can do ahead of its input has been issued
 
   // ---- 2. x depends on the previous kernel: wait for it only now, then stage it permuted ----
-  if (rec) ts[1] = gtimer();
+  if (rec) ts[GLB_GEMV_TIMELINE ? 1 : 0] = gtimer();
   pdl_wait_prior_grids();
-  if (rec) ts[2] = gtimer();
+  if (rec) ts[GLB_GEMV_TIMELINE ? 2 : 0] = gtimer();
   if (P.late_trigger == 2) pdl_launch_dependents();  // prefetch depth 1: the next layer streams while this one computes
   {
     // Each thread stages one 8-element word: permuted to {(k0,k4),(k1,k5),(k2,k6),(k3,k7)} (the B-fragment pairs
@@ -539,7 +548,7 @@ gemv_w4_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
     if (threadIdx.x < 4) zero16[threadIdx.x] = 0u;
   }
   __syncthreads();              // also publishes the mbarrier initialisation to every thread
-  if (rec) ts[3] = gtimer();
+  if (rec) ts[GLB_GEMV_TIMELINE ? 3 : 0] = gtimer();
 
   // ---- 3. main loop: warp w walks groups w, w + NW, ... of this CTA's K range ----
   float out[4][2];
@@ -554,11 +563,11 @@ gemv_w4_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
   const unsigned char* wl = wbuf + (2 * t4) * 128;
   const int sw0 = (g8 ^ (2 * t4)) << 4, sw1 = (g8 ^ (2 * t4 + 1)) << 4;   // swizzled chunk offsets for a = 0 / 1
   ptx::mbar_wait(&bars[GT_NCH], 0);                               // scales / zeros landed
-  if (rec) ts[4] = gtimer();
+  if (rec) ts[GLB_GEMV_TIMELINE ? 4 : 0] = gtimer();
 
   for (int gl = warp; gl < ((P.debug & 1) ? 0 : Gc); gl += NW) {
     if (!(P.debug & 2)) ptx::mbar_wait(&bars[(gl * rpg) >> P.chunk_shift], 0);   // this group's weight chunk landed
-    if (rec && gl == warp) ts[5] = gtimer();
+    if (rec && gl == warp) ts[GLB_GEMV_TIMELINE ? 5 : 0] = gtimer();
     // four independent accumulator chains per run: [column pair][k half]
     float dacc[2][2][4];
 #pragma unroll
@@ -619,7 +628,7 @@ gemv_w4_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
   }
 
   if (P.late_trigger == 1) pdl_launch_dependents();
-  if (rec) ts[6] = gtimer();
+  if (rec) ts[GLB_GEMV_TIMELINE ? 6 : 0] = gtimer();
   // ---- 4. cross-warp reduction, cluster (split-K) reduction through DSMEM, epilogue ----
 #pragma unroll
   for (int tk = 0; tk < 2; ++tk) {
@@ -631,11 +640,11 @@ gemv_w4_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
   }
   __syncthreads();
   if (rec) {
-    ts[7] = gtimer();
+    ts[GLB_GEMV_TIMELINE ? 7 : 0] = gtimer();
     const unsigned int pos = atomicAdd(&g_timeline_pos, 1u);
     if (pos < 8192 / 9) {
       g_timeline[pos * 9] = blockIdx.x;
-      for (int k = 0; k < 8; ++k) g_timeline[pos * 9 + 1 + k] = ts[k];
+      for (int k = 0; k < (GLB_GEMV_TIMELINE ? 8 : 1); ++k) g_timeline[pos * 9 + 1 + k] = ts[k];
     }
   }
   float part = 0.f;
