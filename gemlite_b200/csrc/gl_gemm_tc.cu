@@ -18,6 +18,7 @@
 //     the MMA lane issues 4 x tcgen05.mma (K=16) and commits to the stage's "empty" barrier.
 //   * persistent: grid = #SMs, tiles are walked token-block-fastest so CTAs running together share
 //     the same weight tile in L2.
+#include <stdlib.h>
 #include <mutex>
 #include <unordered_map>
 
@@ -598,6 +599,13 @@ int launch_gemm_tc(const glb_linear& L, const void* x, const float* scales_x, vo
 #undef GLB_T8
   }
   const bool bf = (L.input_dtype == GLB_BF16);
+  {
+    // large M: CTA-pair kernel with the weight operand in tensor memory (gl_gemm_tc2.cu); GLB_PREFILL_VARIANT=1 keeps
+    // the single-CTA kernel below for A/B comparisons
+    static int variant = -1;
+    if (variant < 0) { const char* e = getenv("GLB_PREFILL_VARIANT"); variant = e ? atoi(e) : 2; }
+    if (variant != 1 && M > 128 && gemm_tc2_supported(L, M)) return launch_gemm_tc2(L, x, y, M, bias, stream);
+  }
   set_kernel_name("gemm_a16w4_tcgen05");
   if (M <= 32) return bf ? launch_tc<true, 32>(L, x, y, M, bias, stream) : launch_tc<false, 32>(L, x, y, M, bias, stream);
   if (M <= 64) return bf ? launch_tc<true, 64>(L, x, y, M, bias, stream) : launch_tc<false, 64>(L, x, y, M, bias, stream);

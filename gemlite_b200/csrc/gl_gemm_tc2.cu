@@ -1,0 +1,354 @@
+// tcgen05 prefill GEMM, CTA-pair flavour (cta_group::2) with the dequantised weights fed to the tensor core
+// from TENSOR MEMORY -- the large-M path of A16W4 (rows a9/a10, config C3).
+//
+// Why (profiles/prefill_r1_ncu.txt): the single-CTA kernel in gl_gemm_tc.cu keeps the tensor pipe only ~49 %
+// busy because the shared-memory data pipe is saturated: per 64-wide k-block a CTA moves 48 KB of operand
+// reads (A 16 KB + B 32 KB), 36 KB of TMA writes and 16 KB (x2 bank conflicts) of dequant stores = ~93 % of the
+// 128 B/clk port.  Here
+//   * a CTA PAIR owns a 256-feature x 256-token tile: tcgen05.mma.cta_group::2, M = 256 (128 TMEM lanes per
+//     CTA), N = 256; each CTA stages only ITS 128 tokens of the x tile (16 KB / k-block) and the tensor cores
+//     of both SMs read both halves -> B traffic per CTA halves;
+//   * the dequantised weight tile never touches shared memory: dequant thread == feature row == TMEM lane,
+//     16 packed pairs per thread go to tensor memory with one tcgen05.st.32x32b.x16 and the MMA takes its A
+//     operand from there ([a_tmem] form).  No STS, no bank conflicts, no async-proxy fence;
+//   * shared memory per stage is 20 KB (x half-tile + 4 KB packed words) -> an 8-deep TMA ring, matching the
+//     8 x 32-column A ring in TMEM (256 columns) next to the 256-column fp32 accumulator.
+// Shared-memory traffic per CTA and k-block: 16 KB operand reads + 20 KB TMA writes + 4 KB packed reads.
+//
+// Arithmetic contract is unchanged (see gl_gemm_tc.cu): weights are dequantised with the reference's rounding
+// (utils.py:57-89) and accumulated in fp32 by the tensor core (gemm_kernels.py:384).
+//
+// Warp roles per CTA (512 threads): w0 TMA producer, w1 MMA issuer (leader CTA only), w2 TMEM allocator,
+// w4-11 dequant (warp % 4 = TMEM lane quarter, (warp-4)/4 = which 32-k half of the k-block), w12-15 epilogue.
+// Barriers: xfull / aready / tempty live in the LEADER's shared memory (the peer reports to them remotely);
+// wfull / empty / tfull are per CTA; tcgen05.commit multicasts its arrival to both CTAs.
+#include "gl_common.cuh"
+#include "gl_ptx.cuh"
+
+namespace glb {
+namespace {
+
+constexpr int T2_BM = 128;            // features per CTA (256 per pair)
+constexpr int T2_BT = 256;            // tokens per pair tile (128 staged per CTA)
+constexpr int T2_BK = 64;
+constexpr int T2_STAGES = 8;
+constexpr int T2_THREADS = 512;
+constexpr int T2_DEQ_WARP0 = 4, T2_DEQ_WARPS = 8, T2_EPI_WARP0 = 12;
+constexpr int T2_X_BYTES = (T2_BT / 2) * T2_BK * 2;        // 16 KB
+constexpr int T2_P_BYTES = (T2_BK / 8) * T2_BM * 4;        // 4 KB
+constexpr int T2_STAGE = T2_X_BYTES + T2_P_BYTES;
+constexpr int T2_SMEM = T2_STAGES * T2_STAGE + 1024 /* barriers */ + 1024 /* alignment slack */;
+constexpr uint32_t T2_ACOL0 = 256;    // first TMEM column of the A ring (accumulator: columns 0..255)
+
+struct Tc2Params {
+  const void* scales;
+  const void* zeros;
+  void* y;
+  const void* bias;
+  int M, N, K;
+  int group_size;
+  int mode;
+  int tiles_m;            // 256-token blocks
+  int tiles_n;            // 256-feature blocks
+};
+
+template <bool BF16> __device__ __forceinline__ void unpack8_nat(uint32_t q, uint32_t (&o)[4]) {
+  // 8 nibbles -> exact integers as 16-bit floats in natural k order: o[i] = (k_{2i}, k_{2i+1})
+  uint32_t h[4];
+  if (!BF16) {
+    const uint32_t t = q >> 8;
+    uint32_t m0, m1, m2, m3;
+    asm("lop3.b32 %0, %1, 0x000F000F, 0x64006400, 0xEA;" : "=r"(m0) : "r"(q));
+    asm("lop3.b32 %0, %1, 0x00F000F0, 0x64006400, 0xEA;" : "=r"(m1) : "r"(q));
+    asm("lop3.b32 %0, %1, 0x000F000F, 0x64006400, 0xEA;" : "=r"(m2) : "r"(t));
+    asm("lop3.b32 %0, %1, 0x00F000F0, 0x64006400, 0xEA;" : "=r"(m3) : "r"(t));
+    const __half2 k1024 = __half2half2(__ushort_as_half((unsigned short)0x6400));
+    const __half2 k16th = __half2half2(__ushort_as_half((unsigned short)0x2C00));
+    const __half2 km64 = __half2half2(__ushort_as_half((unsigned short)0xD400));
+    __half2 r0 = __hsub2(*reinterpret_cast<__half2*>(&m0), k1024);           // (k0,k4)
+    __half2 r1 = __hfma2(*reinterpret_cast<__half2*>(&m1), k16th, km64);      // (k1,k5)
+    __half2 r2 = __hsub2(*reinterpret_cast<__half2*>(&m2), k1024);           // (k2,k6)
+    __half2 r3 = __hfma2(*reinterpret_cast<__half2*>(&m3), k16th, km64);      // (k3,k7)
+    h[0] = *reinterpret_cast<uint32_t*>(&r0); h[1] = *reinterpret_cast<uint32_t*>(&r1);
+    h[2] = *reinterpret_cast<uint32_t*>(&r2); h[3] = *reinterpret_cast<uint32_t*>(&r3);
+  } else {
+    const __nv_bfloat162 k128 = __bfloat162bfloat162(__ushort_as_bfloat16((unsigned short)0x4300));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint32_t v;
+      asm("lop3.b32 %0, %1, 0x000F000F, 0x43004300, 0xEA;" : "=r"(v) : "r"(q >> (4 * i)));
+      __nv_bfloat162 r = __hsub2(*reinterpret_cast<__nv_bfloat162*>(&v), k128);   // (k_i, k_{i+4})
+      h[i] = *reinterpret_cast<uint32_t*>(&r);
+    }
+  }
+  o[0] = __byte_perm(h[0], h[1], 0x5410);   // (k0,k1)
+  o[1] = __byte_perm(h[2], h[3], 0x5410);   // (k2,k3)
+  o[2] = __byte_perm(h[0], h[1], 0x7632);   // (k4,k5)
+  o[3] = __byte_perm(h[2], h[3], 0x7632);   // (k6,k7)
+}
+
+template <bool BF16> __device__ __forceinline__ uint32_t dequant2_ref(uint32_t q2, uint32_t s2, uint32_t z2, int mode) {
+  if (!BF16) {
+    const __half2 q = *reinterpret_cast<__half2*>(&q2), s = *reinterpret_cast<__half2*>(&s2), z = *reinterpret_cast<__half2*>(&z2);
+    __half2 r = (mode == 4) ? __hfma2(q, s, z) : ((mode == 3) ? __hmul2(__hsub2(q, z), s) : __hmul2(q, s));
+    return *reinterpret_cast<uint32_t*>(&r);
+  } else {
+    const __nv_bfloat162 q = *reinterpret_cast<__nv_bfloat162*>(&q2), s = *reinterpret_cast<__nv_bfloat162*>(&s2),
+                         z = *reinterpret_cast<__nv_bfloat162*>(&z2);
+    __nv_bfloat162 r = (mode == 4) ? __hfma2(q, s, z) : ((mode == 3) ? __hmul2(__hsub2(q, z), s) : __hmul2(q, s));
+    return *reinterpret_cast<uint32_t*>(&r);
+  }
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(T2_THREADS, 1)
+gemm_a16w4_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const Tc2Params P) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw;
+  if ((ptx::smem_u32(smem_raw) & 1023u) != 0u) __trap();
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + T2_STAGES * T2_STAGE);
+  uint64_t* xfull = bars;                       // [STAGES] leader: both x half-tiles landed
+  uint64_t* wfull = bars + T2_STAGES;           // [STAGES] local : packed words landed
+  uint64_t* aready = bars + 2 * T2_STAGES;      // [STAGES] leader: both CTAs' dequant warps wrote A slot s
+  uint64_t* empty = bars + 3 * T2_STAGES;       // [STAGES] local : MMAs reading stage s completed (multicast commit)
+  uint64_t* tfull = bars + 4 * T2_STAGES;       // [1]      local : accumulator complete (multicast commit)
+  uint64_t* tempty = bars + 4 * T2_STAGES + 1;  // [1]      leader: both CTAs' epilogue warps drained it
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * T2_STAGES + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = (rank == 0);
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int kblocks = P.K / T2_BK;
+  const int ntiles = P.tiles_m * P.tiles_n;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_x);
+    ptx::prefetch_tmap(&tmap_w);
+    for (int s = 0; s < T2_STAGES; ++s) {
+      ptx::mbar_init(&xfull[s], 1);
+      ptx::mbar_init(&wfull[s], 1);
+      ptx::mbar_init(&aready[s], 2 * T2_DEQ_WARPS);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    ptx::mbar_init(tfull, 1);
+    ptx::mbar_init(tempty, 2 * 4);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) ptx::tmem_alloc_2cta(tmem_slot, 512);
+  ptx::tc_fence_before_sync();
+  ptx::cluster_sync();                 // barrier inits of BOTH CTAs visible before any remote arrival / TMA completion
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer (one lane in each CTA) =================
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int t = pair; t < ntiles; t += npairs) {
+        const int tm = t % P.tiles_m, tn = t / P.tiles_m;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          ptx::mbar_wait(&empty[s], ph ^ 1);
+          unsigned char* st = smem + s * T2_STAGE;
+          if (leader) ptx::mbar_arrive_expect_tx(&xfull[s], 2 * T2_X_BYTES);
+          ptx::tma_load_2d_2cta(st, &tmap_x, ptx::mapa(ptx::smem_u32(&xfull[s]), 0u), kb * T2_BK,
+                                tm * T2_BT + (int)rank * (T2_BT / 2));
+          ptx::mbar_arrive_expect_tx(&wfull[s], T2_P_BYTES);
+          ptx::tma_load_2d(st + T2_X_BYTES, &tmap_w, &wfull[s], tn * 2 * T2_BM + (int)rank * T2_BM, kb * (T2_BK / 8));
+          if (++s == T2_STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (leader CTA, one elected lane) =================
+    if (leader) {
+      constexpr uint32_t idesc = ptx::make_idesc(1u, BF16 ? 1u : 0u, BF16 ? 1u : 0u, 2 * T2_BM, T2_BT);
+      int s = 0; uint32_t ph = 0;
+      int it = 0;
+      for (int t = pair; t < ntiles; t += npairs, ++it) {
+        ptx::mbar_wait(tempty, (uint32_t)(it & 1) ^ 1u);      // epilogue of the previous tile drained the accumulator
+        ptx::tc_fence_after_sync();
+        for (int kb = 0; kb < kblocks; ++kb) {
+          ptx::mbar_wait(&xfull[s], ph);
+          ptx::mbar_wait(&aready[s], ph);
+          ptx::tc_fence_after_sync();
+          if (ptx::elect_one()) {
+            const uint64_t bdesc = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + s * T2_STAGE));
+            const uint32_t a_tmem = tmem_base + T2_ACOL0 + (uint32_t)s * 32u;
+#pragma unroll
+            for (int k = 0; k < T2_BK / 16; ++k)     // K = 16 per instruction: 8 TMEM columns of A, 32 bytes of each B row
+              ptx::mma_f16_ts_2cta(tmem_base, a_tmem + (uint32_t)(8 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+            ptx::mma_commit_2cta(&empty[s], (uint16_t)3);
+            if (kb == kblocks - 1) ptx::mma_commit_2cta(tfull, (uint16_t)3);
+          }
+          __syncwarp();
+          if (++s == T2_STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= T2_DEQ_WARP0 && warp < T2_DEQ_WARP0 + T2_DEQ_WARPS) {
+    // ================= dequant: thread == feature row == TMEM lane; 4 packed words (32 k) per thread =================
+    const int q4 = warp & 3;                                // TMEM lane quarter this warp may touch
+    const int row = q4 * 32 + lane;                         // feature row inside this CTA's 128
+    const int half = (warp - T2_DEQ_WARP0) >> 2;            // which 32-k half of the 64-k block
+    const uint16_t* sc_g = reinterpret_cast<const uint16_t*>(P.scales);
+    const uint16_t* zr_g = reinterpret_cast<const uint16_t*>(P.zeros);
+    const uint32_t taddr0 = tmem_base + ((uint32_t)(q4 * 32) << 16) + T2_ACOL0 + (uint32_t)half * 16u;
+    const uint32_t aready_leader = ptx::mapa(ptx::smem_u32(&aready[0]), 0u);
+    int s = 0; uint32_t ph = 0;
+    for (int t = pair; t < ntiles; t += npairs) {
+      const int tn = t / P.tiles_m;
+      const int n = tn * 2 * T2_BM + (int)rank * T2_BM + row;
+      int g = (half * 32) / P.group_size, rem = (half * 32) % P.group_size;
+      int cur_g = -1, pre_g = -1;
+      uint32_t s2 = 0, z2 = 0;
+      uint16_t psv = 0, pzv = 0;
+      auto dup = [](uint16_t v) { return (uint32_t)v | ((uint32_t)v << 16); };
+      for (int kb = 0; kb < kblocks; ++kb) {
+        const int k0 = kb * T2_BK + half * 32;
+        if (g != cur_g) {
+          if (g == pre_g) { s2 = dup(psv); z2 = dup(pzv); }
+          else {
+            const int64_t mi = (int64_t)g * P.N + n;
+            s2 = dup(sc_g[mi]);
+            z2 = (P.mode != 2) ? dup(zr_g[mi]) : 0u;
+          }
+          cur_g = g;
+        }
+        int gn = g, remn = rem + T2_BK;
+        while (remn >= P.group_size) { remn -= P.group_size; ++gn; }
+        if (kb + 1 < kblocks && gn != cur_g && gn != pre_g) {      // next block's metadata: issue now, use next iteration
+          const int64_t mi = (int64_t)gn * P.N + n;
+          psv = sc_g[mi];
+          pzv = (P.mode != 2) ? zr_g[mi] : (uint16_t)0;
+          pre_g = gn;
+        }
+        ptx::mbar_wait(&wfull[s], ph);      // also implies: the MMAs that last read A slot s have completed (producer waited on empty[s])
+        const uint32_t* pk = reinterpret_cast<const uint32_t*>(smem + s * T2_STAGE + T2_X_BYTES);
+        uint32_t w[4];
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) w[cc] = pk[(half * 4 + cc) * T2_BM + row];
+        uint32_t o[16];
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          uint32_t ls2 = s2, lz2 = z2;
+          if (P.group_size < 32) {                         // a 32-k span may cross groups only for gs = 8 / 16 / 24
+            const int gg = (k0 + cc * 8) / P.group_size;
+            if (gg != cur_g) {
+              const int64_t mi = (int64_t)gg * P.N + n;
+              ls2 = dup(sc_g[mi]);
+              lz2 = (P.mode != 2) ? dup(zr_g[mi]) : 0u;
+            }
+          }
+          uint32_t q[4];
+          unpack8_nat<BF16>(w[cc], q);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o[cc * 4 + j] = dequant2_ref<BF16>(q[j], ls2, lz2, P.mode);
+        }
+        ptx::tc_fence_after_sync();
+        ptx::tmem_st_32x16(taddr0 + (uint32_t)s * 32u, o);
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_cluster(aready_leader + (uint32_t)s * 8u);
+        if (++s == T2_STAGES) { s = 0; ph ^= 1; }
+        g = gn; rem = remn;
+      }
+    }
+  } else if (warp >= T2_EPI_WARP0) {
+    // ================= epilogue: TMEM -> registers -> global (each CTA drains its own 128 feature rows) =================
+    const int q4 = warp - T2_EPI_WARP0;
+    const int row = q4 * 32 + lane;
+    const uint32_t tempty_leader = ptx::mapa(ptx::smem_u32(tempty), 0u);
+    int it = 0;
+    for (int t = pair; t < ntiles; t += npairs, ++it) {
+      const int tm = t % P.tiles_m, tn = t / P.tiles_m;
+      const int n = tn * 2 * T2_BM + (int)rank * T2_BM + row;
+      float bv = 0.f;
+      if (P.bias) bv = BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(P.bias)[n])
+                            : __half2float(reinterpret_cast<const __half*>(P.bias)[n]);
+      ptx::mbar_wait(tfull, (uint32_t)(it & 1));
+      ptx::tc_fence_after_sync();
+#pragma unroll 1
+      for (int c0 = 0; c0 < T2_BT; c0 += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)c0, r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int m = tm * T2_BT + c0 + j;
+          if (m < P.M) {
+            float v = __uint_as_float(r[j]);
+            if (BF16) {
+              if (P.bias) v = __bfloat162float(__float2bfloat16_rn(v)) + bv;
+              reinterpret_cast<__nv_bfloat16*>(P.y)[(int64_t)m * P.N + n] = __float2bfloat16_rn(v);
+            } else {
+              if (P.bias) v = __half2float(__float2half_rn(v)) + bv;
+              reinterpret_cast<__half*>(P.y)[(int64_t)m * P.N + n] = __float2half_rn(v);
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_cluster(tempty_leader);
+    }
+  }
+
+  // ---- teardown: nobody leaves (or frees tensor memory) while the pair may still touch this CTA ----
+  ptx::tc_fence_before_sync();
+  ptx::cluster_sync();
+  ptx::tc_fence_after_sync();
+  if (warp == 2) ptx::tmem_dealloc_2cta(tmem_base, 512);
+}
+
+template <bool BF16>
+int launch_tc2(const glb_linear& L, const void* x, void* y, int64_t M, const void* bias, cudaStream_t stream) {
+  CUtensorMap tx, tw;
+  int rc = make_tmap_2d(&tx, BF16 ? GLB_BF16 : GLB_FP16, x, (uint64_t)L.K, (uint64_t)M, (uint64_t)L.K * 2, T2_BK, T2_BT / 2, 1);
+  if (rc != GLB_OK) return rc;
+  rc = make_tmap_2d(&tw, GLB_INT32, L.W_q, (uint64_t)L.N, (uint64_t)(L.K / 8), (uint64_t)L.N * 4, T2_BM, T2_BK / 8, 0);
+  if (rc != GLB_OK) return rc;
+  Tc2Params P;
+  P.scales = L.scales; P.zeros = (L.W_group_mode == 2) ? nullptr : L.zeros;
+  P.y = y; P.bias = bias; P.M = (int)M; P.N = (int)L.N; P.K = (int)L.K;
+  P.group_size = L.group_size; P.mode = L.W_group_mode;
+  P.tiles_m = (int)((M + T2_BT - 1) / T2_BT); P.tiles_n = (int)(L.N / (2 * T2_BM));
+  auto kern = gemm_a16w4_tc2_kernel<BF16>;
+  static thread_local bool configured = false;
+  if (!configured) {
+    GLB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM));
+    configured = true;
+  }
+  const int pairs = std::min(num_sms() / 2, P.tiles_m * P.tiles_n);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(2 * pairs));
+  cfg.blockDim = dim3(T2_THREADS);
+  cfg.dynamicSmemBytes = T2_SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  GLB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tx, tw, P));
+  count_launch();
+  return GLB_OK;
+}
+
+}  // namespace
+
+// shapes the pair kernel takes on top of gemm_tc_supported(): whole 256-feature tiles
+bool gemm_tc2_supported(const glb_linear& L, int64_t M) {
+  if (M < 1) return false;
+  if (L.N % (2 * T2_BM) != 0 || L.K % T2_BK != 0) return false;
+  return true;
+}
+
+int launch_gemm_tc2(const glb_linear& L, const void* x, void* y, int64_t M, const void* bias, cudaStream_t stream) {
+  const bool bf = (L.input_dtype == GLB_BF16);
+  set_kernel_name("gemm_a16w4_tcgen05_2cta");
+  return bf ? launch_tc2<true>(L, x, y, M, bias, stream) : launch_tc2<false>(L, x, y, M, bias, stream);
+}
+
+}  // namespace glb

@@ -424,12 +424,16 @@ struct GemvTmaParams {
   int late_trigger;      // dependents are signalled 0: at kernel start, 1: after the main loop, 2: right after griddepcontrol.wait
   int bulk1d;            // 1: descriptor-free cp.async.bulk row copies instead of tensor-map TMA for the weights
   const uint32_t* W;     // (K/8, N) int32 (for bulk1d)
+  const void* scales;    // (G, N)   (META_REGS flavour reads them with plain loads)
+  const void* zeros;     // (G, N) or null
   int chunk_shift;       // log2(rows per weight chunk)
   int debug;             // diagnostics only: bit 0 skip the main loop, bit 1 skip the weight copies
 };
 
-template <bool BF16, int MT, int RPG, int KSPLIT, bool FAST, int NW>
-__global__ void __launch_bounds__(NW * 32, (NW == 8) ? 4 : 2)
+constexpr int GT_GPW = 4;    // META_REGS: groups a warp may own (their scale / zero vectors live in registers)
+
+template <bool BF16, int MT, int RPG, int KSPLIT, bool FAST, int NW, bool META_REGS>
+__global__ void __launch_bounds__(NW * 32, (NW == 8) ? (META_REGS ? 3 : 4) : 2)
 gemv_w4_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_s,
                    const __grid_constant__ CUtensorMap tmap_z, const GemvTmaParams P) {
   static_assert(MT <= 8, "one token block");
@@ -449,9 +453,10 @@ gemv_w4_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
   // shared memory carve-up (weight buffer 1024-byte aligned: it is written by TMA with the 128B swizzle)
   unsigned char* wbuf = smem_raw;                                        // rows_c x 128 B (no integer round-trip: keeps LDS)
   if ((ptx::smem_u32(smem_raw) & 1023u) != 0u) __trap();
-  unsigned char* sbuf = wbuf + (size_t)rows_c * 128;                     // Gc x 64 B (padded to 128)
-  unsigned char* zbuf = sbuf + (((size_t)Gc * 64 + 127) & ~(size_t)127);
-  uint16_t* xs = reinterpret_cast<uint16_t*>(zbuf + (((size_t)Gc * 64 + 127) & ~(size_t)127));
+  const size_t meta_bytes_smem = META_REGS ? 0 : (((size_t)Gc * 64 + 127) & ~(size_t)127);
+  unsigned char* sbuf = wbuf + (size_t)rows_c * 128;                     // Gc x 64 B (padded to 128); absent with META_REGS
+  unsigned char* zbuf = sbuf + meta_bytes_smem;
+  uint16_t* xs = reinterpret_cast<uint16_t*>(zbuf + meta_bytes_smem);
   uint32_t* zero16 = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(xs) + (size_t)MT * Kc * 2);
   float* red = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(zero16) + 16);
   float* peer = red + NW * MT * GV_COLS;
@@ -475,10 +480,12 @@ gemv_w4_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
     ptx::prefetch_tmap(&tmap_s);
     for (int c = 0; c <= GT_NCH; ++c) ptx::mbar_init(&bars[c], 1);
     ptx::fence_mbar_init();
-    const uint32_t meta_bytes = (uint32_t)Gc * 64u * (P.mode != 2 ? 2u : 1u);
-    ptx::mbar_arrive_expect_tx(&bars[GT_NCH], meta_bytes);
-    ptx::tma_load_2d(sbuf, &tmap_s, &bars[GT_NCH], col0, gbeg);
-    if (P.mode != 2) ptx::tma_load_2d(zbuf, &tmap_z, &bars[GT_NCH], col0, gbeg);
+    if (!META_REGS) {
+      const uint32_t meta_bytes = (uint32_t)Gc * 64u * (P.mode != 2 ? 2u : 1u);
+      ptx::mbar_arrive_expect_tx(&bars[GT_NCH], meta_bytes);
+      ptx::tma_load_2d(sbuf, &tmap_s, &bars[GT_NCH], col0, gbeg);
+      if (P.mode != 2) ptx::tma_load_2d(zbuf, &tmap_z, &bars[GT_NCH], col0, gbeg);
+    }
     for (int c = 0; c < ((P.debug & 2) ? 0 : nch); ++c) {
       ptx::mbar_arrive_expect_tx(&bars[c], (uint32_t)chunk_rows * 128u);
       if (!P.bulk1d) ptx::tma_load_2d(wbuf + (size_t)c * chunk_rows * 128, &tmap_w, &bars[c], col0, (kbeg >> 3) + c * chunk_rows);
@@ -493,6 +500,20 @@ gemv_w4_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
                        ptx::smem_u32(wbuf + (size_t)r * 128)),
                    "l"(src), "r"(128u), "r"(ptx::smem_u32(&bars[r / chunk_rows]))
                    : "memory");
+    }
+  }
+  // META_REGS: the scale / zero vectors of this lane's four columns, for the (<= GT_GPW) groups its warp owns
+  uint2 sreg[GT_GPW], zreg[GT_GPW];
+  if (META_REGS) {
+#pragma unroll
+    for (int i = 0; i < GT_GPW; ++i) {
+      const int gl = warp + NW * i;
+      sreg[i] = make_uint2(0u, 0u); zreg[i] = make_uint2(0u, 0u);
+      if (gl < Gc) {
+        const size_t mo = (size_t)(gbeg + gl) * N + col0 + 4 * g8;
+        sreg[i] = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(P.scales) + mo));
+        if (P.mode != 2) zreg[i] = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(P.zeros) + mo));
+      }
     }
   }
   if (P.late_trigger == 0) pdl_launch_dependents();  // everything this CTA can do ahead of its input has been issued
@@ -562,10 +583,13 @@ gemv_w4_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
   const unsigned char* xb = reinterpret_cast<const unsigned char*>(xs + (size_t)(tok_ok ? g8 : 0) * Kc) + (2 * t4) * 16;
   const unsigned char* wl = wbuf + (2 * t4) * 128;
   const int sw0 = (g8 ^ (2 * t4)) << 4, sw1 = (g8 ^ (2 * t4 + 1)) << 4;   // swizzled chunk offsets for a = 0 / 1
-  ptx::mbar_wait(&bars[GT_NCH], 0);                               // scales / zeros landed
+  if (!META_REGS) ptx::mbar_wait(&bars[GT_NCH], 0);               // scales / zeros landed
   if (rec) ts[GLB_GEMV_TIMELINE ? 4 : 0] = gtimer();
 
-  for (int gl = warp; gl < ((P.debug & 1) ? 0 : Gc); gl += NW) {
+#pragma unroll
+  for (int gi = 0; gi < (META_REGS ? GT_GPW : (1 << 20)); ++gi) {
+    const int gl = warp + NW * gi;
+    if (gl >= ((P.debug & 1) ? 0 : Gc)) break;
     if (!(P.debug & 2)) ptx::mbar_wait(&bars[(gl * rpg) >> P.chunk_shift], 0);   // this group's weight chunk landed
     if (rec && gl == warp) ts[GLB_GEMV_TIMELINE ? 5 : 0] = gtimer();
     // four independent accumulator chains per run: [column pair][k half]
@@ -597,9 +621,12 @@ gemv_w4_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
       }
     }
     // ---- end of group: y += s * (sum(x q)) + z' * sum(x) ----
-    const uint2 sw = *reinterpret_cast<const uint2*>(sbuf + (size_t)gl * 64 + g8 * 8);
-    uint2 zw = make_uint2(0u, 0u);
-    if (P.mode != 2) zw = *reinterpret_cast<const uint2*>(zbuf + (size_t)gl * 64 + g8 * 8);
+    uint2 sw, zw = make_uint2(0u, 0u);
+    if (META_REGS) { sw = sreg[gi < GT_GPW ? gi : 0]; zw = zreg[gi < GT_GPW ? gi : 0]; }
+    else {
+      sw = *reinterpret_cast<const uint2*>(sbuf + (size_t)gl * 64 + g8 * 8);
+      if (P.mode != 2) zw = *reinterpret_cast<const uint2*>(zbuf + (size_t)gl * 64 + g8 * 8);
+    }
     const uint32_t swa[2] = {sw.x, sw.y}, zwa[2] = {zw.x, zw.y};
     float sx[2] = {0.f, 0.f}, off[2] = {0.f, 0.f};
     if (P.mode != 2 || FAST) {
@@ -667,14 +694,16 @@ gemv_w4_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
   }
 }
 
-template <int MT, int KSPLIT, int NW> size_t gemv_tma_smem_bytes(int K, int group_size) {
+template <int MT, int KSPLIT, int NW, bool META_REGS> size_t gemv_tma_smem_bytes(int K, int group_size) {
   const int Kc = K / KSPLIT, Gc = K / group_size / KSPLIT;
-  const size_t meta = ((size_t)Gc * 64 + 127) & ~(size_t)127;
+  const size_t meta = META_REGS ? 0 : (((size_t)Gc * 64 + 127) & ~(size_t)127);
+  // (dynamic shared memory starts 1024-byte aligned -- the kernel traps otherwise -- so no alignment slack: with
+  // META_REGS the K = 4096 slab takes 74.9 KB and THREE layers fit on an SM)
   return (size_t)(Kc / 8) * 128 + 2 * meta + (size_t)MT * Kc * 2 + 16 + (size_t)NW * MT * GV_COLS * 4 +
-         (size_t)MT * GV_COLS * 4 + (size_t)MT * Gc * 8 + (GT_NCH + 1) * 8 + 128 + 1024;
+         (size_t)MT * GV_COLS * 4 + (size_t)MT * Gc * 8 + (GT_NCH + 1) * 8 + 64;
 }
 
-template <bool BF16, int MT, int RPG, int KSPLIT, bool FAST, int NW>
+template <bool BF16, int MT, int RPG, int KSPLIT, bool FAST, int NW, bool META_REGS = false>
 int launch_w4_tma(const glb_linear& L, const GemvParams& P0, int late_trigger, cudaStream_t stream) {
   const int Kc = P0.K / KSPLIT, Gc = P0.K / P0.group_size / KSPLIT, rows_c = Kc / 8;
   constexpr int rpg = RPG * 4;
@@ -692,6 +721,7 @@ int launch_w4_tma(const glb_linear& L, const GemvParams& P0, int late_trigger, c
   P.late_trigger = late_trigger % 10;
   P.bulk1d = late_trigger / 10;
   P.W = reinterpret_cast<const uint32_t*>(L.W_q);
+  P.scales = P0.scales; P.zeros = P0.zeros;
   {
     int cr = rows_c / nch, sh = 0;
     while ((1 << sh) < cr) ++sh;
@@ -700,8 +730,8 @@ int launch_w4_tma(const glb_linear& L, const GemvParams& P0, int late_trigger, c
     if (dbg < 0) { const char* e = getenv("GLB_GEMV_DEBUG"); dbg = e ? atoi(e) : 0; }
     P.debug = dbg;
   }
-  const size_t smem = gemv_tma_smem_bytes<MT, KSPLIT, NW>(P0.K, P0.group_size);
-  auto kern = gemv_w4_tma_kernel<BF16, MT, RPG, KSPLIT, FAST, NW>;
+  const size_t smem = gemv_tma_smem_bytes<MT, KSPLIT, NW, META_REGS>(P0.K, P0.group_size);
+  auto kern = gemv_w4_tma_kernel<BF16, MT, RPG, KSPLIT, FAST, NW, META_REGS>;
   if (smem > 48 * 1024) {
     static thread_local size_t configured = 0;
     if (configured < smem) {
@@ -735,7 +765,8 @@ int launch_w4_tma(const glb_linear& L, const GemvParams& P0, int late_trigger, c
 
 // Kernel flavour (GLB_GEMV_VARIANT, read once): 3 = register prefetch + 2-CTA cluster; 4 = TMA + 2-CTA cluster,
 // 256 threads (default); 41 = same with the dependent-launch trigger after the main loop; 5 / 51 = TMA, one
-// 512-thread CTA per slab over the full K (exactly two CTAs per SM), early / late trigger.
+// 512-thread CTA per slab over the full K (exactly two CTAs per SM), early / late trigger; 6 / 62 = TMA, one
+// 256-thread CTA per slab, scale / zero vectors in registers -> 74.9 KB of shared memory, THREE layers per SM.
 int gemv_variant() {
   static int v = -1;
   if (v < 0) {
@@ -775,7 +806,9 @@ int dispatch_w4(const glb_linear& L, const GemvParams& P, cudaStream_t stream) {
         (P.mode == 2 || (reinterpret_cast<uintptr_t>(L.zeros) & 15) == 0) && (P.N * 2) % 16 == 0) {   \
       /* x1: late trigger, x2: trigger after wait, x3: bulk1d + trigger after wait */               \
       const int late = (variant % 10 == 1 && variant > 10) ? 1 : ((variant % 10 == 2 && variant > 10) ? 2 : ((variant % 10 == 3 && variant > 10) ? 12 : 0)); \
-      if ((variant == 5 || variant / 10 == 5) && gemv_tma_ok(P, 1))                                   \
+      if ((variant == 6 || variant / 10 == 6) && MT8 == 1 && gemv_tma_ok(P, 1) && G <= GT_GPW * 8)     \
+        return launch_w4_tma<BF16, MT8, RPG, 1, F, 8, true>(L, P, late, stream);                      \
+      if ((variant == 5 || variant / 10 == 5 || variant == 6 || variant / 10 == 6) && gemv_tma_ok(P, 1)) \
         return launch_w4_tma<BF16, MT8, RPG, 1, F, 16>(L, P, late, stream);                           \
       if (split && gemv_tma_ok(P, 2)) return launch_w4_tma<BF16, MT8, RPG, 2, F, 8>(L, P, late, stream); \
       if (gemv_tma_ok(P, 1)) return launch_w4_tma<BF16, MT8, RPG, 1, F, 8>(L, P, late, stream);       \

@@ -216,6 +216,59 @@ def test_a16w4_decode_and_small_batch_vs_oracle(dtype, mode, gs):
     assert layer(xgen(6, K, dtype, 2).view(2, 3, K).to(DEV)).shape == (2, 3, N)
 
 
+# ------------------------------------------------------------------------------------------------
+# Prefill: the CTA-pair tcgen05 kernel (gl_gemm_tc2.cu: 2-CTA MMA, dequantised weights in tensor memory)
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("mode", ["fma", "nofma", "sym"])
+@pytest.mark.parametrize("gs", [32, 64, 128])
+def test_a16w4_prefill_pair_kernel_vs_oracle(dtype, mode, gs):
+    N, K = 512, 1024
+    W_q, scales, zeros = gen_int(N, K, 4, gs, dtype, seed=gs + (17 if mode == "fma" else 23))
+    gd = gemlite_b200.dtypes.TORCH_TO_DTYPE[dtype]
+    bias = (torch.randn(N, generator=torch.Generator().manual_seed(4)) / 10).to(dtype)
+    layer = GemLiteLinear(4, gs, K, N, gd, gd)
+    z_in = None if mode == "sym" else zeros
+    layer.pack(W_q.to(DEV), scales.to(DEV), None if z_in is None else z_in.to(DEV), bias.to(DEV), fma_mode=(mode == "fma"))
+    p = O.prepare(W_q, scales, z_in, W_nbits=4, group_size=gs, in_features=K, out_features=N,
+                  input_dtype=O.DTYPE_OF[dtype], output_dtype=O.DTYPE_OF[dtype], bias=bias, fma_mode=(mode == "fma"))
+    for M in (129, 256, 300, 700):          # ragged last token block, one and several token blocks
+        x = xgen(M, K, dtype, 90 + M)
+        y = layer(x.to(DEV))
+        assert _cabi.last_kernel() == "gemm_a16w4_tcgen05_2cta", _cabi.last_kernel()
+        e = relerr(y, O.forward(p, x))
+        assert e <= REL[dtype], (dtype, mode, gs, M, e)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_prefill_pair_kernel_dequant_is_bit_exact(dtype):
+    """x = identity => y[m, n] is the dequantised weight W[n, m] itself (one non-zero product per output, fp32
+    accumulate): the tensor-memory operand must hold exactly the reference's dequantize() values (utils.py:57-89)."""
+    N, K, gs = 512, 256, 64
+    W_q, scales, zeros = gen_int(N, K, 4, gs, dtype, seed=5)
+    gd = gemlite_b200.dtypes.TORCH_TO_DTYPE[dtype]
+    layer = GemLiteLinear(4, gs, K, N, gd, gd).pack(W_q.to(DEV), scales.to(DEV), zeros.to(DEV))
+    p = O.prepare(W_q, scales, zeros, W_nbits=4, group_size=gs, in_features=K, out_features=N,
+                  input_dtype=O.DTYPE_OF[dtype], output_dtype=O.DTYPE_OF[dtype])
+    x = torch.eye(K, dtype=dtype)
+    y = layer(x.to(DEV))
+    assert _cabi.last_kernel() == "gemm_a16w4_tcgen05_2cta"
+    assert torch.equal(y.cpu(), O.forward(p, x))
+
+
+def test_prefill_pair_kernel_many_tiles_per_pair():
+    """More tiles than CTA pairs (100 > 74): exercises the accumulator hand-over between consecutive tiles and the
+    ring phases; checked on the device against torch fp32 dequant + matmul."""
+    M, N, K, gs = 2560, 2560, 512, 128
+    W_q, scales, zeros = gen_int(N, K, 4, gs, torch.float16, seed=9)
+    layer = A16W4_HQQ_INT(device=DEV, dtype=torch.float16).from_weights(W_q, scales, zeros)
+    x = xgen(M, K, torch.float16, 77).to(DEV)
+    y = layer(x)
+    assert _cabi.last_kernel() == "gemm_a16w4_tcgen05_2cta"
+    Wd = ((W_q.to(DEV).view(-1, gs).float() - zeros.to(DEV).float()) * scales.to(DEV).float()).view(N, K)
+    assert relerr(y, x.float() @ Wd.t()) <= REL[torch.float16]
+    assert torch.equal(layer(x), y)          # deterministic
+
+
 def test_decode_kernel_is_used_for_the_headline_shape():
     N = K = 4096
     W_q, scales, zeros = gen_int(N, K, 4, 128, torch.float16, seed=0)

@@ -16,5 +16,6 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemv
     python bench.py --steps 2 --warmup 1 > gpurun_out/ncu_full.log 2>&1
 echo "== ncu full (prefill kernel)"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_a16w4 -c 2 -o gpurun_out/prefill_full -f \
-    python tools/run_prefill.py > gpurun_out/ncu_prefill.log 2>&1
+    python tools/run_prefill.py --quick > gpurun_out/ncu_prefill.log 2>&1
+echo "== prefill sweep"; timeout 300 python tools/run_prefill.py 2>&1 | tail -6 | tee gpurun_out/prefill_sweep.log
 ls -la gpurun_out | tail -20
