@@ -12,7 +12,8 @@ import torch
 from .dtypes import TORCH_TO_DTYPE, DType
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgemlite_b200.so")
+# GLB_LIB_PATH: diagnostics only (e.g. the phase-timeline build, `python -m gemlite_b200.build --timeline`)
+LIB_PATH = os.environ.get("GLB_LIB_PATH") or os.path.join(_HERE, "libgemlite_b200.so")
 
 _lib = None
 _lock = threading.Lock()

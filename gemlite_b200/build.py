@@ -37,18 +37,25 @@ def _digest():
     return h.hexdigest()
 
 
-def build(force=False, verbose=False):
-    """Compile every .cu to an object (parallel) and link the shared library. Returns the path."""
+def build(force=False, verbose=False, timeline=False):
+    """Compile every .cu to an object (parallel) and link the shared library. Returns the path.
+    timeline=True builds the diagnostic flavour (decode kernel records %globaltimer phase stamps) next to it."""
+    if timeline:
+        return _build(True, verbose, os.path.join(HERE, "libgemlite_b200_timeline.so"), os.path.join(CSRC, "build_tl"),
+                      ["-DGLB_GEMV_TIMELINE=1"], None)
     dig = _digest()
     if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == dig:
         return LIB
+    return _build(force, verbose, LIB, os.path.join(CSRC, "build"), [], dig)
+
+
+def _build(force, verbose, LIB, objdir, extra, dig):
     nvcc = _nvcc()
-    objdir = os.path.join(CSRC, "build")
     os.makedirs(objdir, exist_ok=True)
     procs = []
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas")
             cmd.insert(2, "-v")
@@ -67,9 +74,10 @@ def build(force=False, verbose=False):
     if r.returncode != 0:
         sys.stderr.write(r.stdout)
         raise RuntimeError("link failed")
-    open(STAMP, "w").write(dig)
+    if dig is not None:
+        open(STAMP, "w").write(dig)
     return LIB
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, timeline="--timeline" in sys.argv))

@@ -131,9 +131,12 @@ __device__ __forceinline__ uint32_t mapa(uint32_t cta_addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_addr), "r"(rank));
   return r;
 }
-// arrive on a barrier that may live in the peer CTA (address from mapa)
+// arrive on a barrier that may live in the peer CTA (address from mapa).  Default semantics (.release.cta), like
+// cutlass ClusterBarrier::arrive(cta_id): a .release.cluster here costs a cluster-scope memory barrier (ERRBAR +
+// MEMBAR, ~17 % of all warp samples in profiles/prefill_tc2_v1_r1_ncu.txt) and publishes nothing we need -- the
+// data handed over lives in tensor memory and is ordered by tcgen05.wait::st / tcgen05.fence.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load issued by either CTA of a pair: data lands in THIS CTA's shared memory, the transaction bytes are
 // reported to the barrier at `cluster_bar_addr` (the leader's) -- cute SM100_TMA_2SM_LOAD_2D.
