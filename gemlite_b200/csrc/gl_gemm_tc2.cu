@@ -18,8 +18,12 @@
 // Arithmetic contract is unchanged (see gl_gemm_tc.cu): weights are dequantised with the reference's rounding
 // (utils.py:57-89) and accumulated in fp32 by the tensor core (gemm_kernels.py:384).
 //
-// Warp roles per CTA (512 threads): w0 TMA producer, w1 MMA issuer (leader CTA only), w2 TMEM allocator,
-// w4-11 dequant (warp % 4 = TMEM lane quarter, (warp-4)/4 = which 32-k half of the k-block), w12-15 epilogue.
+// Warp roles per CTA (768 threads): w0 TMA producer, w1 MMA issuer (leader CTA only), w2 TMEM allocator,
+// w4-19 dequant (warp % 4 = TMEM lane quarter, bit 2 of (warp-4) = which 32-k half of the k-block, bit 3 = which
+// k-blocks (even / odd) the warp serves), w20-23 epilogue.  Two dequant warp groups on alternating k-blocks and the
+// arrival for a stage being sent one iteration late (after the NEXT block's arithmetic) keep the per-warp
+// LDS -> unpack -> tcgen05.st -> wait::st -> arrive chain off the MMA's critical path (r1 profile: the single-group
+// version left the MMA issuer spinning on `aready` ~50 % of the time).  Requires group_size % 64 == 0.
 // Barriers: xfull / aready / tempty live in the LEADER's shared memory (the peer reports to them remotely);
 // wfull / empty / tfull are per CTA; tcgen05.commit multicasts its arrival to both CTAs.
 #include "gl_common.cuh"
@@ -32,8 +36,8 @@ constexpr int T2_BM = 128;            // features per CTA (256 per pair)
 constexpr int T2_BT = 256;            // tokens per pair tile (128 staged per CTA)
 constexpr int T2_BK = 64;
 constexpr int T2_STAGES = 8;
-constexpr int T2_THREADS = 512;
-constexpr int T2_DEQ_WARP0 = 4, T2_DEQ_WARPS = 8, T2_EPI_WARP0 = 12;
+constexpr int T2_THREADS = 768;
+constexpr int T2_DEQ_WARP0 = 4, T2_DEQ_WARPS = 16, T2_EPI_WARP0 = 20;   // 16 dequant warps: [k-block parity][k half][lane quarter]
 constexpr int T2_X_BYTES = (T2_BT / 2) * T2_BK * 2;        // 16 KB
 constexpr int T2_P_BYTES = (T2_BK / 8) * T2_BM * 4;        // 4 KB
 constexpr int T2_STAGE = T2_X_BYTES + T2_P_BYTES;
@@ -128,7 +132,7 @@ gemm_a16w4_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     for (int s = 0; s < T2_STAGES; ++s) {
       ptx::mbar_init(&xfull[s], 1);
       ptx::mbar_init(&wfull[s], 1);
-      ptx::mbar_init(&aready[s], 2 * T2_DEQ_WARPS);
+      ptx::mbar_init(&aready[s], 2 * (T2_DEQ_WARPS / 2));
       ptx::mbar_init(&empty[s], 1);
     }
     ptx::mbar_init(tfull, 1);
@@ -188,72 +192,66 @@ gemm_a16w4_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     }
   } else if (warp >= T2_DEQ_WARP0 && warp < T2_DEQ_WARP0 + T2_DEQ_WARPS) {
     // ================= dequant: thread == feature row == TMEM lane; 4 packed words (32 k) per thread =================
-    const int q4 = warp & 3;                                // TMEM lane quarter this warp may touch
+    const int d = warp - T2_DEQ_WARP0;
+    const int q4 = d & 3;                                   // TMEM lane quarter this warp may touch (== warp % 4)
     const int row = q4 * 32 + lane;                         // feature row inside this CTA's 128
-    const int half = (warp - T2_DEQ_WARP0) >> 2;            // which 32-k half of the 64-k block
-    const uint16_t* sc_g = reinterpret_cast<const uint16_t*>(P.scales);
-    const uint16_t* zr_g = reinterpret_cast<const uint16_t*>(P.zeros);
+    const int half = (d >> 2) & 1;                          // which 32-k half of the 64-k block
+    const uint32_t parity = (uint32_t)(d >> 3);             // this warp serves k-blocks whose running index has this parity
+    const int kbpg = P.group_size >> 6;                     // k-blocks per quantisation group (group_size % 64 == 0)
     const uint32_t taddr0 = tmem_base + ((uint32_t)(q4 * 32) << 16) + T2_ACOL0 + (uint32_t)half * 16u;
     const uint32_t aready_leader = ptx::mapa(ptx::smem_u32(&aready[0]), 0u);
-    int s = 0; uint32_t ph = 0;
+    const uint32_t* pk0 = reinterpret_cast<const uint32_t*>(smem + T2_X_BYTES) + (half * 4) * T2_BM + row;
+    auto dup = [](uint16_t v) { return (uint32_t)v | ((uint32_t)v << 16); };
+    uint32_t cnt = 0;                                       // running k-block index over all tiles of this pair
+    int pend = -1;                                          // stage whose tcgen05.st is in flight (arrival still owed)
     for (int t = pair; t < ntiles; t += npairs) {
       const int tn = t / P.tiles_m;
       const int n = tn * 2 * T2_BM + (int)rank * T2_BM + row;
-      int g = (half * 32) / P.group_size, rem = (half * 32) % P.group_size;
-      int cur_g = -1, pre_g = -1;
-      uint32_t s2 = 0, z2 = 0;
-      uint16_t psv = 0, pzv = 0;
-      auto dup = [](uint16_t v) { return (uint32_t)v | ((uint32_t)v << 16); };
-      for (int kb = 0; kb < kblocks; ++kb) {
-        const int k0 = kb * T2_BK + half * 32;
-        if (g != cur_g) {
-          if (g == pre_g) { s2 = dup(psv); z2 = dup(pzv); }
-          else {
-            const int64_t mi = (int64_t)g * P.N + n;
-            s2 = dup(sc_g[mi]);
-            z2 = (P.mode != 2) ? dup(zr_g[mi]) : 0u;
+      const uint16_t* sp = reinterpret_cast<const uint16_t*>(P.scales) + n;
+      const uint16_t* zp = (P.mode != 2) ? reinterpret_cast<const uint16_t*>(P.zeros) + n : sp;
+      uint32_t s2n = dup(*sp), z2n = (P.mode != 2) ? dup(*zp) : 0u;
+      for (int kb0 = 0; kb0 < kblocks; kb0 += kbpg) {
+        const uint32_t s2 = s2n, z2 = z2n;
+        if (kb0 + kbpg < kblocks) {                         // next group's metadata: requested now, consumed next round
+          sp += P.N; zp += P.N;
+          s2n = dup(*sp);
+          z2n = (P.mode != 2) ? dup(*zp) : 0u;
+        }
+#pragma unroll 1
+        for (int j = 0; j < kbpg; ++j, ++cnt) {
+          if ((cnt & 1u) != parity) continue;
+          const uint32_t s = cnt & (T2_STAGES - 1), ph = (cnt >> 3) & 1u;
+          static_assert(T2_STAGES == 8, "stage / phase arithmetic above assumes an 8-deep ring");
+          ptx::mbar_wait(&wfull[s], ph);      // also implies the MMAs that last read A slot s completed (producer saw empty[s])
+          const uint32_t* pk = pk0 + s * (T2_STAGE / 4);
+          uint32_t w[4];
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) w[cc] = pk[cc * T2_BM];
+          uint32_t o[16];
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            uint32_t q[4];
+            unpack8_nat<BF16>(w[cc], q);
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) o[cc * 4 + jj] = dequant2_ref<BF16>(q[jj], s2, z2, P.mode);
           }
-          cur_g = g;
-        }
-        int gn = g, remn = rem + T2_BK;
-        while (remn >= P.group_size) { remn -= P.group_size; ++gn; }
-        if (kb + 1 < kblocks && gn != cur_g && gn != pre_g) {      // next block's metadata: issue now, use next iteration
-          const int64_t mi = (int64_t)gn * P.N + n;
-          psv = sc_g[mi];
-          pzv = (P.mode != 2) ? zr_g[mi] : (uint16_t)0;
-          pre_g = gn;
-        }
-        ptx::mbar_wait(&wfull[s], ph);      // also implies: the MMAs that last read A slot s have completed (producer waited on empty[s])
-        const uint32_t* pk = reinterpret_cast<const uint32_t*>(smem + s * T2_STAGE + T2_X_BYTES);
-        uint32_t w[4];
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) w[cc] = pk[(half * 4 + cc) * T2_BM + row];
-        uint32_t o[16];
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          uint32_t ls2 = s2, lz2 = z2;
-          if (P.group_size < 32) {                         // a 32-k span may cross groups only for gs = 8 / 16 / 24
-            const int gg = (k0 + cc * 8) / P.group_size;
-            if (gg != cur_g) {
-              const int64_t mi = (int64_t)gg * P.N + n;
-              ls2 = dup(sc_g[mi]);
-              lz2 = (P.mode != 2) ? dup(zr_g[mi]) : 0u;
-            }
+          if (pend >= 0) {                    // the previous block's store has had a whole block of arithmetic to land
+            ptx::tmem_st_wait();
+            ptx::tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(aready_leader + (uint32_t)pend * 8u);
           }
-          uint32_t q[4];
-          unpack8_nat<BF16>(w[cc], q);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) o[cc * 4 + j] = dequant2_ref<BF16>(q[j], ls2, lz2, P.mode);
+          ptx::tc_fence_after_sync();
+          ptx::tmem_st_32x16(taddr0 + s * 32u, o);
+          pend = (int)s;
         }
-        ptx::tc_fence_after_sync();
-        ptx::tmem_st_32x16(taddr0 + (uint32_t)s * 32u, o);
-        ptx::tmem_st_wait();
-        ptx::tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive_cluster(aready_leader + (uint32_t)s * 8u);
-        if (++s == T2_STAGES) { s = 0; ph ^= 1; }
-        g = gn; rem = remn;
       }
+    }
+    if (pend >= 0) {
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_cluster(aready_leader + (uint32_t)pend * 8u);
     }
   } else if (warp >= T2_EPI_WARP0) {
     // ================= epilogue: TMEM -> registers -> global (each CTA drains its own 128 feature rows) =================
@@ -267,24 +265,31 @@ gemm_a16w4_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       float bv = 0.f;
       if (P.bias) bv = BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(P.bias)[n])
                             : __half2float(reinterpret_cast<const __half*>(P.bias)[n]);
-      ptx::mbar_wait(tfull, (uint32_t)(it & 1));
+      ptx::mbar_wait_sleep(tfull, (uint32_t)(it & 1));     // a whole main loop away: do not burn issue slots spinning
       ptx::tc_fence_after_sync();
+      // the accumulator is single-buffered (tensor memory is full), so this drain is exposed: keep it lean --
+      // one cvt + one address mad + one 2-byte store per element, no per-element predicates on whole tiles
+      const int mrem = P.M - tm * T2_BT;                                  // valid tokens in this tile
+      unsigned char* ybase = reinterpret_cast<unsigned char*>(P.y) + ((int64_t)(tm * T2_BT) * P.N + n) * 2;
+      const int64_t ystride = (int64_t)P.N * 2;
 #pragma unroll 1
       for (int c0 = 0; c0 < T2_BT; c0 += 32) {
+        if (c0 >= mrem) break;
         uint32_t r[32];
         ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)c0, r);
         ptx::tmem_ld_wait();
+        unsigned char* yp = ybase + (int64_t)c0 * ystride;
+        const bool whole = (c0 + 32 <= mrem);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const int m = tm * T2_BT + c0 + j;
-          if (m < P.M) {
+          if (whole || c0 + j < mrem) {
             float v = __uint_as_float(r[j]);
             if (BF16) {
               if (P.bias) v = __bfloat162float(__float2bfloat16_rn(v)) + bv;
-              reinterpret_cast<__nv_bfloat16*>(P.y)[(int64_t)m * P.N + n] = __float2bfloat16_rn(v);
+              *reinterpret_cast<__nv_bfloat16*>(yp + j * ystride) = __float2bfloat16_rn(v);
             } else {
               if (P.bias) v = __half2float(__float2half_rn(v)) + bv;
-              reinterpret_cast<__half*>(P.y)[(int64_t)m * P.N + n] = __float2half_rn(v);
+              *reinterpret_cast<__half*>(yp + j * ystride) = __float2half_rn(v);
             }
           }
         }
@@ -342,6 +347,7 @@ int launch_tc2(const glb_linear& L, const void* x, void* y, int64_t M, const voi
 bool gemm_tc2_supported(const glb_linear& L, int64_t M) {
   if (M < 1) return false;
   if (L.N % (2 * T2_BM) != 0 || L.K % T2_BK != 0) return false;
+  if (L.group_size % T2_BK != 0) return false;       // a 64-wide k-block never straddles quantisation groups
   return true;
 }
 

@@ -70,7 +70,7 @@ def gather_columns(y_local: Tensor, group=None) -> Tensor:
         return y_local
     y_local = y_local.contiguous()
     out = torch.empty((world,) + tuple(y_local.shape), dtype=y_local.dtype, device=y_local.device)
-    dist.all_gather_into_tensor(out, y_local, group=group)
+    dist.all_gather_into_tensor(out.view(-1), y_local.view(-1), group=group)      # flat views: accepted by NCCL and gloo alike
     return out.movedim(0, -2).reshape(*y_local.shape[:-1], world * y_local.shape[-1])
 
 
