@@ -1,31 +1,33 @@
 // tcgen05 prefill GEMM, CTA-pair flavour (cta_group::2) with the dequantised weights fed to the tensor core
 // from TENSOR MEMORY -- the large-M path of A16W4 (rows a9/a10, config C3).
 //
-// Why (profiles/prefill_r1_ncu.txt): the single-CTA kernel in gl_gemm_tc.cu keeps the tensor pipe only ~49 %
+// Why (profiles/prefill_tc1_r1_ncu.txt): the single-CTA kernel in gl_gemm_tc.cu keeps the tensor pipe only ~49 %
 // busy because the shared-memory data pipe is saturated: per 64-wide k-block a CTA moves 48 KB of operand
 // reads (A 16 KB + B 32 KB), 36 KB of TMA writes and 16 KB (x2 bank conflicts) of dequant stores = ~93 % of the
 // 128 B/clk port.  Here
 //   * a CTA PAIR owns a 256-feature x 256-token tile: tcgen05.mma.cta_group::2, M = 256 (128 TMEM lanes per
-//     CTA), N = 256; each CTA stages only ITS 128 tokens of the x tile (16 KB / k-block) and the tensor cores
-//     of both SMs read both halves -> B traffic per CTA halves;
+//     CTA), N = 256; each CTA stages only ITS 128 tokens of the x tile and the tensor cores of both SMs read
+//     both halves -> B traffic per CTA halves;
 //   * the dequantised weight tile never touches shared memory: dequant thread == feature row == TMEM lane,
 //     16 packed pairs per thread go to tensor memory with one tcgen05.st.32x32b.x16 and the MMA takes its A
 //     operand from there ([a_tmem] form).  No STS, no bank conflicts, no async-proxy fence;
-//   * shared memory per stage is 20 KB (x half-tile + 4 KB packed words) -> an 8-deep TMA ring, matching the
-//     8 x 32-column A ring in TMEM (256 columns) next to the 256-column fp32 accumulator.
-// Shared-memory traffic per CTA and k-block: 16 KB operand reads + 20 KB TMA writes + 4 KB packed reads.
+//   * a pipeline stage is 128 k wide (two 128B-swizzled x boxes of 16 KB + 8 KB of packed words = 40 KB, 4 stages;
+//     the A ring in TMEM is 4 x 64 columns next to the 256-column fp32 accumulator), so every per-stage cost --
+//     barrier round trips, the MMA issuer's loop body, the producer's bookkeeping -- is paid once per 8 MMAs
+//     (1024 tensor-core cycles).  The MMA issuer waits on ONE barrier per stage (`ready`: TMA bytes of both CTAs
+//     + the arrivals of all 32 dequant warps of the pair).
+// Shared-memory traffic per CTA and 128 k: 32 KB operand reads + 40 KB TMA writes + 8 KB packed reads.
 //
 // Arithmetic contract is unchanged (see gl_gemm_tc.cu): weights are dequantised with the reference's rounding
 // (utils.py:57-89) and accumulated in fp32 by the tensor core (gemm_kernels.py:384).
 //
 // Warp roles per CTA (768 threads): w0 TMA producer, w1 MMA issuer (leader CTA only), w2 TMEM allocator,
-// w4-19 dequant (warp % 4 = TMEM lane quarter, bit 2 of (warp-4) = which 32-k half of the k-block, bit 3 = which
-// k-blocks (even / odd) the warp serves), w20-23 epilogue.  Two dequant warp groups on alternating k-blocks and the
-// arrival for a stage being sent one iteration late (after the NEXT block's arithmetic) keep the per-warp
-// LDS -> unpack -> tcgen05.st -> wait::st -> arrive chain off the MMA's critical path (r1 profile: the single-group
-// version left the MMA issuer spinning on `aready` ~50 % of the time).  Requires group_size % 64 == 0.
-// Barriers: xfull / aready / tempty live in the LEADER's shared memory (the peer reports to them remotely);
+// w4-19 dequant (warp % 4 = TMEM lane quarter, (warp-4)/4 = which 32-k quarter of the stage), w20-23 epilogue.
+// A dequant warp sends the arrival for a stage one iteration late (after the NEXT stage's arithmetic), so its
+// tcgen05.st -> wait::st -> arrive chain is off the MMA's critical path.  Requires group_size % 32 == 0.
+// Barriers: ready / tempty live in the LEADER's shared memory (the peer reports to them remotely);
 // wfull / empty / tfull are per CTA; tcgen05.commit multicasts its arrival to both CTAs.
+// History of this kernel's profile: profiles/prefill_tc2_*_r1_ncu.txt.
 #include "gl_common.cuh"
 #include "gl_ptx.cuh"
 
@@ -34,15 +36,17 @@ namespace {
 
 constexpr int T2_BM = 128;            // features per CTA (256 per pair)
 constexpr int T2_BT = 256;            // tokens per pair tile (128 staged per CTA)
-constexpr int T2_BK = 64;
-constexpr int T2_STAGES = 8;
+constexpr int T2_BK = 128;            // k per pipeline stage
+constexpr int T2_STAGES = 4;
 constexpr int T2_THREADS = 768;
-constexpr int T2_DEQ_WARP0 = 4, T2_DEQ_WARPS = 16, T2_EPI_WARP0 = 20;   // 16 dequant warps: [k-block parity][k half][lane quarter]
-constexpr int T2_X_BYTES = (T2_BT / 2) * T2_BK * 2;        // 16 KB
-constexpr int T2_P_BYTES = (T2_BK / 8) * T2_BM * 4;        // 4 KB
-constexpr int T2_STAGE = T2_X_BYTES + T2_P_BYTES;
+constexpr int T2_DEQ_WARP0 = 4, T2_DEQ_WARPS = 16, T2_EPI_WARP0 = 20;   // 16 dequant warps: [32-k quarter][lane quarter]
+constexpr int T2_XBOX_BYTES = (T2_BT / 2) * 64 * 2;        // one 64-k x box: 128 tokens x 128 B = 16 KB
+constexpr int T2_X_BYTES = 2 * T2_XBOX_BYTES;              // 32 KB
+constexpr int T2_P_BYTES = (T2_BK / 8) * T2_BM * 4;        // 8 KB
+constexpr int T2_STAGE = T2_X_BYTES + T2_P_BYTES;          // 40 KB
 constexpr int T2_SMEM = T2_STAGES * T2_STAGE + 1024 /* barriers */ + 1024 /* alignment slack */;
 constexpr uint32_t T2_ACOL0 = 256;    // first TMEM column of the A ring (accumulator: columns 0..255)
+constexpr uint32_t T2_ACOLS = T2_BK / 2;   // 64 columns of A per stage
 
 struct Tc2Params {
   const void* scales;
@@ -111,13 +115,12 @@ gemm_a16w4_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
   unsigned char* smem = smem_raw;
   if ((ptx::smem_u32(smem_raw) & 1023u) != 0u) __trap();
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + T2_STAGES * T2_STAGE);
-  uint64_t* xfull = bars;                       // [STAGES] leader: both x half-tiles landed
+  uint64_t* ready = bars;                       // [STAGES] leader: x bytes of both CTAs landed + all 32 dequant warps wrote A slot s
   uint64_t* wfull = bars + T2_STAGES;           // [STAGES] local : packed words landed
-  uint64_t* aready = bars + 2 * T2_STAGES;      // [STAGES] leader: both CTAs' dequant warps wrote A slot s
-  uint64_t* empty = bars + 3 * T2_STAGES;       // [STAGES] local : MMAs reading stage s completed (multicast commit)
-  uint64_t* tfull = bars + 4 * T2_STAGES;       // [1]      local : accumulator complete (multicast commit)
-  uint64_t* tempty = bars + 4 * T2_STAGES + 1;  // [1]      leader: both CTAs' epilogue warps drained it
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * T2_STAGES + 2);
+  uint64_t* empty = bars + 2 * T2_STAGES;       // [STAGES] local : MMAs reading stage s completed (multicast commit)
+  uint64_t* tfull = bars + 3 * T2_STAGES;       // [1]      local : accumulator complete (multicast commit)
+  uint64_t* tempty = bars + 3 * T2_STAGES + 1;  // [1]      leader: both CTAs' epilogue warps drained it
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * T2_STAGES + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = ptx::cluster_ctarank();
@@ -130,9 +133,8 @@ gemm_a16w4_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     ptx::prefetch_tmap(&tmap_x);
     ptx::prefetch_tmap(&tmap_w);
     for (int s = 0; s < T2_STAGES; ++s) {
-      ptx::mbar_init(&xfull[s], 1);
+      ptx::mbar_init(&ready[s], 1 + 2 * T2_DEQ_WARPS);   // the leader producer's expect_tx arrival + 32 dequant warps
       ptx::mbar_init(&wfull[s], 1);
-      ptx::mbar_init(&aready[s], 2 * (T2_DEQ_WARPS / 2));
       ptx::mbar_init(&empty[s], 1);
     }
     ptx::mbar_init(tfull, 1);
@@ -148,110 +150,120 @@ gemm_a16w4_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
   if (warp == 0) {
     // ================= TMA producer (one lane in each CTA) =================
     if (lane == 0) {
-      int s = 0; uint32_t ph = 0;
+      const uint32_t ready_leader = ptx::mapa(ptx::smem_u32(&ready[0]), 0u);
+      const int tok_off = (int)rank * (T2_BT / 2), feat_off = (int)rank * T2_BM;
+      uint32_t s = 0, ph = 0;
       for (int t = pair; t < ntiles; t += npairs) {
         const int tm = t % P.tiles_m, tn = t / P.tiles_m;
+        const int tok0 = tm * T2_BT + tok_off, feat0 = tn * 2 * T2_BM + feat_off;
         for (int kb = 0; kb < kblocks; ++kb) {
-          ptx::mbar_wait(&empty[s], ph ^ 1);
+          ptx::mbar_wait(&empty[s], ph ^ 1u);
           unsigned char* st = smem + s * T2_STAGE;
-          if (leader) ptx::mbar_arrive_expect_tx(&xfull[s], 2 * T2_X_BYTES);
-          ptx::tma_load_2d_2cta(st, &tmap_x, ptx::mapa(ptx::smem_u32(&xfull[s]), 0u), kb * T2_BK,
-                                tm * T2_BT + (int)rank * (T2_BT / 2));
+          if (leader) ptx::mbar_arrive_expect_tx(&ready[s], 2 * T2_X_BYTES);
+          ptx::tma_load_2d_2cta(st, &tmap_x, ready_leader + s * 8u, kb * T2_BK, tok0);
+          ptx::tma_load_2d_2cta(st + T2_XBOX_BYTES, &tmap_x, ready_leader + s * 8u, kb * T2_BK + 64, tok0);
           ptx::mbar_arrive_expect_tx(&wfull[s], T2_P_BYTES);
-          ptx::tma_load_2d(st + T2_X_BYTES, &tmap_w, &wfull[s], tn * 2 * T2_BM + (int)rank * T2_BM, kb * (T2_BK / 8));
-          if (++s == T2_STAGES) { s = 0; ph ^= 1; }
+          ptx::tma_load_2d(st + T2_X_BYTES, &tmap_w, &wfull[s], feat0, kb * (T2_BK / 8));
+          if (++s == T2_STAGES) { s = 0; ph ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer (leader CTA, one elected lane) =================
+    // ================= MMA issuer (leader CTA; the warp stays converged, one elected lane issues) =================
+    // The loop body is paid once per 8 MMAs (1024 tensor-core cycles): one barrier wait, one fence, 8 x tcgen05.mma
+    // whose operands are stage base + constants, one commit.
     if (leader) {
       constexpr uint32_t idesc = ptx::make_idesc(1u, BF16 ? 1u : 0u, BF16 ? 1u : 0u, 2 * T2_BM, T2_BT);
-      int s = 0; uint32_t ph = 0;
+      const uint64_t bdesc0 = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem));
+      uint32_t s = 0, ph = 0;
       int it = 0;
       for (int t = pair; t < ntiles; t += npairs, ++it) {
         ptx::mbar_wait(tempty, (uint32_t)(it & 1) ^ 1u);      // epilogue of the previous tile drained the accumulator
         ptx::tc_fence_after_sync();
         for (int kb = 0; kb < kblocks; ++kb) {
-          ptx::mbar_wait(&xfull[s], ph);
-          ptx::mbar_wait(&aready[s], ph);
+          ptx::mbar_wait(&ready[s], ph);
           ptx::tc_fence_after_sync();
           if (ptx::elect_one()) {
-            const uint64_t bdesc = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + s * T2_STAGE));
-            const uint32_t a_tmem = tmem_base + T2_ACOL0 + (uint32_t)s * 32u;
+            const uint64_t bd = bdesc0 + (uint64_t)(s * (uint32_t)(T2_STAGE >> 4));
+            const uint32_t at = tmem_base + T2_ACOL0 + s * T2_ACOLS;
 #pragma unroll
-            for (int k = 0; k < T2_BK / 16; ++k)     // K = 16 per instruction: 8 TMEM columns of A, 32 bytes of each B row
-              ptx::mma_f16_ts_2cta(tmem_base, a_tmem + (uint32_t)(8 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+            for (int k = 0; k < T2_BK / 16; ++k) {
+              // K = 16 per instruction: 8 TMEM columns of A; B: box k/4 (16 KB apart), 32 bytes (2 descriptor units) per step
+              const uint64_t bk = bd + (uint64_t)((k >> 2) * (T2_XBOX_BYTES >> 4) + (k & 3) * 2);
+              ptx::mma_f16_ts_2cta(tmem_base, at + (uint32_t)(8 * k), bk, idesc, (kb | k) ? 1u : 0u);
+            }
             ptx::mma_commit_2cta(&empty[s], (uint16_t)3);
             if (kb == kblocks - 1) ptx::mma_commit_2cta(tfull, (uint16_t)3);
           }
           __syncwarp();
-          if (++s == T2_STAGES) { s = 0; ph ^= 1; }
+          if (++s == T2_STAGES) { s = 0; ph ^= 1u; }
         }
       }
     }
   } else if (warp >= T2_DEQ_WARP0 && warp < T2_DEQ_WARP0 + T2_DEQ_WARPS) {
-    // ================= dequant: thread == feature row == TMEM lane; 4 packed words (32 k) per thread =================
+    // ================= dequant: thread == feature row == TMEM lane; 4 packed words (32 k) per thread and stage =================
     const int d = warp - T2_DEQ_WARP0;
     const int q4 = d & 3;                                   // TMEM lane quarter this warp may touch (== warp % 4)
     const int row = q4 * 32 + lane;                         // feature row inside this CTA's 128
-    const int half = (d >> 2) & 1;                          // which 32-k half of the 64-k block
-    const uint32_t parity = (uint32_t)(d >> 3);             // this warp serves k-blocks whose running index has this parity
-    const int kbpg = P.group_size >> 6;                     // k-blocks per quantisation group (group_size % 64 == 0)
-    const uint32_t taddr0 = tmem_base + ((uint32_t)(q4 * 32) << 16) + T2_ACOL0 + (uint32_t)half * 16u;
-    const uint32_t aready_leader = ptx::mapa(ptx::smem_u32(&aready[0]), 0u);
-    const uint32_t* pk0 = reinterpret_cast<const uint32_t*>(smem + T2_X_BYTES) + (half * 4) * T2_BM + row;
+    const int kq = d >> 2;                                  // which 32-k quarter of the 128-k stage
+    const uint32_t taddr0 = tmem_base + ((uint32_t)(q4 * 32) << 16) + T2_ACOL0 + (uint32_t)kq * 16u;
+    const uint32_t ready_leader = ptx::mapa(ptx::smem_u32(&ready[0]), 0u);
+    const uint32_t* pk0 = reinterpret_cast<const uint32_t*>(smem + T2_X_BYTES) + (kq * 4) * T2_BM + row;
     auto dup = [](uint16_t v) { return (uint32_t)v | ((uint32_t)v << 16); };
-    uint32_t cnt = 0;                                       // running k-block index over all tiles of this pair
+    uint32_t s = 0, ph = 0;
     int pend = -1;                                          // stage whose tcgen05.st is in flight (arrival still owed)
     for (int t = pair; t < ntiles; t += npairs) {
       const int tn = t / P.tiles_m;
       const int n = tn * 2 * T2_BM + (int)rank * T2_BM + row;
-      const uint16_t* sp = reinterpret_cast<const uint16_t*>(P.scales) + n;
-      const uint16_t* zp = (P.mode != 2) ? reinterpret_cast<const uint16_t*>(P.zeros) + n : sp;
-      uint32_t s2n = dup(*sp), z2n = (P.mode != 2) ? dup(*zp) : 0u;
-      for (int kb0 = 0; kb0 < kblocks; kb0 += kbpg) {
-        const uint32_t s2 = s2n, z2 = z2n;
-        if (kb0 + kbpg < kblocks) {                         // next group's metadata: requested now, consumed next round
-          sp += P.N; zp += P.N;
-          s2n = dup(*sp);
-          z2n = (P.mode != 2) ? dup(*zp) : 0u;
+      // this warp's k offsets are kq*32 + 128*kb: a 32-wide span never straddles a group (group_size % 32 == 0)
+      int g = (kq * 32) / P.group_size, rem = (kq * 32) % P.group_size;
+      const uint16_t* sp = reinterpret_cast<const uint16_t*>(P.scales) + (size_t)g * P.N + n;
+      const uint16_t* zp = (P.mode != 2) ? reinterpret_cast<const uint16_t*>(P.zeros) + (size_t)g * P.N + n : sp;
+      uint16_t sraw = *sp, zraw = (P.mode != 2) ? *zp : (uint16_t)0;   // raw: touching the value would stall on the load
+      uint32_t s2 = 0u, z2 = 0u;
+      bool fresh = true;                                    // sraw / zraw belong to a group not yet expanded into s2 / z2
+      for (int kb = 0; kb < kblocks; ++kb) {
+        if (fresh) { s2 = dup(sraw); z2 = dup(zraw); fresh = false; }
+        // where the next stage lands; if it is another group, request its metadata now and expand it next iteration
+        rem += T2_BK;
+        if (rem >= P.group_size && kb + 1 < kblocks) {
+          int adv = 0;
+          while (rem >= P.group_size) { rem -= P.group_size; ++adv; }
+          sp += (size_t)adv * P.N; zp += (size_t)adv * P.N;
+          sraw = *sp;
+          if (P.mode != 2) zraw = *zp;
+          fresh = true;
         }
-#pragma unroll 1
-        for (int j = 0; j < kbpg; ++j, ++cnt) {
-          if ((cnt & 1u) != parity) continue;
-          const uint32_t s = cnt & (T2_STAGES - 1), ph = (cnt >> 3) & 1u;
-          static_assert(T2_STAGES == 8, "stage / phase arithmetic above assumes an 8-deep ring");
-          ptx::mbar_wait(&wfull[s], ph);      // also implies the MMAs that last read A slot s completed (producer saw empty[s])
-          const uint32_t* pk = pk0 + s * (T2_STAGE / 4);
-          uint32_t w[4];
+        ptx::mbar_wait(&wfull[s], ph);        // also implies the MMAs that last read A slot s completed (producer saw empty[s])
+        const uint32_t* pk = pk0 + s * (uint32_t)(T2_STAGE / 4);
+        uint32_t w[4];
 #pragma unroll
-          for (int cc = 0; cc < 4; ++cc) w[cc] = pk[cc * T2_BM];
-          uint32_t o[16];
+        for (int cc = 0; cc < 4; ++cc) w[cc] = pk[cc * T2_BM];
+        uint32_t o[16];
 #pragma unroll
-          for (int cc = 0; cc < 4; ++cc) {
-            uint32_t q[4];
-            unpack8_nat<BF16>(w[cc], q);
+        for (int cc = 0; cc < 4; ++cc) {
+          uint32_t q[4];
+          unpack8_nat<BF16>(w[cc], q);
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) o[cc * 4 + jj] = dequant2_ref<BF16>(q[jj], s2, z2, P.mode);
-          }
-          if (pend >= 0) {                    // the previous block's store has had a whole block of arithmetic to land
-            ptx::tmem_st_wait();
-            ptx::tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive_cluster(aready_leader + (uint32_t)pend * 8u);
-          }
-          ptx::tc_fence_after_sync();
-          ptx::tmem_st_32x16(taddr0 + s * 32u, o);
-          pend = (int)s;
+          for (int jj = 0; jj < 4; ++jj) o[cc * 4 + jj] = dequant2_ref<BF16>(q[jj], s2, z2, P.mode);
         }
+        if (pend >= 0) {                      // the previous stage's store has had a whole stage of arithmetic to land
+          ptx::tmem_st_wait();
+          ptx::tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive_cluster(ready_leader + (uint32_t)pend * 8u);
+        }
+        ptx::tc_fence_after_sync();
+        ptx::tmem_st_32x16(taddr0 + s * T2_ACOLS, o);
+        pend = (int)s;
+        if (++s == T2_STAGES) { s = 0; ph ^= 1u; }
       }
     }
     if (pend >= 0) {
       ptx::tmem_st_wait();
       ptx::tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive_cluster(aready_leader + (uint32_t)pend * 8u);
+      if (lane == 0) ptx::mbar_arrive_cluster(ready_leader + (uint32_t)pend * 8u);
     }
   } else if (warp >= T2_EPI_WARP0) {
     // ================= epilogue: TMEM -> registers -> global (each CTA drains its own 128 feature rows) =================
@@ -310,7 +322,7 @@ gemm_a16w4_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
 template <bool BF16>
 int launch_tc2(const glb_linear& L, const void* x, void* y, int64_t M, const void* bias, cudaStream_t stream) {
   CUtensorMap tx, tw;
-  int rc = make_tmap_2d(&tx, BF16 ? GLB_BF16 : GLB_FP16, x, (uint64_t)L.K, (uint64_t)M, (uint64_t)L.K * 2, T2_BK, T2_BT / 2, 1);
+  int rc = make_tmap_2d(&tx, BF16 ? GLB_BF16 : GLB_FP16, x, (uint64_t)L.K, (uint64_t)M, (uint64_t)L.K * 2, 64, T2_BT / 2, 1);
   if (rc != GLB_OK) return rc;
   rc = make_tmap_2d(&tw, GLB_INT32, L.W_q, (uint64_t)L.N, (uint64_t)(L.K / 8), (uint64_t)L.N * 4, T2_BM, T2_BK / 8, 0);
   if (rc != GLB_OK) return rc;
@@ -347,7 +359,7 @@ int launch_tc2(const glb_linear& L, const void* x, void* y, int64_t M, const voi
 bool gemm_tc2_supported(const glb_linear& L, int64_t M) {
   if (M < 1) return false;
   if (L.N % (2 * T2_BM) != 0 || L.K % T2_BK != 0) return false;
-  if (L.group_size % T2_BK != 0) return false;       // a 64-wide k-block never straddles quantisation groups
+  if (L.group_size % 32 != 0) return false;          // a dequant warp's 32-wide k span never straddles quantisation groups
   return true;
 }
 

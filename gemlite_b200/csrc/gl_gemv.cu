@@ -647,7 +647,7 @@ gemv_w4_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
       if (P.mode == 3) zc = -zc * sc;
       const int pr = c >> 1, hi = (c & 1) * 2;        // c0,c2 -> rows 0-7 (d0,d1) ; c1,c3 -> rows 8-15 (d2,d3)
 #pragma unroll
-      for (int tk = 0; tk < 2; ++tk) {
+      for (int tk = 0; tk < ((MT == 1) ? 1 : 2); ++tk) {     // MT == 1: token 1 does not exist, skip its arithmetic
         const float d = dacc[pr][0][hi + tk] + dacc[pr][1][hi + tk];
         out[c][tk] = fmaf(sc, d - off[tk], fmaf(zc, sx[tk], out[c][tk]));
       }
