@@ -11,22 +11,24 @@
 //   * the dequantised weight tile never touches shared memory: dequant thread == feature row == TMEM lane,
 //     16 packed pairs per thread go to tensor memory with one tcgen05.st.32x32b.x16 and the MMA takes its A
 //     operand from there ([a_tmem] form).  No STS, no bank conflicts, no async-proxy fence;
-//   * a pipeline stage is 128 k wide (two 128B-swizzled x boxes of 16 KB + 8 KB of packed words = 40 KB, 4 stages;
-//     the A ring in TMEM is 4 x 64 columns next to the 256-column fp32 accumulator), so every per-stage cost --
-//     barrier round trips, the MMA issuer's loop body, the producer's bookkeeping -- is paid once per 8 MMAs
-//     (1024 tensor-core cycles).  The MMA issuer waits on ONE barrier per stage (`ready`: TMA bytes of both CTAs
-//     + the arrivals of all 32 dequant warps of the pair).
+//   * a pipeline stage is 128 k wide (two 128B-swizzled x boxes of 16 KB, 4 stages; the A ring in TMEM is
+//     4 x 64 columns next to the 256-column fp32 accumulator), so every per-stage cost -- barrier round trips,
+//     the MMA issuer's loop body, the producers' bookkeeping -- is paid once per 8 MMAs (1024 tensor-core cycles).
+//     The MMA issuer waits on ONE barrier per stage (`ready`: TMA bytes of both CTAs + the arrivals of all 32
+//     dequant warps of the pair);
+//   * the 8 KB packed-word tiles have their OWN 8-deep ring and producer: they are requested two A-ring
+//     revolutions ahead, so when the MMAs free A slot s the dequant warps find their input already in shared
+//     memory -- the TMA latency is no longer inside the free-slot -> ready chain (tensor pipe 74 % -> see profiles/).
 // Shared-memory traffic per CTA and 128 k: 32 KB operand reads + 40 KB TMA writes + 8 KB packed reads.
 //
 // Arithmetic contract is unchanged (see gl_gemm_tc.cu): weights are dequantised with the reference's rounding
 // (utils.py:57-89) and accumulated in fp32 by the tensor core (gemm_kernels.py:384).
 //
-// Warp roles per CTA (768 threads): w0 TMA producer, w1 MMA issuer (leader CTA only), w2 TMEM allocator,
-// w4-19 dequant (warp % 4 = TMEM lane quarter, (warp-4)/4 = which 32-k quarter of the stage), w20-23 epilogue.
-// A dequant warp sends the arrival for a stage one iteration late (after the NEXT stage's arithmetic), so its
-// tcgen05.st -> wait::st -> arrive chain is off the MMA's critical path.  Requires group_size % 32 == 0.
+// Warp roles per CTA (768 threads): w0 x producer, w1 MMA issuer (leader CTA only), w2 TMEM allocator, w3 packed-word
+// producer, w4-19 dequant (warp % 4 = TMEM lane quarter, (warp-4)/4 = which 32-k quarter of the stage), w20-23
+// epilogue.  Requires group_size % 32 == 0 and K % 128 == 0.
 // Barriers: ready / tempty live in the LEADER's shared memory (the peer reports to them remotely);
-// wfull / empty / tfull are per CTA; tcgen05.commit multicasts its arrival to both CTAs.
+// pfull / pfree / empty / tfull are per CTA; tcgen05.commit multicasts its arrival to both CTAs.
 // History of this kernel's profile: profiles/prefill_tc2_*_r1_ncu.txt.
 #include "gl_common.cuh"
 #include "gl_ptx.cuh"
@@ -43,8 +45,10 @@ constexpr int T2_DEQ_WARP0 = 4, T2_DEQ_WARPS = 16, T2_EPI_WARP0 = 20;   // 16 de
 constexpr int T2_XBOX_BYTES = (T2_BT / 2) * 64 * 2;        // one 64-k x box: 128 tokens x 128 B = 16 KB
 constexpr int T2_X_BYTES = 2 * T2_XBOX_BYTES;              // 32 KB
 constexpr int T2_P_BYTES = (T2_BK / 8) * T2_BM * 4;        // 8 KB
-constexpr int T2_STAGE = T2_X_BYTES + T2_P_BYTES;          // 40 KB
-constexpr int T2_SMEM = T2_STAGES * T2_STAGE + 1024 /* barriers */ + 1024 /* alignment slack */;
+constexpr int T2_PSTAGES = 8;                              // packed-word ring (decoupled from the x / A ring, see below)
+constexpr int T2_P_OFF = T2_STAGES * T2_X_BYTES;           // packed ring starts after the x ring (128 KB)
+constexpr int T2_BAR_OFF = T2_P_OFF + T2_PSTAGES * T2_P_BYTES;   // 192 KB
+constexpr int T2_SMEM = T2_BAR_OFF + 1024 /* barriers */ + 1024 /* alignment slack */;
 constexpr uint32_t T2_ACOL0 = 256;    // first TMEM column of the A ring (accumulator: columns 0..255)
 constexpr uint32_t T2_ACOLS = T2_BK / 2;   // 64 columns of A per stage
 
@@ -114,13 +118,14 @@ gemm_a16w4_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = smem_raw;
   if ((ptx::smem_u32(smem_raw) & 1023u) != 0u) __trap();
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + T2_STAGES * T2_STAGE);
-  uint64_t* ready = bars;                       // [STAGES] leader: x bytes of both CTAs landed + all 32 dequant warps wrote A slot s
-  uint64_t* wfull = bars + T2_STAGES;           // [STAGES] local : packed words landed
-  uint64_t* empty = bars + 2 * T2_STAGES;       // [STAGES] local : MMAs reading stage s completed (multicast commit)
-  uint64_t* tfull = bars + 3 * T2_STAGES;       // [1]      local : accumulator complete (multicast commit)
-  uint64_t* tempty = bars + 3 * T2_STAGES + 1;  // [1]      leader: both CTAs' epilogue warps drained it
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * T2_STAGES + 2);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + T2_BAR_OFF);
+  uint64_t* ready = bars;                         // [STAGES]  leader: x bytes of both CTAs landed + all 32 dequant warps wrote A slot s
+  uint64_t* empty = bars + T2_STAGES;             // [STAGES]  local : MMAs reading x stage / A slot s completed (multicast commit)
+  uint64_t* pfull = bars + 2 * T2_STAGES;         // [PSTAGES] local : packed words landed
+  uint64_t* pfree = pfull + T2_PSTAGES;           // [PSTAGES] local : all 16 dequant warps have read the packed words
+  uint64_t* tfull = pfree + T2_PSTAGES;           // [1]       local : accumulator complete (multicast commit)
+  uint64_t* tempty = tfull + 1;                   // [1]       leader: both CTAs' epilogue warps drained it
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = ptx::cluster_ctarank();
@@ -134,8 +139,11 @@ gemm_a16w4_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     ptx::prefetch_tmap(&tmap_w);
     for (int s = 0; s < T2_STAGES; ++s) {
       ptx::mbar_init(&ready[s], 1 + 2 * T2_DEQ_WARPS);   // the leader producer's expect_tx arrival + 32 dequant warps
-      ptx::mbar_init(&wfull[s], 1);
       ptx::mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < T2_PSTAGES; ++s) {
+      ptx::mbar_init(&pfull[s], 1);
+      ptx::mbar_init(&pfree[s], T2_DEQ_WARPS);
     }
     ptx::mbar_init(tfull, 1);
     ptx::mbar_init(tempty, 2 * 4);
@@ -148,23 +156,35 @@ gemm_a16w4_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ================= TMA producer (one lane in each CTA) =================
+    // ================= x producer (one lane in each CTA): follows the MMA's `empty` signal =================
     if (lane == 0) {
       const uint32_t ready_leader = ptx::mapa(ptx::smem_u32(&ready[0]), 0u);
-      const int tok_off = (int)rank * (T2_BT / 2), feat_off = (int)rank * T2_BM;
+      const int tok_off = (int)rank * (T2_BT / 2);
       uint32_t s = 0, ph = 0;
       for (int t = pair; t < ntiles; t += npairs) {
-        const int tm = t % P.tiles_m, tn = t / P.tiles_m;
-        const int tok0 = tm * T2_BT + tok_off, feat0 = tn * 2 * T2_BM + feat_off;
+        const int tok0 = (t % P.tiles_m) * T2_BT + tok_off;
         for (int kb = 0; kb < kblocks; ++kb) {
           ptx::mbar_wait(&empty[s], ph ^ 1u);
-          unsigned char* st = smem + s * T2_STAGE;
+          unsigned char* st = smem + s * T2_X_BYTES;
           if (leader) ptx::mbar_arrive_expect_tx(&ready[s], 2 * T2_X_BYTES);
           ptx::tma_load_2d_2cta(st, &tmap_x, ready_leader + s * 8u, kb * T2_BK, tok0);
           ptx::tma_load_2d_2cta(st + T2_XBOX_BYTES, &tmap_x, ready_leader + s * 8u, kb * T2_BK + 64, tok0);
-          ptx::mbar_arrive_expect_tx(&wfull[s], T2_P_BYTES);
-          ptx::tma_load_2d(st + T2_X_BYTES, &tmap_w, &wfull[s], feat0, kb * (T2_BK / 8));
           if (++s == T2_STAGES) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ================= packed-word producer: runs up to 8 k-blocks ahead, gated only by the dequant warps' reads =================
+    if (lane == 0) {
+      const int feat_off = (int)rank * T2_BM;
+      uint32_t s = 0, ph = 0;
+      for (int t = pair; t < ntiles; t += npairs) {
+        const int feat0 = (t / P.tiles_m) * 2 * T2_BM + feat_off;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          ptx::mbar_wait(&pfree[s], ph ^ 1u);
+          ptx::mbar_arrive_expect_tx(&pfull[s], T2_P_BYTES);
+          ptx::tma_load_2d(smem + T2_P_OFF + s * T2_P_BYTES, &tmap_w, &pfull[s], feat0, kb * (T2_BK / 8));
+          if (++s == T2_PSTAGES) { s = 0; ph ^= 1u; }
         }
       }
     }
@@ -184,7 +204,7 @@ gemm_a16w4_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
           ptx::mbar_wait(&ready[s], ph);
           ptx::tc_fence_after_sync();
           if (ptx::elect_one()) {
-            const uint64_t bd = bdesc0 + (uint64_t)(s * (uint32_t)(T2_STAGE >> 4));
+            const uint64_t bd = bdesc0 + (uint64_t)(s * (uint32_t)(T2_X_BYTES >> 4));
             const uint32_t at = tmem_base + T2_ACOL0 + s * T2_ACOLS;
 #pragma unroll
             for (int k = 0; k < T2_BK / 16; ++k) {
@@ -208,10 +228,10 @@ gemm_a16w4_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     const int kq = d >> 2;                                  // which 32-k quarter of the 128-k stage
     const uint32_t taddr0 = tmem_base + ((uint32_t)(q4 * 32) << 16) + T2_ACOL0 + (uint32_t)kq * 16u;
     const uint32_t ready_leader = ptx::mapa(ptx::smem_u32(&ready[0]), 0u);
-    const uint32_t* pk0 = reinterpret_cast<const uint32_t*>(smem + T2_X_BYTES) + (kq * 4) * T2_BM + row;
+    const uint32_t* pk0 = reinterpret_cast<const uint32_t*>(smem + T2_P_OFF) + (kq * 4) * T2_BM + row;
     auto dup = [](uint16_t v) { return (uint32_t)v | ((uint32_t)v << 16); };
-    uint32_t s = 0, ph = 0;
-    int pend = -1;                                          // stage whose tcgen05.st is in flight (arrival still owed)
+    uint32_t s = 0, ph = 0;                                 // x / A ring position
+    uint32_t ps = 0, pph = 0;                               // packed ring position
     for (int t = pair; t < ntiles; t += npairs) {
       const int tn = t / P.tiles_m;
       const int n = tn * 2 * T2_BM + (int)rank * T2_BM + row;
@@ -234,8 +254,9 @@ gemm_a16w4_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
           if (P.mode != 2) zraw = *zp;
           fresh = true;
         }
-        ptx::mbar_wait(&wfull[s], ph);        // also implies the MMAs that last read A slot s completed (producer saw empty[s])
-        const uint32_t* pk = pk0 + s * (uint32_t)(T2_STAGE / 4);
+        // 1. packed words (landed long ago in steady state) -> exact integers in registers; release the ring slot
+        ptx::mbar_wait(&pfull[ps], pph);
+        const uint32_t* pk = pk0 + ps * (uint32_t)(T2_P_BYTES / 4);
         uint32_t w[4];
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) w[cc] = pk[cc * T2_BM];
@@ -247,23 +268,19 @@ gemm_a16w4_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
 #pragma unroll
           for (int jj = 0; jj < 4; ++jj) o[cc * 4 + jj] = dequant2_ref<BF16>(q[jj], s2, z2, P.mode);
         }
-        if (pend >= 0) {                      // the previous stage's store has had a whole stage of arithmetic to land
-          ptx::tmem_st_wait();
-          ptx::tc_fence_before_sync();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive_cluster(ready_leader + (uint32_t)pend * 8u);
-        }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&pfree[ps]);          // every lane's LDS results have been consumed above
+        if (++ps == T2_PSTAGES) { ps = 0; pph ^= 1u; }
+        // 2. A slot s is free once the MMAs of its previous use completed; store, publish
+        ptx::mbar_wait(&empty[s], ph ^ 1u);
         ptx::tc_fence_after_sync();
         ptx::tmem_st_32x16(taddr0 + s * T2_ACOLS, o);
-        pend = (int)s;
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_cluster(ready_leader + s * 8u);
         if (++s == T2_STAGES) { s = 0; ph ^= 1u; }
       }
-    }
-    if (pend >= 0) {
-      ptx::tmem_st_wait();
-      ptx::tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive_cluster(ready_leader + (uint32_t)pend * 8u);
     }
   } else if (warp >= T2_EPI_WARP0) {
     // ================= epilogue: TMEM -> registers -> global (each CTA drains its own 128 feature rows) =================

@@ -234,8 +234,7 @@ def test_a16w4_prefill_pair_kernel_vs_oracle(dtype, mode, gs):
     for M in (129, 256, 300, 700):          # ragged last token block, one and several token blocks
         x = xgen(M, K, dtype, 90 + M)
         y = layer(x.to(DEV))
-        # the pair kernel takes groups that are whole 64-wide k-blocks; gs = 32 stays on the single-CTA tcgen05 kernel
-        assert _cabi.last_kernel() == ("gemm_a16w4_tcgen05_2cta" if gs % 64 == 0 else "gemm_a16w4_tcgen05"), _cabi.last_kernel()
+        assert _cabi.last_kernel() == "gemm_a16w4_tcgen05_2cta", _cabi.last_kernel()   # group_size % 32 == 0, K % 128 == 0
         e = relerr(y, O.forward(p, x))
         assert e <= REL[dtype], (dtype, mode, gs, M, e)
 
