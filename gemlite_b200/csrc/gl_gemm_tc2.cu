@@ -112,6 +112,20 @@ template <bool BF16> __device__ __forceinline__ uint32_t dequant2_ref(uint32_t q
   }
 }
 
+// Tile order: token blocks are walked in groups of T2_GROUP_M; inside a group the feature tile is the slow index.
+// The ~74 tiles in flight then share 4 token blocks (16 MB of x at K = 8192) instead of all of them: the x working
+// set of a wave stays resident in one die's share of the L2 (the r1 profile of the plain token-fastest order read x
+// from DRAM once per wave: 438 MB of DRAM reads for a 104 MB problem, and the x boxes arrived late).
+constexpr int T2_GROUP_M = 4;
+__device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int& tm, int& tn) {
+  const int per_group = T2_GROUP_M * tiles_n;
+  const int grp = t / per_group, r = t - grp * per_group;
+  const int m0 = grp * T2_GROUP_M;
+  const int gsz = (tiles_m - m0 < T2_GROUP_M) ? (tiles_m - m0) : T2_GROUP_M;     // last group may be short
+  tn = r / gsz;
+  tm = m0 + (r - tn * gsz);
+}
+
 template <bool BF16>
 __global__ void __launch_bounds__(T2_THREADS, 1)
 gemm_a16w4_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const Tc2Params P) {
@@ -162,7 +176,9 @@ gemm_a16w4_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       const int tok_off = (int)rank * (T2_BT / 2);
       uint32_t s = 0, ph = 0;
       for (int t = pair; t < ntiles; t += npairs) {
-        const int tok0 = (t % P.tiles_m) * T2_BT + tok_off;
+        int tm, tn;
+        tile_coords(t, P.tiles_m, P.tiles_n, tm, tn);
+        const int tok0 = tm * T2_BT + tok_off;
         for (int kb = 0; kb < kblocks; ++kb) {
           ptx::mbar_wait(&empty[s], ph ^ 1u);
           unsigned char* st = smem + s * T2_X_BYTES;
@@ -179,7 +195,9 @@ gemm_a16w4_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       const int feat_off = (int)rank * T2_BM;
       uint32_t s = 0, ph = 0;
       for (int t = pair; t < ntiles; t += npairs) {
-        const int feat0 = (t / P.tiles_m) * 2 * T2_BM + feat_off;
+        int tm, tn;
+        tile_coords(t, P.tiles_m, P.tiles_n, tm, tn);
+        const int feat0 = tn * 2 * T2_BM + feat_off;
         for (int kb = 0; kb < kblocks; ++kb) {
           ptx::mbar_wait(&pfree[s], ph ^ 1u);
           ptx::mbar_arrive_expect_tx(&pfull[s], T2_P_BYTES);
@@ -233,7 +251,8 @@ gemm_a16w4_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     uint32_t s = 0, ph = 0;                                 // x / A ring position
     uint32_t ps = 0, pph = 0;                               // packed ring position
     for (int t = pair; t < ntiles; t += npairs) {
-      const int tn = t / P.tiles_m;
+      int tm, tn;
+      tile_coords(t, P.tiles_m, P.tiles_n, tm, tn);
       const int n = tn * 2 * T2_BM + (int)rank * T2_BM + row;
       // this warp's k offsets are kq*32 + 128*kb: a 32-wide span never straddles a group (group_size % 32 == 0)
       int g = (kq * 32) / P.group_size, rem = (kq * 32) % P.group_size;
@@ -289,7 +308,8 @@ gemm_a16w4_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     const uint32_t tempty_leader = ptx::mapa(ptx::smem_u32(tempty), 0u);
     int it = 0;
     for (int t = pair; t < ntiles; t += npairs, ++it) {
-      const int tm = t % P.tiles_m, tn = t / P.tiles_m;
+      int tm, tn;
+      tile_coords(t, P.tiles_m, P.tiles_n, tm, tn);
       const int n = tn * 2 * T2_BM + (int)rank * T2_BM + row;
       float bv = 0.f;
       if (P.bias) bv = BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(P.bias)[n])
