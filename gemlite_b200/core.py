@@ -95,6 +95,7 @@ def get_matmul_type(batch_size: int, W_nbits: int, mx_dtype: bool = False) -> st
 # ---------------------------------------------------------------------------------------------------
 _DESC_CACHE = {}
 _WORKSPACE = {}
+_WS_BYTES = {}       # (descriptor id, M, matmul_type) -> workspace bytes the C library asked for (descriptors are cached, ids are stable)
 
 
 def _strides2(t: Tensor):
@@ -156,13 +157,27 @@ def _matmul(x2d: Tensor, bias: Optional[Tensor], tensor_args: List[Tensor], meta
         return out
     if bias is not None and (bias.dtype != out.dtype or not bias.is_contiguous()):
         bias = bias.to(out.dtype).contiguous()
-    with torch.cuda.device(x2d.device):
-        need = lib.glb_workspace_bytes(ctypes.byref(desc), M, matmul_type)
-        ws = _workspace(x2d.device, need)
+    dev = x2d.device
+    switch = dev.index is not None and dev.index != torch.cuda.current_device()
+    if switch:
+        prev = torch.cuda.current_device()
+        torch.cuda.set_device(dev)
+    try:
+        wkey = (id(desc), M, matmul_type)
+        need = _WS_BYTES.get(wkey)
+        if need is None:
+            need = lib.glb_workspace_bytes(ctypes.byref(desc), M, matmul_type)
+            if len(_WS_BYTES) > 65536:
+                _WS_BYTES.clear()
+            _WS_BYTES[wkey] = need
+        ws = _workspace(dev, need)
         rc = lib.glb_matmul(ctypes.byref(desc), x2d.data_ptr(),
                             scales_x.data_ptr() if scales_x is not None else None, out.data_ptr(), M, matmul_type,
                             ws.data_ptr() if ws is not None else None, ws.numel() if ws is not None else 0,
-                            bias.data_ptr() if bias is not None else None, _cabi.current_stream_ptr(x2d.device))
+                            bias.data_ptr() if bias is not None else None, _cabi.current_stream_ptr(dev))
+    finally:
+        if switch:
+            torch.cuda.set_device(prev)
     _cabi.check(rc, "glb_matmul")
     return out
 
@@ -177,11 +192,10 @@ def enable_activation_scaling(batch_size):
     return True
 
 
-@torch.library.custom_op(f"{_OP_NS}::forward_functional", mutates_args=())
-def forward_functional(x: Tensor, bias: Optional[Tensor], tensor_args: List[Tensor], meta_args: List[int],
-                       matmul_type: int = -1) -> Tensor:
-    """x (..., K) -> (..., N).  matmul_type: -1 auto (reference dispatch), else index into
-    GEMLITE_MATMUL_TYPES.  Dynamic-activation layers quantise x per token first (core.py:155-175)."""
+def _forward_eager(x: Tensor, bias: Optional[Tensor], tensor_args, meta_args, matmul_type: int = -1) -> Tensor:
+    """Body of the functional forward.  `GemLiteLinear.forward` calls it directly in eager mode: the custom-op
+    dispatcher below costs ~20 us per call on the host, ten launches' worth at decode sizes; it is only needed when
+    a compiler traces the module."""
     out_features = tensor_args[0].shape[1]
     if not x.is_contiguous():
         x = x.contiguous()
@@ -205,6 +219,14 @@ def forward_functional(x: Tensor, bias: Optional[Tensor], tensor_args: List[Tens
         raise TypeError(f"activations are {x2d.dtype}, layer expects {expected}")
     out = _matmul(x2d, bias, tensor_args, meta_args, scales_x, int(matmul_type))
     return out.view(out_shape)
+
+
+@torch.library.custom_op(f"{_OP_NS}::forward_functional", mutates_args=())
+def forward_functional(x: Tensor, bias: Optional[Tensor], tensor_args: List[Tensor], meta_args: List[int],
+                       matmul_type: int = -1) -> Tensor:
+    """x (..., K) -> (..., N).  matmul_type: -1 auto (reference dispatch), else index into
+    GEMLITE_MATMUL_TYPES.  Dynamic-activation layers quantise x per token first (core.py:155-175)."""
+    return _forward_eager(x, bias, tensor_args, meta_args, matmul_type)
 
 
 @torch.library.register_fake(f"{_OP_NS}::forward_functional")
@@ -395,7 +417,9 @@ class GemLiteLinear(torch.nn.Module):
                                   GEMLITE_MATMUL_TYPES_MAPPING[matmul_type])
 
     def forward_auto_no_warmup(self, x: Tensor) -> Tensor:
-        return forward_functional(x, self.bias, self.get_tensor_args(), self.get_meta_args())
+        if torch.compiler.is_compiling():      # traced: go through the registered op (fake impl, no graph break)
+            return forward_functional(x, self.bias, self.get_tensor_args(), self.get_meta_args())
+        return _forward_eager(x, self.bias, (self.W_q, self.scales, self.zeros), self.get_meta_args(), -1)
 
     # ---- config cache (API kept; there is nothing to autotune on this backend) ---------------------
     @staticmethod

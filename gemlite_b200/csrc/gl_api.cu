@@ -5,6 +5,10 @@
 #include <cuda.h>
 #include <mutex>
 
+#include <string.h>
+#include <mutex>
+#include <unordered_map>
+
 #include "gl_common.cuh"
 
 namespace glb {
@@ -40,8 +44,40 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+// Encoded tensor maps are cached: a decode call needs three (weights, scales, zeros) and cuTensorMapEncodeTiled costs
+// ~1 us each on the host -- more than the kernel's own launch.  Key = every argument; bounded, cleared when full.
+namespace {
+struct TmapKey {
+  uint64_t v[8];
+  bool operator==(const TmapKey& o) const { return memcmp(v, o.v, sizeof(v)) == 0; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = 1469598103934665603ull;
+    for (int i = 0; i < 8; ++i) { h ^= k.v[i]; h *= 1099511628211ull; }
+    return (size_t)h;
+  }
+};
+struct TmapVal { alignas(64) unsigned char b[128]; };
+std::mutex g_tmap_mu;
+std::unordered_map<TmapKey, TmapVal, TmapKeyHash> g_tmap_cache;
+}  // namespace
+
 int make_tmap_2d(void* out_tmap, int dt, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
                  uint32_t box_inner, uint32_t box_outer, int swizzle128) {
+  static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap is 128 bytes");
+  int dev = 0;
+  cudaGetDevice(&dev);
+  TmapKey key = {{(uint64_t)dt | ((uint64_t)dev << 32), (uint64_t)(uintptr_t)base, inner, outer, row_stride_bytes, box_inner,
+                  box_outer, (uint64_t)swizzle128}};
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    auto it = g_tmap_cache.find(key);
+    if (it != g_tmap_cache.end()) {
+      memcpy(out_tmap, it->second.b, 128);
+      return GLB_OK;
+    }
+  }
   EncodeTiledFn fn = get_encode_fn();
   GLB_REQUIRE(fn != nullptr, GLB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   CUtensorMapDataType cdt;
@@ -60,6 +96,13 @@ int make_tmap_2d(void* out_tmap, int dt, const void* base, uint64_t inner, uint6
                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   GLB_REQUIRE(r == CUDA_SUCCESS, GLB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    if (g_tmap_cache.size() > 8192) g_tmap_cache.clear();
+    TmapVal v;
+    memcpy(v.b, out_tmap, 128);
+    g_tmap_cache[key] = v;
+  }
   return GLB_OK;
 }
 
