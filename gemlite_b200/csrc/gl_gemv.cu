@@ -428,6 +428,7 @@ struct GemvTmaParams {
   const void* zeros;     // (G, N) or null
   int chunk_shift;       // log2(rows per weight chunk)
   int debug;             // diagnostics only: bit 0 skip the main loop, bit 1 skip the weight copies
+  int issue_mode;        // who issues the TMA copies (see the kernel)
 };
 
 constexpr int GT_GPW = 4;    // META_REGS: groups a warp may own (their scale / zero vectors live in registers)
@@ -475,20 +476,43 @@ gemv_w4_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
 #endif
   if (rec) ts[GLB_GEMV_TIMELINE ? 0 : 0] = gtimer();
   // ---- 1. weights + metadata -> shared memory by TMA (independent of the previous kernel) ----
-  if (threadIdx.x == 0) {
-    ptx::prefetch_tmap(&tmap_w);
-    ptx::prefetch_tmap(&tmap_s);
-    for (int c = 0; c <= GT_NCH; ++c) ptx::mbar_init(&bars[c], 1);
-    ptx::fence_mbar_init();
-    if (!META_REGS) {
-      const uint32_t meta_bytes = (uint32_t)Gc * 64u * (P.mode != 2 ? 2u : 1u);
-      ptx::mbar_arrive_expect_tx(&bars[GT_NCH], meta_bytes);
-      ptx::tma_load_2d(sbuf, &tmap_s, &bars[GT_NCH], col0, gbeg);
-      if (P.mode != 2) ptx::tma_load_2d(zbuf, &tmap_z, &bars[GT_NCH], col0, gbeg);
+  // P.issue_mode 0: thread 0 issues everything (one serial chain of ~12 asynchronous operations);
+  //          bit 1: wait for the metadata before griddepcontrol.wait;
+//          bit 0: the LAST GT_NCH + 1 warps issue one copy each, in parallel (each lane initialises the barrier it
+  //                 uses): shorter start -> first-byte latency, and high warp ids are favoured by the scheduler while
+  //                 the SM is still busy with the previous layer's main loop.
+  if ((P.issue_mode & 1) == 0 || P.bulk1d) {
+    if (threadIdx.x == 0) {
+      ptx::prefetch_tmap(&tmap_w);
+      ptx::prefetch_tmap(&tmap_s);
+      for (int c = 0; c <= GT_NCH; ++c) ptx::mbar_init(&bars[c], 1);
+      ptx::fence_mbar_init();
+      if (!META_REGS) {
+        const uint32_t meta_bytes = (uint32_t)Gc * 64u * (P.mode != 2 ? 2u : 1u);
+        ptx::mbar_arrive_expect_tx(&bars[GT_NCH], meta_bytes);
+        ptx::tma_load_2d(sbuf, &tmap_s, &bars[GT_NCH], col0, gbeg);
+        if (P.mode != 2) ptx::tma_load_2d(zbuf, &tmap_z, &bars[GT_NCH], col0, gbeg);
+      }
+      for (int c = 0; c < ((P.debug & 2) ? 0 : nch); ++c) {
+        ptx::mbar_arrive_expect_tx(&bars[c], (uint32_t)chunk_rows * 128u);
+        if (!P.bulk1d) ptx::tma_load_2d(wbuf + (size_t)c * chunk_rows * 128, &tmap_w, &bars[c], col0, (kbeg >> 3) + c * chunk_rows);
+      }
     }
-    for (int c = 0; c < ((P.debug & 2) ? 0 : nch); ++c) {
+  } else if (lane == 0 && warp >= NW - (GT_NCH + 1)) {
+    const int c = warp - (NW - (GT_NCH + 1));            // 0 .. GT_NCH-1: weight chunk c, GT_NCH: metadata
+    ptx::mbar_init(&bars[c], 1);
+    ptx::fence_mbar_init();
+    if (c == GT_NCH) {
+      if (!META_REGS) {
+        ptx::prefetch_tmap(&tmap_s);
+        const uint32_t meta_bytes = (uint32_t)Gc * 64u * (P.mode != 2 ? 2u : 1u);
+        ptx::mbar_arrive_expect_tx(&bars[GT_NCH], meta_bytes);
+        ptx::tma_load_2d(sbuf, &tmap_s, &bars[GT_NCH], col0, gbeg);
+        if (P.mode != 2) ptx::tma_load_2d(zbuf, &tmap_z, &bars[GT_NCH], col0, gbeg);
+      }
+    } else if (c < nch && !(P.debug & 2)) {
       ptx::mbar_arrive_expect_tx(&bars[c], (uint32_t)chunk_rows * 128u);
-      if (!P.bulk1d) ptx::tma_load_2d(wbuf + (size_t)c * chunk_rows * 128, &tmap_w, &bars[c], col0, (kbeg >> 3) + c * chunk_rows);
+      ptx::tma_load_2d(wbuf + (size_t)c * chunk_rows * 128, &tmap_w, &bars[c], col0, (kbeg >> 3) + c * chunk_rows);
     }
   }
   if (P.bulk1d) {
@@ -517,6 +541,12 @@ gemv_w4_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
     }
   }
   if (P.late_trigger == 0) pdl_launch_dependents();  // everything this CTA can do ahead of its input has been issued
+  if ((P.issue_mode & 2) && !META_REGS) {
+    // the metadata wait does not depend on the previous layer either: take it (and the barrier-init visibility it
+    // needs) before griddepcontrol.wait, off the x -> y critical path
+    __syncthreads();
+    ptx::mbar_wait(&bars[GT_NCH], 0);
+  }
 
   // ---- 2. x depends on the previous kernel: wait for it only now, then stage it permuted ----
   if (rec) ts[GLB_GEMV_TIMELINE ? 1 : 0] = gtimer();
@@ -583,7 +613,7 @@ gemv_w4_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
   const unsigned char* xb = reinterpret_cast<const unsigned char*>(xs + (size_t)(tok_ok ? g8 : 0) * Kc) + (2 * t4) * 16;
   const unsigned char* wl = wbuf + (2 * t4) * 128;
   const int sw0 = (g8 ^ (2 * t4)) << 4, sw1 = (g8 ^ (2 * t4 + 1)) << 4;   // swizzled chunk offsets for a = 0 / 1
-  if (!META_REGS) ptx::mbar_wait(&bars[GT_NCH], 0);               // scales / zeros landed
+  if (!META_REGS && !(P.issue_mode & 2)) ptx::mbar_wait(&bars[GT_NCH], 0);   // scales / zeros landed
   if (rec) ts[GLB_GEMV_TIMELINE ? 4 : 0] = gtimer();
 
 #pragma unroll
@@ -726,9 +756,11 @@ int launch_w4_tma(const glb_linear& L, const GemvParams& P0, int late_trigger, c
     int cr = rows_c / nch, sh = 0;
     while ((1 << sh) < cr) ++sh;
     P.chunk_shift = sh;
-    static int dbg = -1;
+    static int dbg = -1, issue = -1;
     if (dbg < 0) { const char* e = getenv("GLB_GEMV_DEBUG"); dbg = e ? atoi(e) : 0; }
+    if (issue < 0) { const char* e = getenv("GLB_GEMV_ISSUE"); issue = e ? atoi(e) : 3; }
     P.debug = dbg;
+    P.issue_mode = (NW > GT_NCH + 1) ? issue : (issue & 2);
   }
   const size_t smem = gemv_tma_smem_bytes<MT, KSPLIT, NW, META_REGS>(P0.K, P0.group_size);
   auto kern = gemv_w4_tma_kernel<BF16, MT, RPG, KSPLIT, FAST, NW, META_REGS>;
