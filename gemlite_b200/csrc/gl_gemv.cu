@@ -758,7 +758,7 @@ int launch_w4_tma(const glb_linear& L, const GemvParams& P0, int late_trigger, c
     P.chunk_shift = sh;
     static int dbg = -1, issue = -1;
     if (dbg < 0) { const char* e = getenv("GLB_GEMV_DEBUG"); dbg = e ? atoi(e) : 0; }
-    if (issue < 0) { const char* e = getenv("GLB_GEMV_ISSUE"); issue = e ? atoi(e) : 3; }
+    if (issue < 0) { const char* e = getenv("GLB_GEMV_ISSUE"); issue = e ? atoi(e) : 0; }   // measured r1 (profiles/decode_issue_sweep_r1.txt): 0 -> 3.59, 1 -> 3.61, 2 -> 3.71, 3 -> 3.89 us/layer
     P.debug = dbg;
     P.issue_mode = (NW > GT_NCH + 1) ? issue : (issue & 2);
   }
