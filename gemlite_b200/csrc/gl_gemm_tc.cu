@@ -565,6 +565,7 @@ bool a8w8_tc_supported(const glb_linear& L, int64_t M) {
 
 bool gemm_tc_supported(const glb_linear& L, int64_t M) {
   if (a8w8_tc_supported(L, M)) return true;
+  if (gemm_mx_tc2_supported(L, M)) return true;
   if (M < 1 || M > (1 << 24)) return false;
   if (!(L.input_dtype == GLB_FP16 || L.input_dtype == GLB_BF16)) return false;
   if (L.output_dtype != L.input_dtype || L.meta_dtype != L.input_dtype) return false;
@@ -598,6 +599,7 @@ int launch_gemm_tc(const glb_linear& L, const void* x, const float* scales_x, vo
     return GLB_T8(256);
 #undef GLB_T8
   }
+  if (gemm_mx_tc2_supported(L, M)) return launch_gemm_tc2(L, x, y, M, bias, stream);
   const bool bf = (L.input_dtype == GLB_BF16);
   {
     // large M: CTA-pair kernel with the weight operand in tensor memory (gl_gemm_tc2.cu); GLB_PREFILL_VARIANT=1 keeps

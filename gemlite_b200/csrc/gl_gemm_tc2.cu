@@ -130,7 +130,30 @@ __device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int
   tm = m0 + (r - tn * gsz);
 }
 
-template <bool BF16>
+// MXFP4 weights (A16W4_MXFP, config C5): two e2m1 codes per byte (even k = low nibble), storage (N, K/2) K-contiguous,
+// one e8m0 scale byte per 32 codes stored (K/32, N).  A dequant thread's 32-k span of a stage is exactly one group:
+// 16 bytes of codes + one scale.  sm_100a converts a byte to two fp16 values in one instruction
+// (cvt.rn.f16x2.e2m1x2 -> F2FP.F16.E2M1.UNPACK_B); fp16 compute multiplies by the group scale in fp16 (exact while the
+// product is a normal fp16 number), bf16 compute goes through fp32 (e2m1 x 2^e is always exact in bf16).
+__device__ __forceinline__ uint32_t e2m1x2_to_f16x2(uint32_t byte) {
+  uint32_t r;
+  asm("{\n\t.reg .b8 t;\n\tcvt.u8.u32 t, %1;\n\tcvt.rn.f16x2.e2m1x2 %0, t;\n\t}" : "=r"(r) : "r"(byte));
+  return r;
+}
+template <bool BF16> __device__ __forceinline__ uint32_t mx_scale_pair(uint32_t v16x2, float sf, uint32_t s16x2) {
+  if (!BF16) {
+    __half2 r = __hmul2(*reinterpret_cast<__half2*>(&v16x2), *reinterpret_cast<__half2*>(&s16x2));
+    return *reinterpret_cast<uint32_t*>(&r);
+  } else {
+    const float2 f = __half22float2(*reinterpret_cast<__half2*>(&v16x2));
+    __nv_bfloat162 r = __floats2bfloat162_rn(f.x * sf, f.y * sf);
+    return *reinterpret_cast<uint32_t*>(&r);
+  }
+}
+
+constexpr int WFMT_INT4 = 0, WFMT_MXFP4 = 1;
+
+template <bool BF16, int WFMT>
 __global__ void __launch_bounds__(T2_THREADS, 1)
 gemm_a16w4_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const Tc2Params P) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -205,7 +228,8 @@ gemm_a16w4_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         for (int kb = 0; kb < kblocks; ++kb) {
           ptx::mbar_wait(&pfree[s], ph ^ 1u);
           ptx::mbar_arrive_expect_tx(&pfull[s], T2_P_BYTES);
-          ptx::tma_load_2d(smem + T2_P_OFF + s * T2_P_BYTES, &tmap_w, &pfull[s], feat0, kb * (T2_BK / 8));
+          if (WFMT == WFMT_INT4) ptx::tma_load_2d(smem + T2_P_OFF + s * T2_P_BYTES, &tmap_w, &pfull[s], feat0, kb * (T2_BK / 8));
+          else ptx::tma_load_2d(smem + T2_P_OFF + s * T2_P_BYTES, &tmap_w, &pfull[s], kb * (T2_BK / 2), feat0);   // [64 B of codes][128 rows]
           if (++s == T2_PSTAGES) { s = 0; ph ^= 1u; }
         }
       }
@@ -258,38 +282,73 @@ gemm_a16w4_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       int tm, tn;
       tile_coords(t, P.tiles_m, P.tiles_n, tm, tn);
       const int n = tn * 2 * T2_BM + (int)rank * T2_BM + row;
+      uint32_t o[16];
+      // ---------------- INT4 grouped metadata state ----------------
       // this warp's k offsets are kq*32 + 128*kb: a 32-wide span never straddles a group (group_size % 32 == 0)
-      int g = (kq * 32) / P.group_size, rem = (kq * 32) % P.group_size;
-      const uint16_t* sp = reinterpret_cast<const uint16_t*>(P.scales) + (size_t)g * P.N + n;
-      const uint16_t* zp = (P.mode != 2) ? reinterpret_cast<const uint16_t*>(P.zeros) + (size_t)g * P.N + n : sp;
-      uint16_t sraw = *sp, zraw = (P.mode != 2) ? *zp : (uint16_t)0;   // raw: touching the value would stall on the load
+      int g = 0, rem = 0;
+      const uint16_t* sp = nullptr;
+      const uint16_t* zp = nullptr;
+      uint16_t sraw = 0, zraw = 0;                          // raw: touching the value would stall on the load
       uint32_t s2 = 0u, z2 = 0u;
       bool fresh = true;                                    // sraw / zraw belong to a group not yet expanded into s2 / z2
+      // ---------------- MXFP4 metadata state: one e8m0 byte per stage, row stride N, requested one stage ahead ----------------
+      const uint8_t* mxp = nullptr;
+      uint8_t mxraw = 0;
+      if (WFMT == WFMT_INT4) {
+        g = (kq * 32) / P.group_size; rem = (kq * 32) % P.group_size;
+        sp = reinterpret_cast<const uint16_t*>(P.scales) + (size_t)g * P.N + n;
+        zp = (P.mode != 2) ? reinterpret_cast<const uint16_t*>(P.zeros) + (size_t)g * P.N + n : sp;
+        sraw = *sp; zraw = (P.mode != 2) ? *zp : (uint16_t)0;
+      } else {
+        mxp = reinterpret_cast<const uint8_t*>(P.scales) + (size_t)kq * P.N + n;
+        mxraw = *mxp;
+      }
       for (int kb = 0; kb < kblocks; ++kb) {
-        if (fresh) { s2 = dup(sraw); z2 = dup(zraw); fresh = false; }
-        // where the next stage lands; if it is another group, request its metadata now and expand it next iteration
-        rem += T2_BK;
-        if (rem >= P.group_size && kb + 1 < kblocks) {
-          int adv = 0;
-          while (rem >= P.group_size) { rem -= P.group_size; ++adv; }
-          sp += (size_t)adv * P.N; zp += (size_t)adv * P.N;
-          sraw = *sp;
-          if (P.mode != 2) zraw = *zp;
-          fresh = true;
+        float mx_sf = 0.f;
+        uint32_t mx_s16 = 0u;
+        if (WFMT == WFMT_INT4) {
+          if (fresh) { s2 = dup(sraw); z2 = dup(zraw); fresh = false; }
+          // where the next stage lands; if it is another group, request its metadata now and expand it next iteration
+          rem += T2_BK;
+          if (rem >= P.group_size && kb + 1 < kblocks) {
+            int adv = 0;
+            while (rem >= P.group_size) { rem -= P.group_size; ++adv; }
+            sp += (size_t)adv * P.N; zp += (size_t)adv * P.N;
+            sraw = *sp;
+            if (P.mode != 2) zraw = *zp;
+            fresh = true;
+          }
+        } else {
+          const uint32_t e = mxraw;
+          mx_sf = e8m0_to_float(e);
+          const __half2 h = __float2half2_rn(mx_sf);
+          mx_s16 = *reinterpret_cast<const uint32_t*>(&h);
+          if (kb + 1 < kblocks) { mxp += (size_t)4 * P.N; mxraw = *mxp; }
         }
-        // 1. packed words (landed long ago in steady state) -> exact integers in registers; release the ring slot
+        // 1. packed words (landed long ago in steady state) -> dequantised pairs in registers; release the ring slot
         ptx::mbar_wait(&pfull[ps], pph);
-        const uint32_t* pk = pk0 + ps * (uint32_t)(T2_P_BYTES / 4);
-        uint32_t w[4];
+        if (WFMT == WFMT_INT4) {
+          const uint32_t* pk = pk0 + ps * (uint32_t)(T2_P_BYTES / 4);
+          uint32_t w[4];
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) w[cc] = pk[cc * T2_BM];
-        uint32_t o[16];
+          for (int cc = 0; cc < 4; ++cc) w[cc] = pk[cc * T2_BM];
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          uint32_t q[4];
-          unpack8_nat<BF16>(w[cc], q);
+          for (int cc = 0; cc < 4; ++cc) {
+            uint32_t q[4];
+            unpack8_nat<BF16>(w[cc], q);
 #pragma unroll
-          for (int jj = 0; jj < 4; ++jj) o[cc * 4 + jj] = dequant2_ref<BF16>(q[jj], s2, z2, P.mode);
+            for (int jj = 0; jj < 4; ++jj) o[cc * 4 + jj] = dequant2_ref<BF16>(q[jj], s2, z2, P.mode);
+          }
+        } else {
+          // row r of the tile is 64 bytes (128 codes); this thread's 32 codes are bytes kq*16 .. kq*16+15
+          const uint4 wv = *reinterpret_cast<const uint4*>(smem + T2_P_OFF + ps * T2_P_BYTES + row * 64 + kq * 16);
+          const uint32_t w[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+              o[cc * 4 + jj] = mx_scale_pair<BF16>(e2m1x2_to_f16x2(w[cc] >> (8 * jj)), mx_sf, mx_s16);
+          }
         }
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&pfree[ps]);          // every lane's LDS results have been consumed above
@@ -360,19 +419,22 @@ gemm_a16w4_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
   if (warp == T2_ALLOC_WARP) ptx::tmem_dealloc_2cta(tmem_base, 512);
 }
 
-template <bool BF16>
+template <bool BF16, int WFMT>
 int launch_tc2(const glb_linear& L, const void* x, void* y, int64_t M, const void* bias, cudaStream_t stream) {
   CUtensorMap tx, tw;
   int rc = make_tmap_2d(&tx, BF16 ? GLB_BF16 : GLB_FP16, x, (uint64_t)L.K, (uint64_t)M, (uint64_t)L.K * 2, 64, T2_BT / 2, 1);
   if (rc != GLB_OK) return rc;
-  rc = make_tmap_2d(&tw, GLB_INT32, L.W_q, (uint64_t)L.N, (uint64_t)(L.K / 8), (uint64_t)L.N * 4, T2_BM, T2_BK / 8, 0);
+  if (WFMT == WFMT_INT4)
+    rc = make_tmap_2d(&tw, GLB_INT32, L.W_q, (uint64_t)L.N, (uint64_t)(L.K / 8), (uint64_t)L.N * 4, T2_BM, T2_BK / 8, 0);
+  else   // (N, K/2) bytes, K contiguous: box = 64 bytes of codes x 128 feature rows
+    rc = make_tmap_2d(&tw, GLB_UINT8, L.W_q, (uint64_t)(L.K / 2), (uint64_t)L.N, (uint64_t)(L.K / 2), T2_BK / 2, T2_BM, 0);
   if (rc != GLB_OK) return rc;
   Tc2Params P;
   P.scales = L.scales; P.zeros = (L.W_group_mode == 2) ? nullptr : L.zeros;
   P.y = y; P.bias = bias; P.M = (int)M; P.N = (int)L.N; P.K = (int)L.K;
   P.group_size = L.group_size; P.mode = L.W_group_mode;
   P.tiles_m = (int)((M + T2_BT - 1) / T2_BT); P.tiles_n = (int)(L.N / (2 * T2_BM));
-  auto kern = gemm_a16w4_tc2_kernel<BF16>;
+  auto kern = gemm_a16w4_tc2_kernel<BF16, WFMT>;
   static thread_local bool configured = false;
   if (!configured) {
     GLB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM));
@@ -404,10 +466,30 @@ bool gemm_tc2_supported(const glb_linear& L, int64_t M) {
   return true;
 }
 
+// MXFP4 weight-only layers (A16W4_MXFP: input_dtype MXFP16 / MXBF16, e2m1 codes two per byte, e8m0 scales per 32)
+bool gemm_mx_tc2_supported(const glb_linear& L, int64_t M) {
+  if (M < 1) return false;
+  if (!(L.input_dtype == GLB_MXFP16 || L.input_dtype == GLB_MXBF16)) return false;
+  if (L.W_nbits != 4 || L.elements_per_sample != 2 || L.wq_dtype != GLB_UINT8 || L.group_size != 32) return false;
+  if (L.W_group_mode != 2 || L.channel_scale_mode != 0) return false;
+  if (L.wq_stride0 != 1 || L.wq_stride1 != L.K / 2) return false;                 // (K/2, N) view of (N, K/2)
+  if (!(L.scales_dtype == GLB_UINT8 || L.scales_dtype == GLB_E8M0)) return false;
+  if (L.scales_numel != (L.K / 32) * L.N || L.s_stride0 != 1 || L.s_stride1 != L.N) return false;   // (N, K/32) view of (K/32, N)
+  if (L.output_dtype != L.input_dtype) return false;
+  if (L.N % (2 * T2_BM) != 0 || L.K % T2_BK != 0) return false;
+  if (reinterpret_cast<uintptr_t>(L.W_q) & 15) return false;
+  return true;
+}
+
 int launch_gemm_tc2(const glb_linear& L, const void* x, void* y, int64_t M, const void* bias, cudaStream_t stream) {
+  if (gemm_mx_tc2_supported(L, M)) {
+    set_kernel_name("gemm_a16w4_mxfp4_tcgen05_2cta");
+    return (L.input_dtype == GLB_MXBF16) ? launch_tc2<true, WFMT_MXFP4>(L, x, y, M, bias, stream)
+                                         : launch_tc2<false, WFMT_MXFP4>(L, x, y, M, bias, stream);
+  }
   const bool bf = (L.input_dtype == GLB_BF16);
   set_kernel_name("gemm_a16w4_tcgen05_2cta");
-  return bf ? launch_tc2<true>(L, x, y, M, bias, stream) : launch_tc2<false>(L, x, y, M, bias, stream);
+  return bf ? launch_tc2<true, WFMT_INT4>(L, x, y, M, bias, stream) : launch_tc2<false, WFMT_INT4>(L, x, y, M, bias, stream);
 }
 
 }  // namespace glb

@@ -375,6 +375,34 @@ def test_mxfp_weight_only_vs_oracle_and_unquantised():
             assert (lin(x.to(DEV)) - y).abs().mean().item() < tol_q
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_mxfp4_pair_kernel_vs_oracle(dtype):
+    """A16W4_MXFP on the CTA-pair tcgen05 kernel (e2m1 codes -> cvt.rn.f16x2.e2m1x2 -> tensor memory): random codes
+    (all 16 patterns incl. -0) and a wide band of e8m0 exponents; e2m1 x 2^e is exact in bf16 (and in fp16 inside
+    its normal range), so the only difference to the oracle is fp32 accumulation order."""
+    N, K = 512, 1024
+    g = torch.Generator().manual_seed(11)
+    codes = torch.randint(0, 16, (N, K), generator=g, dtype=torch.int32).to(torch.uint8)
+    lo, hi = (105, 131) if dtype == torch.bfloat16 else (117, 126)
+    sc = torch.randint(lo, hi, (N, K // 32), generator=g, dtype=torch.int32).to(torch.uint8).view(torch.float8_e8m0fnu)
+    bias = (torch.randn(N, generator=g) / 10).to(dtype)
+    layer = A16W4_MXFP(device=DEV, dtype=dtype).from_weights(codes.to(DEV), sc.to(DEV), bias=bias.to(DEV))
+    gd = O.MXFP16 if dtype == torch.float16 else O.MXBF16
+    p = O.prepare(codes, sc, None, W_nbits=4, group_size=32, in_features=K, out_features=N, input_dtype=gd, output_dtype=gd,
+                  bias=bias)
+    assert torch.equal(layer.W_q.data.cpu().contiguous().view(torch.uint8), p.W_q.contiguous().view(torch.uint8))
+    for M in (1, 7, 300):
+        x = xgen(M, K, dtype, 300 + M)
+        y = layer(x.to(DEV))
+        assert _cabi.last_kernel() == "gemm_a16w4_mxfp4_tcgen05_2cta", _cabi.last_kernel()
+        assert y.dtype == dtype and relerr(y, O.forward(p, x)) <= REL[dtype], (dtype, M)
+    # x = identity: every output is one dequantised weight -> bit-exact against the oracle's table * 2^(e-127)
+    layer_nb = A16W4_MXFP(device=DEV, dtype=dtype).from_weights(codes.to(DEV), sc.to(DEV))
+    p.bias = None
+    x = torch.eye(K, dtype=dtype)
+    assert torch.equal(layer_nb(x.to(DEV)).cpu(), O.forward(p, x))
+
+
 def test_bitnet_and_state_dict_roundtrip(tmp_path):
     N, K = 128, 512
     g = torch.Generator().manual_seed(4)
