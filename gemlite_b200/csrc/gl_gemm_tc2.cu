@@ -30,6 +30,8 @@
 // Barriers: ready / tempty live in the LEADER's shared memory (the peer reports to them remotely);
 // pfull / pfree / empty / tfull are per CTA; tcgen05.commit multicasts its arrival to both CTAs.
 // History of this kernel's profile: profiles/prefill_tc2_*_r1_ncu.txt.
+#include <stdlib.h>
+
 #include "gl_common.cuh"
 #include "gl_ptx.cuh"
 
@@ -66,6 +68,7 @@ struct Tc2Params {
   int mode;
   int tiles_m;            // 256-token blocks
   int tiles_n;            // 256-feature blocks
+  int prefetch;           // x stages of L2 prefetch distance (0 = off)
 };
 
 template <bool BF16> __device__ __forceinline__ void unpack8_nat(uint32_t q, uint32_t (&o)[4]) {
@@ -212,6 +215,10 @@ gemm_a16w4_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
           if (leader) ptx::mbar_arrive_expect_tx(&ready[s], 2 * T2_X_BYTES);
           ptx::tma_load_2d_2cta(st, &tmap_x, ready_leader + s * 8u, kb * T2_BK, tok0);
           ptx::tma_load_2d_2cta(st + T2_XBOX_BYTES, &tmap_x, ready_leader + s * 8u, kb * T2_BK + 64, tok0);
+          if (P.prefetch && kb + P.prefetch < kblocks) {      // warm the L2 for the stage `prefetch` ahead of this one
+            ptx::tma_prefetch_2d(&tmap_x, (kb + P.prefetch) * T2_BK, tok0);
+            ptx::tma_prefetch_2d(&tmap_x, (kb + P.prefetch) * T2_BK + 64, tok0);
+          }
           if (++s == T2_STAGES) { s = 0; ph ^= 1u; }
         }
       }
@@ -434,6 +441,11 @@ int launch_tc2(const glb_linear& L, const void* x, void* y, int64_t M, const voi
   P.y = y; P.bias = bias; P.M = (int)M; P.N = (int)L.N; P.K = (int)L.K;
   P.group_size = L.group_size; P.mode = L.W_group_mode;
   P.tiles_m = (int)((M + T2_BT - 1) / T2_BT); P.tiles_n = (int)(L.N / (2 * T2_BM));
+  {
+    static int pf = -1;
+    if (pf < 0) { const char* e = getenv("GLB_PREFILL_PREFETCH"); pf = e ? atoi(e) : 0; }
+    P.prefetch = pf;
+  }
   auto kern = gemm_a16w4_tc2_kernel<BF16, WFMT>;
   static thread_local bool configured = false;
   if (!configured) {

@@ -243,7 +243,7 @@ def test_a16w4_prefill_pair_kernel_vs_oracle(dtype, mode, gs):
 def test_prefill_pair_kernel_dequant_is_bit_exact(dtype):
     """x = identity => y[m, n] is the dequantised weight W[n, m] itself (one non-zero product per output, fp32
     accumulate): the tensor-memory operand must hold exactly the reference's dequantize() values (utils.py:57-89)."""
-    N, K, gs = 512, 256, 64
+    N, K, gs = 512, 512, 64
     W_q, scales, zeros = gen_int(N, K, 4, gs, dtype, seed=5)
     gd = gemlite_b200.dtypes.TORCH_TO_DTYPE[dtype]
     layer = GemLiteLinear(4, gs, K, N, gd, gd).pack(W_q.to(DEV), scales.to(DEV), zeros.to(DEV))
