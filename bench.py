@@ -267,13 +267,17 @@ def run_ours(args, rank, world, local_rank):
 
     def step_body():
         x = x_in
-        for i, layer in enumerate(layers):
+        if world > 1:
+            # shard outputs are collected for the single gather with ONE concatenation at the end of the step (a copy
+            # per layer would put a non-PDL kernel between every two decode launches)
+            ys = [layer(x) for layer in layers]
+            torch.stack(ys, out=outs)
+            return outs
+        for layer in layers:
             y = layer(x)
-            if world > 1:
-                outs[i].copy_(y)      # shard outputs collected for the single gather
-            elif not INDEPENDENT:
+            if not INDEPENDENT:
                 x = y
-        return x if world == 1 else outs
+        return x
 
     # warm up eagerly (module load, smem opt-in), then capture the step in a CUDA graph
     for _ in range(2):
