@@ -140,7 +140,8 @@ def _workspace(device, nbytes: int) -> Optional[Tensor]:
     key = (device, torch.cuda.current_stream(device).cuda_stream)
     ws = _WORKSPACE.get(key)
     if ws is None or ws.numel() < nbytes:
-        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        # zero-initialised: the split-K kernels keep per-slice arrival counters in it and leave them at zero again
+        ws = torch.zeros(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
         _WORKSPACE[key] = ws
     return ws
 

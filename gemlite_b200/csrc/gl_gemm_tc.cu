@@ -582,11 +582,23 @@ bool gemm_tc_supported(const glb_linear& L, int64_t M) {
   return true;
 }
 
-size_t gemm_tc_workspace(const glb_linear&, int64_t) { return 0; }
+// which A16W4 / MXFP4 launches go to the CTA-pair kernel (gl_gemm_tc2.cu): MXFP4 always; INT4 above the decode range
+// (GLB_PREFILL_VARIANT=1 keeps the single-CTA kernel for A/B comparisons)
+static bool use_pair_kernel(const glb_linear& L, int64_t M) {
+  if (gemm_mx_tc2_supported(L, M)) return true;
+  static int variant = -1;
+  if (variant < 0) { const char* e = getenv("GLB_PREFILL_VARIANT"); variant = e ? atoi(e) : 2; }
+  if (a8w8_tc_supported(L, M)) return false;
+  return variant != 1 && M > 16 && gemm_tc2_supported(L, M);
+}
+
+size_t gemm_tc_workspace(const glb_linear& L, int64_t M) {
+  if (!gemm_tc_supported(L, M)) return 0;
+  return use_pair_kernel(L, M) ? gemm_tc2_workspace(L, M) : 0;
+}
 
 int launch_gemm_tc(const glb_linear& L, const void* x, const float* scales_x, void* y, int64_t M, void* workspace,
                    size_t ws_bytes, const void* bias, cudaStream_t stream) {
-  (void)workspace; (void)ws_bytes;
   GLB_REQUIRE(gemm_tc_supported(L, M), GLB_ERR_UNSUPPORTED, "tcgen05 GEMM: unsupported layer configuration");
   GLB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, GLB_ERR_INVALID, "tcgen05 GEMM: x must be 16-byte aligned");
   if (a8w8_tc_supported(L, M)) {
@@ -599,15 +611,8 @@ int launch_gemm_tc(const glb_linear& L, const void* x, const float* scales_x, vo
     return GLB_T8(256);
 #undef GLB_T8
   }
-  if (gemm_mx_tc2_supported(L, M)) return launch_gemm_tc2(L, x, y, M, bias, stream);
+  if (use_pair_kernel(L, M)) return launch_gemm_tc2(L, x, y, M, workspace, ws_bytes, bias, stream);
   const bool bf = (L.input_dtype == GLB_BF16);
-  {
-    // large M: CTA-pair kernel with the weight operand in tensor memory (gl_gemm_tc2.cu); GLB_PREFILL_VARIANT=1 keeps
-    // the single-CTA kernel below for A/B comparisons
-    static int variant = -1;
-    if (variant < 0) { const char* e = getenv("GLB_PREFILL_VARIANT"); variant = e ? atoi(e) : 2; }
-    if (variant != 1 && M > 128 && gemm_tc2_supported(L, M)) return launch_gemm_tc2(L, x, y, M, bias, stream);
-  }
   set_kernel_name("gemm_a16w4_tcgen05");
   if (M <= 32) return bf ? launch_tc<true, 32>(L, x, y, M, bias, stream) : launch_tc<false, 32>(L, x, y, M, bias, stream);
   if (M <= 64) return bf ? launch_tc<true, 64>(L, x, y, M, bias, stream) : launch_tc<false, 64>(L, x, y, M, bias, stream);

@@ -31,6 +31,7 @@
 // pfull / pfree / empty / tfull are per CTA; tcgen05.commit multicasts its arrival to both CTAs.
 // History of this kernel's profile: profiles/prefill_tc2_*_r1_ncu.txt.
 #include <stdlib.h>
+#include <algorithm>
 
 #include "gl_common.cuh"
 #include "gl_ptx.cuh"
@@ -69,6 +70,14 @@ struct Tc2Params {
   int tiles_m;            // 256-token blocks
   int tiles_n;            // 256-feature blocks
   int prefetch;           // x stages of L2 prefetch distance (0 = off)
+  // split-K (few tiles, e.g. M <= 256 on a 4096-wide layer): work item = (tile, split); every CTA writes its fp32 partial
+  // slice to `ws_partial`, the LAST epilogue warp to finish a slice (per-slice counter) sums the partials in split order
+  // -> deterministic, no second kernel, counters return to zero
+  int splits;             // >= 1
+  int kb_per_split;       // 128-k stages per work item
+  int n_mma;              // MMA N (tokens per tile actually computed): 64 / 128 / 256
+  float* ws_partial;      // [tile][split][rank][128 rows][n_mma]  (splits > 1)
+  int* ws_counter;        // [tile][rank][quarter], zero on entry and on exit
 };
 
 template <bool BF16> __device__ __forceinline__ void unpack8_nat(uint32_t q, uint32_t (&o)[4]) {
@@ -175,8 +184,8 @@ gemm_a16w4_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
   const uint32_t rank = ptx::cluster_ctarank();
   const bool leader = (rank == 0);
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-  const int kblocks = P.K / T2_BK;
-  const int ntiles = P.tiles_m * P.tiles_n;
+  const int kblocks = P.kb_per_split;                 // stages per work item
+  const int ntiles = P.tiles_m * P.tiles_n * P.splits;   // work items; item w = (tile w / splits, split w % splits)
 
   if (warp == T2_XPROD_WARP && lane == 0) {
     ptx::prefetch_tmap(&tmap_x);
@@ -203,19 +212,20 @@ gemm_a16w4_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     // ================= x producer (one lane in each CTA): follows the MMA's `empty` signal =================
     if (lane == 0) {
       const uint32_t ready_leader = ptx::mapa(ptx::smem_u32(&ready[0]), 0u);
-      const int tok_off = (int)rank * (T2_BT / 2);
+      const int tok_off = (int)rank * (P.n_mma / 2);     // B rows of the MMA: tokens [0, n/2) from the leader, [n/2, n) from the peer
       uint32_t s = 0, ph = 0;
       for (int t = pair; t < ntiles; t += npairs) {
         int tm, tn;
-        tile_coords(t, P.tiles_m, P.tiles_n, tm, tn);
+        tile_coords(t / P.splits, P.tiles_m, P.tiles_n, tm, tn);
         const int tok0 = tm * T2_BT + tok_off;
-        for (int kb = 0; kb < kblocks; ++kb) {
+        const int kb0 = (t % P.splits) * kblocks;
+        for (int kb = kb0; kb < kb0 + kblocks; ++kb) {
           ptx::mbar_wait(&empty[s], ph ^ 1u);
           unsigned char* st = smem + s * T2_X_BYTES;
           if (leader) ptx::mbar_arrive_expect_tx(&ready[s], 2 * T2_X_BYTES);
           ptx::tma_load_2d_2cta(st, &tmap_x, ready_leader + s * 8u, kb * T2_BK, tok0);
           ptx::tma_load_2d_2cta(st + T2_XBOX_BYTES, &tmap_x, ready_leader + s * 8u, kb * T2_BK + 64, tok0);
-          if (P.prefetch && kb + P.prefetch < kblocks) {      // warm the L2 for the stage `prefetch` ahead of this one
+          if (P.prefetch && kb + P.prefetch < kb0 + kblocks) {      // warm the L2 for the stage `prefetch` ahead of this one
             ptx::tma_prefetch_2d(&tmap_x, (kb + P.prefetch) * T2_BK, tok0);
             ptx::tma_prefetch_2d(&tmap_x, (kb + P.prefetch) * T2_BK + 64, tok0);
           }
@@ -230,9 +240,10 @@ gemm_a16w4_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       uint32_t s = 0, ph = 0;
       for (int t = pair; t < ntiles; t += npairs) {
         int tm, tn;
-        tile_coords(t, P.tiles_m, P.tiles_n, tm, tn);
+        tile_coords(t / P.splits, P.tiles_m, P.tiles_n, tm, tn);
         const int feat0 = tn * 2 * T2_BM + feat_off;
-        for (int kb = 0; kb < kblocks; ++kb) {
+        const int kb0 = (t % P.splits) * kblocks;
+        for (int kb = kb0; kb < kb0 + kblocks; ++kb) {
           ptx::mbar_wait(&pfree[s], ph ^ 1u);
           ptx::mbar_arrive_expect_tx(&pfull[s], T2_P_BYTES);
           if (WFMT == WFMT_INT4) ptx::tma_load_2d(smem + T2_P_OFF + s * T2_P_BYTES, &tmap_w, &pfull[s], feat0, kb * (T2_BK / 8));
@@ -246,7 +257,7 @@ gemm_a16w4_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     // The loop body is paid once per 8 MMAs (1024 tensor-core cycles): one barrier wait, one fence, 8 x tcgen05.mma
     // whose operands are stage base + constants, one commit.
     if (leader) {
-      constexpr uint32_t idesc = ptx::make_idesc(1u, BF16 ? 1u : 0u, BF16 ? 1u : 0u, 2 * T2_BM, T2_BT);
+      const uint32_t idesc = ptx::make_idesc(1u, BF16 ? 1u : 0u, BF16 ? 1u : 0u, 2 * T2_BM, (uint32_t)P.n_mma);
       const uint64_t bdesc0 = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem));
       uint32_t s = 0, ph = 0;
       int it = 0;
@@ -287,8 +298,9 @@ gemm_a16w4_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     uint32_t ps = 0, pph = 0;                               // packed ring position
     for (int t = pair; t < ntiles; t += npairs) {
       int tm, tn;
-      tile_coords(t, P.tiles_m, P.tiles_n, tm, tn);
+      tile_coords(t / P.splits, P.tiles_m, P.tiles_n, tm, tn);
       const int n = tn * 2 * T2_BM + (int)rank * T2_BM + row;
+      const int kstage0 = (t % P.splits) * kblocks;         // first 128-k stage of this work item
       uint32_t o[16];
       // ---------------- INT4 grouped metadata state ----------------
       // this warp's k offsets are kq*32 + 128*kb: a 32-wide span never straddles a group (group_size % 32 == 0)
@@ -302,12 +314,12 @@ gemm_a16w4_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       const uint8_t* mxp = nullptr;
       uint8_t mxraw = 0;
       if (WFMT == WFMT_INT4) {
-        g = (kq * 32) / P.group_size; rem = (kq * 32) % P.group_size;
+        g = (kstage0 * T2_BK + kq * 32) / P.group_size; rem = (kstage0 * T2_BK + kq * 32) % P.group_size;
         sp = reinterpret_cast<const uint16_t*>(P.scales) + (size_t)g * P.N + n;
         zp = (P.mode != 2) ? reinterpret_cast<const uint16_t*>(P.zeros) + (size_t)g * P.N + n : sp;
         sraw = *sp; zraw = (P.mode != 2) ? *zp : (uint16_t)0;
       } else {
-        mxp = reinterpret_cast<const uint8_t*>(P.scales) + (size_t)kq * P.N + n;
+        mxp = reinterpret_cast<const uint8_t*>(P.scales) + (size_t)(kstage0 * 4 + kq) * P.N + n;
         mxraw = *mxp;
       }
       for (int kb = 0; kb < kblocks; ++kb) {
@@ -376,46 +388,90 @@ gemm_a16w4_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     const int q4 = warp - T2_EPI_WARP0;
     const int row = q4 * 32 + lane;
     const uint32_t tempty_leader = ptx::mapa(ptx::smem_u32(tempty), 0u);
+    const int ncols = P.n_mma;
     int it = 0;
     for (int t = pair; t < ntiles; t += npairs, ++it) {
+      const int tile = t / P.splits, split = t % P.splits;
       int tm, tn;
-      tile_coords(t, P.tiles_m, P.tiles_n, tm, tn);
+      tile_coords(tile, P.tiles_m, P.tiles_n, tm, tn);
       const int n = tn * 2 * T2_BM + (int)rank * T2_BM + row;
       float bv = 0.f;
       if (P.bias) bv = BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(P.bias)[n])
                             : __half2float(reinterpret_cast<const __half*>(P.bias)[n]);
       ptx::mbar_wait_sleep(tfull, (uint32_t)(it & 1));     // a whole main loop away: do not burn issue slots spinning
       ptx::tc_fence_after_sync();
-      // the accumulator is single-buffered (tensor memory is full), so this drain is exposed: keep it lean --
-      // one cvt + one address mad + one 2-byte store per element, no per-element predicates on whole tiles
       const int mrem = P.M - tm * T2_BT;                                  // valid tokens in this tile
       unsigned char* ybase = reinterpret_cast<unsigned char*>(P.y) + ((int64_t)(tm * T2_BT) * P.N + n) * 2;
       const int64_t ystride = (int64_t)P.N * 2;
+      auto store_out = [&](int c, float v) {                              // one output element (token c of the tile, this row)
+        if (BF16) {
+          if (P.bias) v = __bfloat162float(__float2bfloat16_rn(v)) + bv;
+          *reinterpret_cast<__nv_bfloat16*>(ybase + c * ystride) = __float2bfloat16_rn(v);
+        } else {
+          if (P.bias) v = __half2float(__float2half_rn(v)) + bv;
+          *reinterpret_cast<__half*>(ybase + c * ystride) = __float2half_rn(v);
+        }
+      };
+      if (P.splits == 1) {
+        // the accumulator is single-buffered (tensor memory is full), so this drain is exposed: keep it lean --
+        // one cvt + one address mad + one 2-byte store per element, no per-element predicates on whole tiles
 #pragma unroll 1
-      for (int c0 = 0; c0 < T2_BT; c0 += 32) {
-        if (c0 >= mrem) break;
-        uint32_t r[32];
-        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)c0, r);
-        ptx::tmem_ld_wait();
-        unsigned char* yp = ybase + (int64_t)c0 * ystride;
-        const bool whole = (c0 + 32 <= mrem);
+        for (int c0 = 0; c0 < ncols; c0 += 32) {
+          if (c0 >= mrem) break;
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)c0, r);
+          ptx::tmem_ld_wait();
+          const bool whole = (c0 + 32 <= mrem);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (whole || c0 + j < mrem) {
-            float v = __uint_as_float(r[j]);
-            if (BF16) {
-              if (P.bias) v = __bfloat162float(__float2bfloat16_rn(v)) + bv;
-              *reinterpret_cast<__nv_bfloat16*>(yp + j * ystride) = __float2bfloat16_rn(v);
-            } else {
-              if (P.bias) v = __half2float(__float2half_rn(v)) + bv;
-              *reinterpret_cast<__half*>(yp + j * ystride) = __float2half_rn(v);
+          for (int j = 0; j < 32; ++j)
+            if (whole || c0 + j < mrem) store_out(c0 + j, __uint_as_float(r[j]));
+        }
+        ptx::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_cluster(tempty_leader);
+      } else {
+        // split-K: park this slice's fp32 partial (row-major per feature row: 128 B per thread and chunk), release the
+        // accumulator, then count in; the LAST of the `splits` warps serving this (tile, rank, quarter) slice reduces it
+        float* mine = P.ws_partial + ((((size_t)tile * P.splits + split) * 2 + rank) * T2_BM + row) * (size_t)ncols;
+#pragma unroll 1
+        for (int c0 = 0; c0 < ncols; c0 += 32) {
+          if (c0 >= mrem) break;
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)c0, r);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<uint4*>(mine + c0 + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+        }
+        ptx::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_cluster(tempty_leader);
+        __threadfence();                                                  // partial visible device-wide before the count
+        __syncwarp();
+        int* ctr = P.ws_counter + (tile * 2 + (int)rank) * 4 + q4;
+        int old = 0;
+        if (lane == 0) old = atomicAdd(ctr, 1);
+        old = __shfl_sync(0xffffffffu, old, 0);
+        if (old == P.splits - 1) {
+          __threadfence();
+          const float* base = P.ws_partial + (((size_t)tile * P.splits * 2 + rank) * T2_BM + row) * (size_t)ncols;
+          const size_t sstride = (size_t)2 * T2_BM * ncols;              // between consecutive splits
+#pragma unroll 1
+          for (int c0 = 0; c0 < ncols; c0 += 4) {
+            if (c0 >= mrem) break;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int sp = 0; sp < P.splits; ++sp) {                       // fixed order -> deterministic
+              const float4 v = __ldcg(reinterpret_cast<const float4*>(base + sp * sstride + c0));
+              acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
             }
+            if (c0 + 0 < mrem) store_out(c0 + 0, acc.x);
+            if (c0 + 1 < mrem) store_out(c0 + 1, acc.y);
+            if (c0 + 2 < mrem) store_out(c0 + 2, acc.z);
+            if (c0 + 3 < mrem) store_out(c0 + 3, acc.w);
           }
+          if (lane == 0) *ctr = 0;                                        // self-cleaning: ready for the next launch
         }
       }
-      ptx::tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive_cluster(tempty_leader);
     }
   }
 
@@ -426,8 +482,29 @@ gemm_a16w4_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
   if (warp == T2_ALLOC_WARP) ptx::tmem_dealloc_2cta(tmem_base, 512);
 }
 
+// How a problem is cut into work items (shared by the launch and by glb_workspace_bytes).
+struct Tc2Plan {
+  int tiles_m, tiles_n, splits, kb_per_split, n_mma;
+  size_t counter_bytes, partial_bytes;
+};
+Tc2Plan make_plan(const glb_linear& L, int64_t M) {
+  Tc2Plan p;
+  p.tiles_m = (int)((M + T2_BT - 1) / T2_BT);
+  p.tiles_n = (int)(L.N / (2 * T2_BM));
+  const int tiles = p.tiles_m * p.tiles_n, kblocks = (int)(L.K / T2_BK), pairs = num_sms() / 2;
+  p.n_mma = (M > 128) ? 256 : ((M > 64) ? 128 : 64);      // tokens the MMA actually computes (TMA zero-fills beyond M)
+  p.splits = 1;
+  for (int s = std::min(16, pairs / std::max(tiles, 1)); s >= 2; --s)
+    if (kblocks % s == 0 && kblocks / s >= T2_STAGES) { p.splits = s; break; }   // fill the SM pairs, keep >= one ring of stages
+  p.kb_per_split = kblocks / p.splits;
+  p.counter_bytes = (p.splits > 1) ? (((size_t)tiles * 8 * sizeof(int) + 255) & ~(size_t)255) : 0;
+  p.partial_bytes = (p.splits > 1) ? (size_t)tiles * p.splits * 2 * T2_BM * p.n_mma * sizeof(float) : 0;
+  return p;
+}
+
 template <bool BF16, int WFMT>
-int launch_tc2(const glb_linear& L, const void* x, void* y, int64_t M, const void* bias, cudaStream_t stream) {
+int launch_tc2(const glb_linear& L, const void* x, void* y, int64_t M, void* workspace, size_t ws_bytes, const void* bias,
+               cudaStream_t stream) {
   CUtensorMap tx, tw;
   int rc = make_tmap_2d(&tx, BF16 ? GLB_BF16 : GLB_FP16, x, (uint64_t)L.K, (uint64_t)M, (uint64_t)L.K * 2, 64, T2_BT / 2, 1);
   if (rc != GLB_OK) return rc;
@@ -436,11 +513,21 @@ int launch_tc2(const glb_linear& L, const void* x, void* y, int64_t M, const voi
   else   // (N, K/2) bytes, K contiguous: box = 64 bytes of codes x 128 feature rows
     rc = make_tmap_2d(&tw, GLB_UINT8, L.W_q, (uint64_t)(L.K / 2), (uint64_t)L.N, (uint64_t)(L.K / 2), T2_BK / 2, T2_BM, 0);
   if (rc != GLB_OK) return rc;
+  const Tc2Plan plan = make_plan(L, M);
   Tc2Params P;
   P.scales = L.scales; P.zeros = (L.W_group_mode == 2) ? nullptr : L.zeros;
   P.y = y; P.bias = bias; P.M = (int)M; P.N = (int)L.N; P.K = (int)L.K;
   P.group_size = L.group_size; P.mode = L.W_group_mode;
-  P.tiles_m = (int)((M + T2_BT - 1) / T2_BT); P.tiles_n = (int)(L.N / (2 * T2_BM));
+  P.tiles_m = plan.tiles_m; P.tiles_n = plan.tiles_n;
+  P.splits = plan.splits; P.kb_per_split = plan.kb_per_split; P.n_mma = plan.n_mma;
+  P.ws_counter = nullptr; P.ws_partial = nullptr;
+  if (plan.splits > 1) {
+    GLB_REQUIRE(workspace != nullptr && ws_bytes >= plan.counter_bytes + plan.partial_bytes, GLB_ERR_WORKSPACE,
+                "split-K needs %zu bytes of (zero-initialised) workspace, got %zu", plan.counter_bytes + plan.partial_bytes, ws_bytes);
+    GLB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, GLB_ERR_INVALID, "workspace must be 16-byte aligned");
+    P.ws_counter = reinterpret_cast<int*>(workspace);
+    P.ws_partial = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + plan.counter_bytes);
+  }
   {
     static int pf = -1;
     if (pf < 0) { const char* e = getenv("GLB_PREFILL_PREFETCH"); pf = e ? atoi(e) : 0; }
@@ -452,7 +539,7 @@ int launch_tc2(const glb_linear& L, const void* x, void* y, int64_t M, const voi
     GLB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM));
     configured = true;
   }
-  const int pairs = std::min(num_sms() / 2, P.tiles_m * P.tiles_n);
+  const int pairs = std::min(num_sms() / 2, P.tiles_m * P.tiles_n * P.splits);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(2 * pairs));
   cfg.blockDim = dim3(T2_THREADS);
@@ -475,6 +562,7 @@ bool gemm_tc2_supported(const glb_linear& L, int64_t M) {
   if (M < 1) return false;
   if (L.N % (2 * T2_BM) != 0 || L.K % T2_BK != 0) return false;
   if (L.group_size % 32 != 0) return false;          // a dequant warp's 32-wide k span never straddles quantisation groups
+  if (L.K % L.group_size != 0) return false;
   return true;
 }
 
@@ -493,15 +581,23 @@ bool gemm_mx_tc2_supported(const glb_linear& L, int64_t M) {
   return true;
 }
 
-int launch_gemm_tc2(const glb_linear& L, const void* x, void* y, int64_t M, const void* bias, cudaStream_t stream) {
+// bytes of zero-initialised workspace launch_gemm_tc2 needs for (L, M): per-slice counters + fp32 partials (0 without split-K)
+size_t gemm_tc2_workspace(const glb_linear& L, int64_t M) {
+  const Tc2Plan p = make_plan(L, M);
+  return p.counter_bytes + p.partial_bytes;
+}
+
+int launch_gemm_tc2(const glb_linear& L, const void* x, void* y, int64_t M, void* workspace, size_t ws_bytes, const void* bias,
+                    cudaStream_t stream) {
   if (gemm_mx_tc2_supported(L, M)) {
     set_kernel_name("gemm_a16w4_mxfp4_tcgen05_2cta");
-    return (L.input_dtype == GLB_MXBF16) ? launch_tc2<true, WFMT_MXFP4>(L, x, y, M, bias, stream)
-                                         : launch_tc2<false, WFMT_MXFP4>(L, x, y, M, bias, stream);
+    return (L.input_dtype == GLB_MXBF16) ? launch_tc2<true, WFMT_MXFP4>(L, x, y, M, workspace, ws_bytes, bias, stream)
+                                         : launch_tc2<false, WFMT_MXFP4>(L, x, y, M, workspace, ws_bytes, bias, stream);
   }
   const bool bf = (L.input_dtype == GLB_BF16);
   set_kernel_name("gemm_a16w4_tcgen05_2cta");
-  return bf ? launch_tc2<true, WFMT_INT4>(L, x, y, M, bias, stream) : launch_tc2<false, WFMT_INT4>(L, x, y, M, bias, stream);
+  return bf ? launch_tc2<true, WFMT_INT4>(L, x, y, M, workspace, ws_bytes, bias, stream)
+            : launch_tc2<false, WFMT_INT4>(L, x, y, M, workspace, ws_bytes, bias, stream);
 }
 
 }  // namespace glb

@@ -269,6 +269,27 @@ def test_prefill_pair_kernel_many_tiles_per_pair():
     assert torch.equal(layer(x), y)          # deterministic
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_pair_kernel_split_k_small_batches(dtype):
+    """16 < M <= 256 on a narrow layer: the pair kernel cuts K into splits so that all SM pairs work; partial sums are
+    parked in the workspace and reduced in split order by the last warp to arrive -> deterministic, counters self-clean."""
+    N, K, gs = 512, 2048, 128
+    W_q, scales, zeros = gen_int(N, K, 4, gs, dtype, seed=21)
+    gd = gemlite_b200.dtypes.TORCH_TO_DTYPE[dtype]
+    bias = (torch.randn(N, generator=torch.Generator().manual_seed(5)) / 10).to(dtype)
+    layer = GemLiteLinear(4, gs, K, N, gd, gd).pack(W_q.to(DEV), scales.to(DEV), zeros.to(DEV), bias.to(DEV))
+    p = O.prepare(W_q, scales, zeros, W_nbits=4, group_size=gs, in_features=K, out_features=N,
+                  input_dtype=O.DTYPE_OF[dtype], output_dtype=O.DTYPE_OF[dtype], bias=bias)
+    for M in (17, 64, 65, 128, 200, 256):
+        x = xgen(M, K, dtype, 500 + M)
+        xd = x.to(DEV)
+        y = layer(xd)
+        assert _cabi.last_kernel() == "gemm_a16w4_tcgen05_2cta", (M, _cabi.last_kernel())
+        assert relerr(y, O.forward(p, x)) <= REL[dtype], (dtype, M)
+        for _ in range(3):                       # same workspace, counters must have returned to zero; bitwise repeatable
+            assert torch.equal(layer(xd), y)
+
+
 def test_decode_kernel_is_used_for_the_headline_shape():
     N = K = 4096
     W_q, scales, zeros = gen_int(N, K, 4, 128, torch.float16, seed=0)
