@@ -494,8 +494,11 @@ Tc2Plan make_plan(const glb_linear& L, int64_t M) {
   const int tiles = p.tiles_m * p.tiles_n, kblocks = (int)(L.K / T2_BK), pairs = num_sms() / 2;
   p.n_mma = (M > 128) ? 256 : ((M > 64) ? 128 : 64);      // tokens the MMA actually computes (TMA zero-fills beyond M)
   p.splits = 1;
-  for (int s = std::min(16, pairs / std::max(tiles, 1)); s >= 2; --s)
-    if (kblocks % s == 0 && kblocks / s >= T2_STAGES) { p.splits = s; break; }   // fill the SM pairs, keep >= one ring of stages
+  // split K only for M <= 128: measured r1 (profiles/configs_r1.txt) 45 -> 22 us at M=32, 51 -> 39 us at M=128 on a 4096^2
+  // layer, but 39 -> 61 us at M=256, where parking and re-reading 256-column fp32 partials costs more than the idle SMs
+  if (M <= 128)
+    for (int s = std::min(16, pairs / std::max(tiles, 1)); s >= 2; --s)
+      if (kblocks % s == 0 && kblocks / s >= T2_STAGES) { p.splits = s; break; }   // fill the SM pairs, keep >= one ring of stages
   p.kb_per_split = kblocks / p.splits;
   p.counter_bytes = (p.splits > 1) ? (((size_t)tiles * 8 * sizeof(int) + 255) & ~(size_t)255) : 0;
   p.partial_bytes = (p.splits > 1) ? (size_t)tiles * p.splits * 2 * T2_BM * p.n_mma * sizeof(float) : 0;
