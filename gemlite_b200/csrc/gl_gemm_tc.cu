@@ -602,6 +602,11 @@ int launch_gemm_tc(const glb_linear& L, const void* x, const float* scales_x, vo
   GLB_REQUIRE(gemm_tc_supported(L, M), GLB_ERR_UNSUPPORTED, "tcgen05 GEMM: unsupported layer configuration");
   GLB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, GLB_ERR_INVALID, "tcgen05 GEMM: x must be 16-byte aligned");
   if (a8w8_tc_supported(L, M)) {
+    {
+      static int a8v = -1;        // GLB_A8W8_VARIANT=1 keeps the single-CTA kernel for A/B comparisons
+      if (a8v < 0) { const char* e = getenv("GLB_A8W8_VARIANT"); a8v = e ? atoi(e) : 2; }
+      if (a8v != 1 && gemm_a8_tc2_supported(L, M)) return launch_gemm_a8_tc2(L, x, scales_x, y, M, bias, stream);
+    }
     const bool is_int = (act_storage_dtype(L.input_dtype) == GLB_INT8);
     set_kernel_name(is_int ? "gemm_a8w8_int8_tcgen05" : "gemm_a8w8_fp8_tcgen05");
 #define GLB_T8(BT) (is_int ? launch_t8<true, BT>(L, x, scales_x, y, M, bias, stream) : launch_t8<false, BT>(L, x, scales_x, y, M, bias, stream))

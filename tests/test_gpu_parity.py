@@ -342,19 +342,22 @@ def test_int8_matmul_bit_exact():
     assert (layer.W_q.data.cpu().int() - p_cpu.W_q.int()).abs().max().item() <= 1
     assert torch.allclose(layer.scales.data.cpu(), p_cpu.scales, rtol=3e-7, atol=0)
     assert (p.W_group_mode, p.channel_scale_mode, p.meta_dtype) == (p_cpu.W_group_mode, p_cpu.channel_scale_mode, p_cpu.meta_dtype)
-    for M in (1, 3, 16, 64, 65, 200):
+    for M in (1, 3, 16, 64, 65, 200, 300, 777):
         x = xgen(M, K, torch.float16, M)
         xq, sx = scale_activations_per_token(x.to(DEV), torch.int8)
         y = layer(x.to(DEV))
+        # M > 128 runs on the CTA-pair kernel (gl_gemm_a8_tc2.cu), below that on the single-CTA one: same bits required
+        assert _cabi.last_kernel() == ("gemm_a8w8_int8_tcgen05_2cta" if M > 128 else "gemm_a8w8_int8_tcgen05"), (M, _cabi.last_kernel())
         y_or = O.forward(p, xq.cpu(), scales_x=sx.cpu())
         assert torch.equal(y.cpu(), y_or), (M, relerr(y, y_or))
         # raw int32 accumulator through an unscaled layer
     acc_layer = GemLiteLinear(8, None, K, N, DType.INT8, DType.INT32)
     Wi = torch.randint(-128, 128, (N, K), generator=torch.Generator().manual_seed(1), dtype=torch.int32).to(torch.int8)
     acc_layer.pack(Wi.to(DEV), None, None)
-    xi = torch.randint(-128, 128, (9, K), generator=torch.Generator().manual_seed(2), dtype=torch.int32).to(torch.int8)
-    got = acc_layer(xi.to(DEV))
-    assert got.dtype == torch.int32 and torch.equal(got.cpu(), xi.int() @ Wi.int().t())
+    for Mi in (9, 300):          # single-CTA and CTA-pair kernel
+        xi = torch.randint(-128, 128, (Mi, K), generator=torch.Generator().manual_seed(2), dtype=torch.int32).to(torch.int8)
+        got = acc_layer(xi.to(DEV))
+        assert got.dtype == torch.int32 and torch.equal(got.cpu(), xi.int() @ Wi.int().t())
 
 
 def test_fp8_dynamic_and_weight_only_paths():
@@ -362,10 +365,11 @@ def test_fp8_dynamic_and_weight_only_paths():
     W = (torch.randn(N, K, generator=torch.Generator().manual_seed(18)) / 10).half()
     layer = A8W8_FP8_dynamic(device=DEV, dtype=torch.float16).from_weights(W.clone())
     p = oracle_from_layer(layer)
-    for M in (1, 4, 70):
+    for M in (1, 4, 70, 300, 520):
         x = xgen(M, K, torch.float16, 40 + M)
         xq, sx = scale_activations_per_token(x.to(DEV), torch.float8_e4m3fn)
         y = layer(x.to(DEV))
+        assert _cabi.last_kernel() == ("gemm_a8w8_fp8_tcgen05_2cta" if M > 128 else "gemm_a8w8_fp8_tcgen05"), (M, _cabi.last_kernel())
         assert relerr(y, O.forward(p, xq.cpu(), scales_x=sx.cpu())) <= REL[torch.float16]
     wl = A16W8_FP8(device=DEV, dtype=torch.float16).from_weights(W.clone())
     pw = oracle_from_layer(wl)
