@@ -74,9 +74,88 @@ __global__ void __launch_bounds__(AQ_THREADS) act_quant_kernel(const XT* __restr
   }
 }
 
+// 16-bit activations, K % 8 == 0, 16-byte aligned rows: 128-bit loads (8 values) and 64-bit stores, VPT vectors per
+// thread register-resident between the absmax and the quantise pass (K <= 2048 * VPT).  Same arithmetic as above.
+// (r1: the scalar kernel above took 55 us for 4096 x 4096 -- 0.9 TB/s -- a third of the whole A8W8 call.)
+template <typename XT, int QD, int VPT>
+__global__ void __launch_bounds__(AQ_THREADS) act_quant_vec_kernel(const XT* __restrict__ x, uint8_t* __restrict__ q,
+                                                                   float* __restrict__ s_out, int64_t K, float qmax,
+                                                                   float lo, float hi) {
+  static_assert(sizeof(XT) == 2, "vector path is for fp16 / bf16 rows");
+  __shared__ float red[AQ_THREADS / 32];
+  __shared__ float s_sh;
+  const int64_t row = blockIdx.x;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + row * K);
+  uint2* qr = reinterpret_cast<uint2*>(q + row * K);
+  const int nvec = (int)(K >> 3);
+  pdl_wait_prior_grids();
+  uint4 raw[VPT];
+  float amax = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int v = i * AQ_THREADS + threadIdx.x;
+    raw[i] = (v < nvec) ? xr[v] : make_uint4(0u, 0u, 0u, 0u);
+    const XT* e = reinterpret_cast<const XT*>(&raw[i]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) amax = fmaxf(amax, fabsf(x_to_float<XT>(e[j])));
+  }
+  amax = warp_max(amax);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = amax;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = (threadIdx.x < AQ_THREADS / 32) ? red[threadIdx.x] : 0.f;
+    v = warp_max(v);
+    if (threadIdx.x == 0) {
+      float s = fmaxf(div_full(v, qmax), 1e-6f);
+      s_sh = s;
+      s_out[row] = s;
+    }
+  }
+  __syncthreads();
+  const float s = s_sh;
+  pdl_launch_dependents();
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int v = i * AQ_THREADS + threadIdx.x;
+    if (v < nvec) {
+      const XT* e = reinterpret_cast<const XT*>(&raw[i]);
+      uint32_t w[2] = {0u, 0u};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) w[j >> 2] |= (uint32_t)quant_one<QD>(x_to_float<XT>(e[j]), s, lo, hi) << (8 * (j & 3));
+      qr[v] = make_uint2(w[0], w[1]);
+    }
+  }
+}
+
+template <typename XT, int QD, int VPT>
+void launch_aq_vec(const void* x, int64_t M, int64_t K, void* q, float* s, float qmax, cudaStream_t stream) {
+  act_quant_vec_kernel<XT, QD, VPT><<<dim3((unsigned)M), dim3(AQ_THREADS), 0, stream>>>((const XT*)x, (uint8_t*)q, s, K, qmax, -qmax - (QD == GLB_INT8 ? 1.f : 0.f), qmax);
+}
+template <typename XT, int QD>
+bool try_aq_vec(const void* x, int64_t M, int64_t K, void* q, float* s, float qmax, cudaStream_t stream) {
+  if ((K & 7) || K > 2048 * 8) return false;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(q) & 7)) return false;
+  if (K <= 2048) launch_aq_vec<XT, QD, 1>(x, M, K, q, s, qmax, stream);
+  else if (K <= 4096) launch_aq_vec<XT, QD, 2>(x, M, K, q, s, qmax, stream);
+  else if (K <= 8192) launch_aq_vec<XT, QD, 4>(x, M, K, q, s, qmax, stream);
+  else launch_aq_vec<XT, QD, 8>(x, M, K, q, s, qmax, stream);
+  return true;
+}
+
 template <typename XT>
 int launch_aq(const void* x, int64_t M, int64_t K, int q_dtype, void* q, float* s, cudaStream_t stream) {
   dim3 grid((unsigned)M), block(AQ_THREADS);
+  if constexpr (sizeof(XT) == 2) {
+    bool done = false;
+    if (q_dtype == GLB_INT8) done = try_aq_vec<XT, GLB_INT8>(x, M, K, q, s, 127.f, stream);
+    else if (q_dtype == GLB_FP8E4) done = try_aq_vec<XT, GLB_FP8E4>(x, M, K, q, s, 448.f, stream);
+    else if (q_dtype == GLB_FP8E5) done = try_aq_vec<XT, GLB_FP8E5>(x, M, K, q, s, 57344.f, stream);
+    if (done) {
+      count_launch();
+      GLB_CHECK_CUDA(cudaGetLastError());
+      return GLB_OK;
+    }
+  }
   switch (q_dtype) {
     case GLB_INT8: act_quant_kernel<XT, GLB_INT8><<<grid, block, 0, stream>>>((const XT*)x, (uint8_t*)q, s, K, 127.f, -128.f, 127.f); break;
     case GLB_FP8E4: act_quant_kernel<XT, GLB_FP8E4><<<grid, block, 0, stream>>>((const XT*)x, (uint8_t*)q, s, K, 448.f, -448.f, 448.f); break;
