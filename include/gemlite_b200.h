@@ -130,7 +130,11 @@ GLB_API int glb_unpack_cols(const void* packed, int64_t rows, int64_t cols, int 
 GLB_API int glb_quant_act_per_token(const void* x, int64_t M, int64_t K, int x_dtype, int q_dtype,
                             void* q, float* s, void* stream);
 
-/* Scratch the matmul needs for (layer, M, matmul_type); 0 when none. */
+/* Scratch the matmul needs for (layer, M, matmul_type); 0 when none.  Non-zero only for the split-K launches of
+ * the CTA-pair tcgen05 kernel (16 < M <= 128 on layers with few 256-feature tiles): per-slice arrival counters
+ * followed by fp32 partial tiles.  The buffer must be ZERO-INITIALISED once by the caller (the reference's Triton
+ * forwards use torch.zeros for the same purpose, gemv_revsplitK_kernels.py:422); every launch leaves the counters
+ * at zero again, so one buffer per stream can be reused by consecutive calls without re-clearing it. */
 GLB_API size_t glb_workspace_bytes(const glb_linear* layer, int64_t M, int matmul_type);
 
 /* y(M, N) = epilogue( x(M, K) . dequant(W_q)(K, N) ) [+ bias]
@@ -139,7 +143,8 @@ GLB_API size_t glb_workspace_bytes(const glb_linear* layer, int64_t M, int matmu
  *   scales_x : (M) fp32 per-token activation scales, or NULL
  *   y        : (M, N) row-major, layer->output_dtype
  *   bias     : (N) in the output dtype, or NULL
- *   workspace: >= glb_workspace_bytes(...) bytes (may be NULL when that is 0) */
+ *   workspace: >= glb_workspace_bytes(...) bytes, 16-byte aligned, zero-initialised once (may be NULL when that is 0);
+ *              not shared between streams that run concurrently */
 GLB_API int glb_matmul(const glb_linear* layer, const void* x, const void* scales_x, void* y, int64_t M,
                int matmul_type, void* workspace, size_t workspace_bytes, const void* bias, void* stream);
 
