@@ -95,6 +95,7 @@ def get_matmul_type(batch_size: int, W_nbits: int, mx_dtype: bool = False) -> st
 # ---------------------------------------------------------------------------------------------------
 _DESC_CACHE = {}
 _WORKSPACE = {}
+_WORKSPACE_RETIRED = []
 _WS_BYTES = {}       # (descriptor id, M, matmul_type) -> workspace bytes the C library asked for (descriptors are cached, ids are stable)
 
 
@@ -135,13 +136,18 @@ def _make_desc(W_q: Tensor, scales: Tensor, zeros: Tensor, meta: List[int]) -> _
 
 
 def _workspace(device, nbytes: int) -> Optional[Tensor]:
+    """Per (device, stream) scratch for the split-K launches.  Zero-initialised once (the kernels keep arrival counters
+    in it and leave them at zero).  Sized so that it never has to grow (the largest request is < 10 MB: at most one
+    work item per SM pair); should it grow anyway, the old buffer stays alive because captured CUDA graphs may still
+    point at it."""
     if nbytes == 0:
         return None
     key = (device, torch.cuda.current_stream(device).cuda_stream)
     ws = _WORKSPACE.get(key)
     if ws is None or ws.numel() < nbytes:
-        # zero-initialised: the split-K kernels keep per-slice arrival counters in it and leave them at zero again
-        ws = torch.zeros(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        if ws is not None:
+            _WORKSPACE_RETIRED.append(ws)
+        ws = torch.zeros(max(nbytes, 16 << 20), dtype=torch.uint8, device=device)
         _WORKSPACE[key] = ws
     return ws
 
