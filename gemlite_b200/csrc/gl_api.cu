@@ -190,6 +190,9 @@ extern "C" int glb_matmul(const glb_linear* L, const void* x, const void* scales
   // 1. decode kernel (M <= 16, packed 4-bit): the automatic choice for small batches, and what the
   //    GEMV names select; 2. tcgen05 kernel: the automatic choice above that, and what the GEMM
   //    names select whenever the layer qualifies.
+  // 0. MXFP4 weight-only layers at M <= 4: streaming CUDA-core kernel (the reference sends every MX dtype at M == 1 to
+  //    GEMM_SPLITK, core.py:100-114); an explicit "GEMM" request keeps the tensor-core kernel
+  if (matmul_type != GLB_MM_GEMM && gemv_mx_supported(*L, M)) return launch_gemv_mx(*L, x, y, M, bias, stream);
   const bool prefer_gemv = can_gemv && (gemv_name || (was_auto && M <= 16) || !can_tc);
   if (prefer_gemv) return launch_gemv(*L, x, sx, y, M, bias, stream);
   if (can_tc) {

@@ -416,11 +416,15 @@ def test_mxfp4_pair_kernel_vs_oracle(dtype):
     p = O.prepare(codes, sc, None, W_nbits=4, group_size=32, in_features=K, out_features=N, input_dtype=gd, output_dtype=gd,
                   bias=bias)
     assert torch.equal(layer.W_q.data.cpu().contiguous().view(torch.uint8), p.W_q.contiguous().view(torch.uint8))
-    for M in (1, 7, 300):
+    for M in (1, 2, 3, 4, 7, 300):
         x = xgen(M, K, dtype, 300 + M)
         y = layer(x.to(DEV))
-        assert _cabi.last_kernel() == "gemm_a16w4_mxfp4_tcgen05_2cta", _cabi.last_kernel()
+        # M <= 4: streaming CUDA-core kernel (gl_gemv_mx.cu); above: CTA-pair tcgen05 kernel
+        assert _cabi.last_kernel() == ("gemv_mxfp4" if M <= 4 else "gemm_a16w4_mxfp4_tcgen05_2cta"), (M, _cabi.last_kernel())
         assert y.dtype == dtype and relerr(y, O.forward(p, x)) <= REL[dtype], (dtype, M)
+        if M <= 4:   # forcing "GEMM" keeps the tensor-core kernel; both kernels must agree with the oracle
+            yg = layer.forward_manual(x.to(DEV), "GEMM")
+            assert _cabi.last_kernel() == "gemm_a16w4_mxfp4_tcgen05_2cta" and relerr(yg, O.forward(p, x)) <= REL[dtype]
     # x = identity: every output is one dequantised weight -> bit-exact against the oracle's table * 2^(e-127)
     layer_nb = A16W4_MXFP(device=DEV, dtype=dtype).from_weights(codes.to(DEV), sc.to(DEV))
     p.bias = None
