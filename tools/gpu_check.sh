@@ -18,4 +18,5 @@ echo "== ncu full (prefill kernel)"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_a16w4_tc2 -c 1 -o gpurun_out/prefill_full -f \
     python tools/run_prefill.py --quick > gpurun_out/ncu_prefill.log 2>&1
 echo "== prefill sweep"; timeout 300 python tools/run_prefill.py 2>&1 | tail -6 | tee gpurun_out/prefill_sweep.log
+echo "== config table"; timeout 600 python tools/bench_configs.py > gpurun_out/configs_final.txt 2>&1; tail -45 gpurun_out/configs_final.txt | cut -c1-200
 ls -la gpurun_out | tail -20
