@@ -55,8 +55,8 @@ def measured_peaks():
 
 class ClockSampler:
     """SM clock / throttle reasons sampled DURING the timed region.  NVML is polled in-process from a thread (a
-    query takes well under a millisecond, so even a 10 ms region gets dozens of samples); nvidia-smi -lms is the
-    fallback when the NVML binding is missing."""
+    query takes well under a millisecond; polled every 4 ms so that the launching thread is not disturbed); nvidia-smi
+    -lms is the fallback when the NVML binding is missing."""
 
     def __init__(self, index=0):
         self.rows, self.proc, self.index = [], None, index
@@ -76,6 +76,10 @@ class ClockSampler:
                     phys = self.index
             self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
             self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            # first NVML queries are slow and can hold driver locks the launch path also needs: pay for them here,
+            # before the timed region starts
+            pynvml.nvmlDeviceGetClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            (getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons)(self.handle)
             self.nvml = pynvml
             self.thr = threading.Thread(target=self._poll, daemon=True)
             self.thr.start()
@@ -111,7 +115,7 @@ class ClockSampler:
                                   for k in ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")])
             except Exception:
                 break
-            time.sleep(0.0005)
+            time.sleep(0.004)      # a few hundred Hz would contend with the launching thread for driver locks
 
     def _read(self):
         for line in self.proc.stdout:
