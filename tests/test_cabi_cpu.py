@@ -105,3 +105,37 @@ def test_matmul_rejects_bad_descriptor_without_gpu():
     assert rc == -1 and b"no weights" in lib.glb_last_error()
     assert lib.glb_pack_cols(None, 4, 64, 3, 32, None, 1, None) == -1
     assert b"nbits" in lib.glb_last_error()
+
+
+def _a16w4_desc(N, K, gs=128):
+    """A descriptor shaped like a packed A16W4 layer (fake, aligned device addresses: nothing is dereferenced)."""
+    d = _cabi.GlbLinear()
+    d.W_q = 0x7f0000000000; d.wq_rows, d.wq_cols = K // 8, N; d.wq_stride0, d.wq_stride1 = N, 1
+    d.wq_dtype = DType.INT32.value
+    d.scales = 0x7f0100000000; d.scales_numel = (K // gs) * N; d.s_stride0, d.s_stride1 = N, 1
+    d.scales_dtype = DType.FP16.value
+    d.zeros = 0x7f0200000000; d.zeros_numel = (K // gs) * N; d.z_stride0, d.z_stride1 = N, 1
+    d.zeros_dtype = DType.FP16.value
+    d.K, d.N = K, N
+    (d.scaled_activations, d.W_nbits, d.group_size, d.unpack_mask, d.elements_per_sample, d.input_dtype, d.output_dtype,
+     d.acc_dtype, d.meta_dtype, d.channel_scale_mode, d.W_group_mode, d.data_contiguous) = (
+        0, 4, gs, 15, 8, DType.FP16.value, DType.FP16.value, DType.FP32.value, DType.FP16.value, 0, 4, 1)
+    return d
+
+
+def test_workspace_plan_without_gpu():
+    """glb_workspace_bytes is pure host logic: zero for the decode kernel and for full-size prefill, counters + fp32
+    partial tiles for the split-K range 16 < M <= 128 of a narrow layer (tiles * splits <= SM pairs)."""
+    lib = _cabi.load()
+    d = _a16w4_desc(4096, 4096)
+    assert lib.glb_workspace_bytes(ctypes.byref(d), 1, -1) == 0          # decode kernel
+    assert lib.glb_workspace_bytes(ctypes.byref(d), 16, -1) == 0
+    assert lib.glb_workspace_bytes(ctypes.byref(d), 4096, -1) == 0       # 256 tiles: no split
+    assert lib.glb_workspace_bytes(ctypes.byref(d), 256, -1) == 0        # split-K is not used above M = 128
+    w32 = lib.glb_workspace_bytes(ctypes.byref(d), 32, -1)
+    # 16 tiles x 4 splits x 2 CTAs x 128 rows x 64 columns fp32 + 16 x 8 counters (padded to 256 B)
+    assert w32 == 16 * 4 * 2 * 128 * 64 * 4 + 512, w32
+    w128 = lib.glb_workspace_bytes(ctypes.byref(d), 128, -1)
+    assert w128 == 16 * 4 * 2 * 128 * 128 * 4 + 512, w128
+    wide = _a16w4_desc(16384, 4096)
+    assert lib.glb_workspace_bytes(ctypes.byref(wide), 64, -1) == 0      # 64 tiles already fill the 74 SM pairs
