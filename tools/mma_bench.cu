@@ -14,13 +14,23 @@ __device__ __forceinline__ void mma_f16_ss_2cta(uint32_t d_tmem, uint64_t a_desc
                "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
 }
 
-// MODE 0: 2-CTA TS (A in TMEM)  1: 2-CTA SS  2: 1-CTA SS  3: 1-CTA TS ; N = accumulator width
+__device__ __forceinline__ void mma_i8_ss_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+               "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mma_f8_ss_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+               "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+
+// MODE 0: 2-CTA TS (A in TMEM)  1: 2-CTA SS  2: 1-CTA SS  3: 1-CTA TS  4: 2-CTA SS kind::i8  5: 2-CTA SS kind::f8f6f4 (e4m3)
+// N = accumulator width; modes 4 / 5 use K = 32 bytes per instruction (same 128 ideal cycles at N = 256)
 template <int MODE, int N>
 __global__ void __launch_bounds__(128, 1) bench(long long* out, int iters) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t slot;
-  constexpr bool TWO = (MODE == 0 || MODE == 1);
+  constexpr bool TWO = (MODE == 0 || MODE == 1 || MODE == 4 || MODE == 5);
   const uint32_t rank = TWO ? ptx::cluster_ctarank() : 0u;
   for (int i = threadIdx.x; i < 96 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0u;
   if (threadIdx.x == 0) { ptx::mbar_init(&bar, 1); ptx::fence_mbar_init(); }
@@ -32,7 +42,7 @@ __global__ void __launch_bounds__(128, 1) bench(long long* out, int iters) {
   const uint32_t tm = slot;
   long long t0 = 0, t1 = 0;
   if (threadIdx.x == 0 && rank == 0) {
-    const uint32_t idesc = ptx::make_idesc(1u, 0u, 0u, TWO ? 256 : 128, N);
+    const uint32_t idesc = (MODE == 4) ? ptx::make_idesc(2u, 1u, 1u, 256, N) : ptx::make_idesc(1u, 0u, 0u, TWO ? 256 : 128, N);
     const uint64_t ad = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem));
     const uint64_t bd = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + 32 * 1024));
     t0 = clock64();
@@ -42,6 +52,8 @@ __global__ void __launch_bounds__(128, 1) bench(long long* out, int iters) {
         if (MODE == 0) ptx::mma_f16_ts_2cta(tm, tm + 256 + 8 * k, bd + 2 * k, idesc, 1u);
         else if (MODE == 1) mma_f16_ss_2cta(tm, ad + 2 * k, bd + 2 * k, idesc, 1u);
         else if (MODE == 2) ptx::mma_f16_ss(tm, ad + 2 * k, bd + 2 * k, idesc, 1u);
+        else if (MODE == 4) mma_i8_ss_2cta(tm, ad + 2 * k, bd + 2 * k, idesc, 1u);
+        else if (MODE == 5) mma_f8_ss_2cta(tm, ad + 2 * k, bd + 2 * k, idesc, 1u);
         else ptx::mma_f16_ts(tm, tm + 256 + 8 * k, bd + 2 * k, idesc, 1u);
       }
     }
@@ -57,7 +69,7 @@ __global__ void __launch_bounds__(128, 1) bench(long long* out, int iters) {
 }
 
 template <int MODE, int N> int run(const char* name, long long* out) {
-  constexpr bool TWO = (MODE == 0 || MODE == 1);
+  constexpr bool TWO = (MODE == 0 || MODE == 1 || MODE == 4 || MODE == 5);
   auto k = bench<MODE, N>;
   CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
   const int iters = 2000;
@@ -89,6 +101,8 @@ int main() {
   if (run<1, 256>("2-CTA SS", out)) return 1;
   if (run<2, 256>("1-CTA SS", out)) return 1;
   if (run<3, 256>("1-CTA TS", out)) return 1;
+  if (run<4, 256>("2-CTA SS kind::i8 (K=32)", out)) return 1;
+  if (run<5, 256>("2-CTA SS kind::f8f6f4 (K=32)", out)) return 1;
   if (run<0, 128>("2-CTA TS (A in TMEM)", out)) return 1;
   if (run<1, 128>("2-CTA SS", out)) return 1;
   if (run<2, 128>("1-CTA SS", out)) return 1;
