@@ -15,6 +15,10 @@
 //   * MMA issuer on the highest warp id, one barrier wait + 4 MMAs (K = 32 bytes each) + one multicast commit per stage.
 // Epilogue arithmetic is identical to the single-CTA kernel's (and the reference's): int32 -> cvt.rn.f32.s32, one
 // fp32 multiply by (scales_x[m] * scales_w[n]) (rounded product), round to the output type, then bias.
+// The first version of this kernel was EPILOGUE-bound (profiles/a8_int8_tc2_r1_ncu.txt: the MMA issuer never waited
+// for data, only for the accumulator to be drained; 4 epilogue warps, one per scheduler, ~80 % busy in dependency
+// stalls of a branchy per-element path).  Now: 8 epilogue warps (two per scheduler, 128 columns each) and a
+// branch-free specialisation for the A8W8_dynamic case (channel_scale_mode 3, fp16 / bf16 output).
 #include <stdlib.h>
 #include <algorithm>
 
@@ -28,7 +32,9 @@ constexpr int A8_BM = 128;            // features per CTA (256 per pair)
 constexpr int A8_BT = 256;            // tokens per pair tile (128 staged per CTA)
 constexpr int A8_BK = 128;            // bytes (= elements) of K per stage
 constexpr int A8_STAGES = 6;
-constexpr int A8_THREADS = 256;       // w0 producer, w1 TMEM alloc, w2-5 epilogue, w6 idle, w7 MMA issuer
+constexpr int A8_THREADS = 384;       // w0 producer, w1 TMEM alloc, w2-9 epilogue (2 per lane quarter), w10 idle, w11 MMA issuer
+constexpr int A8_EPI_WARPS = 8;
+constexpr int A8_MMA_WARP = 11;
 constexpr int A8_W_BYTES = A8_BM * A8_BK;          // 16 KB
 constexpr int A8_X_BYTES = (A8_BT / 2) * A8_BK;    // 16 KB
 constexpr int A8_STAGE = A8_W_BYTES + A8_X_BYTES;
@@ -93,7 +99,7 @@ gemm_a8w8_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     ptx::prefetch_tmap(&tmap_x);
     ptx::prefetch_tmap(&tmap_w);
     for (int s = 0; s < A8_STAGES; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { ptx::mbar_init(&tfull[b], 1); ptx::mbar_init(&tempty[b], 2 * 4); }
+    for (int b = 0; b < 2; ++b) { ptx::mbar_init(&tfull[b], 1); ptx::mbar_init(&tempty[b], 2 * A8_EPI_WARPS); }
     ptx::fence_mbar_init();
   }
   if (warp == 1) ptx::tmem_alloc_2cta(tmem_slot, 512);
@@ -121,7 +127,7 @@ gemm_a8w8_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         }
       }
     }
-  } else if (warp == 7) {
+  } else if (warp == A8_MMA_WARP) {
     // ================= MMA issuer (leader CTA) =================
     if (leader) {
       const uint64_t adesc0 = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem));
@@ -149,11 +155,13 @@ gemm_a8w8_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         }
       }
     }
-  } else if (warp >= 2 && warp < 6) {
-    // ================= epilogue: each CTA drains its own 128 feature rows =================
-    const int q4 = warp & 3;                            // TMEM lane quarter == warp % 4  (warps 2,3,4,5 -> 2,3,0,1)
+  } else if (warp >= 2 && warp < 2 + A8_EPI_WARPS) {
+    // ================= epilogue: each CTA drains its own 128 feature rows; warp = (lane quarter, column half) =================
+    const int q4 = warp & 3;                            // TMEM lane quarter == warp % 4
+    const int chalf = (warp - 2) >> 2;                  // columns [chalf * 128, +128)
     const int row = q4 * 32 + lane;
     const uint32_t tempty_leader = ptx::mapa(ptx::smem_u32(&tempty[0]), 0u);
+    const bool fast16 = (P.csm == 3) && (P.out_dtype == GLB_FP16 || P.out_dtype == GLB_BF16);
     int it = 0;
     for (int t = pair; t < ntiles; t += npairs, ++it) {
       int tm, tn;
@@ -171,7 +179,7 @@ gemm_a8w8_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
       ptx::mbar_wait_sleep(&tfull[buf], (uint32_t)((it >> 1) & 1));
       ptx::tc_fence_after_sync();
 #pragma unroll 1
-      for (int c0 = 0; c0 < A8_BT; c0 += 32) {
+      for (int c0 = chalf * 128; c0 < chalf * 128 + 128; c0 += 32) {
         if (c0 >= mrem) break;
         uint32_t r[32];
         ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * A8_BT + c0), r);
@@ -179,29 +187,52 @@ gemm_a8w8_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         float sxl = 1.f;
         if ((P.csm == 2 || P.csm == 3) && c0 + lane < mrem) sxl = P.scales_x[tm * A8_BT + c0 + lane];
         ptx::tmem_ld_wait();
+        if (fast16) {
+          // A8W8_dynamic: v = cvt(acc) * (sx * sb), rounded to fp16 / bf16 (+ bias): no per-element branches but the edge mask
+          unsigned char* yp = reinterpret_cast<unsigned char*>(P.y) + ((int64_t)(tm * A8_BT + c0) * P.N + n) * 2;
+          const int64_t ystride = (int64_t)P.N * 2;
+          const bool f16 = (P.out_dtype == GLB_FP16), hb = (P.bias != nullptr);
+          const int cnt = mrem - c0;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float sx = __shfl_sync(0xffffffffu, sxl, j);
-          if (c0 + j < mrem) {
-            const int64_t oi = (int64_t)(tm * A8_BT + c0 + j) * P.N + n;
-            if (IS_INT && P.out_dtype == GLB_INT32 && P.csm == 0 && !P.bias) {
-              reinterpret_cast<int32_t*>(P.y)[oi] = (int32_t)r[j];
-              continue;
-            }
-            float v = IS_INT ? (float)(int32_t)r[j] : __uint_as_float(r[j]);     // cvt.rn.f32.s32
-            if (P.csm == 1) v = __fmul_rn(v, sb);
-            else if (P.csm == 2) v = __fmul_rn(v, sx);
-            else if (P.csm == 3) v = __fmul_rn(v, __fmul_rn(sx, sb));
-            if (P.out_dtype == GLB_FP16) {
-              if (P.bias) v = __half2float(__float2half_rn(v)) + bv;
-              reinterpret_cast<__half*>(P.y)[oi] = __float2half_rn(v);
-            } else if (P.out_dtype == GLB_BF16) {
-              if (P.bias) v = __bfloat162float(__float2bfloat16_rn(v)) + bv;
-              reinterpret_cast<__nv_bfloat16*>(P.y)[oi] = __float2bfloat16_rn(v);
-            } else if (P.out_dtype == GLB_FP32) {
-              reinterpret_cast<float*>(P.y)[oi] = v + bv;
+          for (int j = 0; j < 32; ++j) {
+            const float sx = __shfl_sync(0xffffffffu, sxl, j);
+            float v = IS_INT ? (float)(int32_t)r[j] : __uint_as_float(r[j]);
+            v = __fmul_rn(v, __fmul_rn(sx, sb));
+            unsigned short o;
+            if (f16) {
+              if (hb) v = __half2float(__float2half_rn(v)) + bv;
+              o = __half_as_ushort(__float2half_rn(v));
             } else {
-              reinterpret_cast<int32_t*>(P.y)[oi] = (int32_t)(v + bv);
+              if (hb) v = __bfloat162float(__float2bfloat16_rn(v)) + bv;
+              o = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+            }
+            if (j < cnt) *reinterpret_cast<unsigned short*>(yp + j * ystride) = o;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float sx = __shfl_sync(0xffffffffu, sxl, j);
+            if (c0 + j < mrem) {
+              const int64_t oi = (int64_t)(tm * A8_BT + c0 + j) * P.N + n;
+              if (IS_INT && P.out_dtype == GLB_INT32 && P.csm == 0 && !P.bias) {
+                reinterpret_cast<int32_t*>(P.y)[oi] = (int32_t)r[j];
+                continue;
+              }
+              float v = IS_INT ? (float)(int32_t)r[j] : __uint_as_float(r[j]);     // cvt.rn.f32.s32
+              if (P.csm == 1) v = __fmul_rn(v, sb);
+              else if (P.csm == 2) v = __fmul_rn(v, sx);
+              else if (P.csm == 3) v = __fmul_rn(v, __fmul_rn(sx, sb));
+              if (P.out_dtype == GLB_FP16) {
+                if (P.bias) v = __half2float(__float2half_rn(v)) + bv;
+                reinterpret_cast<__half*>(P.y)[oi] = __float2half_rn(v);
+              } else if (P.out_dtype == GLB_BF16) {
+                if (P.bias) v = __bfloat162float(__float2bfloat16_rn(v)) + bv;
+                reinterpret_cast<__nv_bfloat16*>(P.y)[oi] = __float2bfloat16_rn(v);
+              } else if (P.out_dtype == GLB_FP32) {
+                reinterpret_cast<float*>(P.y)[oi] = v + bv;
+              } else {
+                reinterpret_cast<int32_t*>(P.y)[oi] = (int32_t)(v + bv);
+              }
             }
           }
         }

@@ -1,0 +1,8 @@
+#!/bin/bash
+set -u
+mkdir -p gpurun_out
+cap() { timeout 300 ncu --set full --clock-control none --import-source on -k regex:"$2" -s $4 -c 1 -o gpurun_out/$1 -f python tools/probe_kernels.py $3 > gpurun_out/ncu_$1.log 2>&1; tail -1 gpurun_out/ncu_$1.log | cut -c1-120; }
+cap a8_int8_tc2 gemm_a8w8_tc2_kernel a8 1
+cap a8_fp8_tc2 gemm_a8w8_tc2_kernel a8 3
+cap mxfp4_tc2 gemm_a16w4_tc2_kernel mx 1
+ls -la gpurun_out/*.ncu-rep | awk '{print $5, $9}'
