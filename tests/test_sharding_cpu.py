@@ -101,3 +101,26 @@ def test_column_range_and_placeholders():
     s_mx = torch.arange(4 * 64, dtype=torch.uint8).view(4, 64).t()
     _, sl, _, _ = S.shard_tensors(W, s_mx, empty, None, 64, 1, 2)
     assert sl.shape == (32, 4) and sl.stride() == (1, 32) and torch.equal(sl, s_mx[32:])
+
+
+def test_column_sharded_linear_builds_a_consistent_local_layer():
+    """ColumnShardedLinear on a CPU-resident packed layer (built through load_state_dict from the oracle's packed
+    tensors -- pack() itself needs the GPU): the local module carries the shard's tensors, the parent's metadata and
+    out_features / world columns.  (Its forward is the ordinary C-ABI call and is covered by the GPU suite.)"""
+    from gemlite_b200 import GemLiteLinear
+    p = _cases()["a16w4_gs64_fma_bias"]
+    layer = GemLiteLinear.__new__(GemLiteLinear)
+    torch.nn.Module.__init__(layer)
+    layer.load_state_dict({"W_q": p.W_q, "bias": p.bias, "scales": p.scales, "zeros": p.zeros,
+                           "metadata": torch.tensor(p.meta_args(), dtype=torch.int32),
+                           "orig_shape": torch.tensor([p.out_features, p.in_features], dtype=torch.int32)})
+    world = 2
+    for rank in range(world):
+        sh = S.ColumnShardedLinear(layer, rank, world)
+        b, e = S.column_range(p.out_features, rank, world)
+        assert (sh.in_features, sh.out_features) == (p.in_features, p.out_features)
+        assert (sh.local.in_features, sh.local.out_features) == (p.in_features, p.out_features // world)
+        assert sh.local.get_meta_args() == layer.get_meta_args()
+        assert torch.equal(sh.local.W_q, p.W_q[:, b:e]) and sh.local.W_q.is_contiguous()
+        assert torch.equal(sh.local.scales, p.scales[:, b:e]) and torch.equal(sh.local.zeros, p.zeros[:, b:e])
+        assert torch.equal(sh.local.bias, p.bias[b:e])
