@@ -15,6 +15,9 @@ step -- torch.cuda.CUDAGraph, the public PyTorch facility) and the output is cop
 all inside the timed region (host wall clock incl. the final synchronize).  The same loop with plain eager
 calls (one Python -> C-ABI call per layer) is reported next to it as `e2e.eager_value`.
 `prefill` reports the second half of the metric (M=4096 TFLOP/s) on configs[2].
+`independent_launches` (N=1, supplementary, never the headline): the same 64 layers with the same x for every call (no
+y -> x chain) on 4 streams inside one CUDA graph -- what the kernel streams once the dependent-launch hand-off is off
+the critical path.
 
 With --gpus N > 1 (torchrun): weak scaling -- every rank owns its own column shard (4096 columns)
 of LAYERS wide layers (global N = 4096*world), x replicated, and the step ends with ONE NCCL
@@ -248,6 +251,63 @@ def time_prefill(dev):
         return {"available": False, "error": repr(e)[:200]}
 
 
+def capture_independent(layers, x, n_streams, dev):
+    """CUDA graph of one call per layer, every call reading the SAME x (no y -> x dependency), spread round-robin
+    over n_streams streams (fork / join inside the capture).  Returns (graph, outputs)."""
+    main = torch.cuda.Stream(device=dev)
+    side = [main] + [torch.cuda.Stream(device=dev) for _ in range(n_streams - 1)]
+    keep = []
+
+    def body():
+        fork = torch.cuda.Event()
+        fork.record(main)
+        for s in side[1:]:
+            s.wait_event(fork)
+        for i, layer in enumerate(layers):
+            with torch.cuda.stream(side[i % n_streams]):
+                keep.append(layer(x))
+        for s in side[1:]:
+            e = torch.cuda.Event()
+            e.record(s)
+            main.wait_event(e)
+
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(main):
+        body()                       # eager warm-up on the same streams
+        torch.cuda.synchronize()
+        keep.clear()
+        with torch.cuda.graph(graph, stream=main):
+            body()
+    return graph, keep
+
+
+def time_graph_us_per_layer(graph, steps, n_layers):
+    for _ in range(5):
+        graph.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e3 / (steps * n_layers)
+
+
+def independent_leg(layers, x, dev, peak, n_streams=4, steps=30):
+    """Supplementary number (never the headline): the same layers without the y -> x chain, on n_streams streams.
+    Shows what the decode kernel streams once the dependent-launch hand-off is off the critical path."""
+    try:
+        graph, keep = capture_independent(layers, x, n_streams, dev)
+        us = time_graph_us_per_layer(graph, steps, len(layers))
+        gbs = ALGO_BYTES / (us * 1e-6) / 1e9
+        return {"streams": n_streams, "us_per_launch": us, "value": gbs, "unit": "GB/s", "frac_of_peak": gbs / peak,
+                "note": "same 64 layers, every call reads the same x (independent launches), CUDA-graph replay; "
+                        "supplementary, not the headline workload"}
+    except Exception as e:      # supplementary only: never lose the bench line over it
+        return {"error": f"{type(e).__name__}: {str(e).splitlines()[0][:160] if str(e) else ''}"}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
     from gemlite_b200 import _cabi
@@ -389,6 +449,7 @@ def run_ours(args, rank, world, local_rank):
     # the CPU baseline is reported at N = 1 only (rank 0); multi-GPU runs do not repeat it
     cpu_v, cpu_calls, cpu_dt = (0.0, 0, 0.0) if (skip or world > 1) else cpu_reference_sample(os.cpu_count() or 1, seconds=12.0, max_calls=100)
     prefill = time_prefill(dev) if (world == 1 and not skip) else None
+    independent = independent_leg(layers, x0, dev, peak) if (world == 1 and not skip and not ALIAS) else None
     line = {
         "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
@@ -412,6 +473,7 @@ def run_ours(args, rank, world, local_rank):
         "gpu_launches": args.steps * LAYERS, "gpu_launches_e2e_eager": int(eager_launches),
         "clocks": clocks.summary(),
         "prefill": prefill,
+        "independent_launches": independent,
     }
     print(json.dumps(line), flush=True)
 

@@ -34,50 +34,29 @@ def build(dev):
 
 
 def capture(layers, x, S, chained, dev):
-    main = torch.cuda.Stream(device=dev)
-    side = [main] + [torch.cuda.Stream(device=dev) for _ in range(S - 1)]
+    if not chained:
+        return bench.capture_independent(layers, x, S, dev)
+    stream = torch.cuda.Stream(device=dev)
     keep = []
 
     def body():
-        if chained:
-            y = x
-            for layer in layers:
-                y = layer(y)
-            keep.append(y)
-            return
-        fork = torch.cuda.Event()
-        fork.record(main)
-        for s in side[1:]:
-            s.wait_event(fork)
-        for i, layer in enumerate(layers):
-            with torch.cuda.stream(side[i % S]):
-                keep.append(layer(x))
-        for s in side[1:]:
-            e = torch.cuda.Event()
-            e.record(s)
-            main.wait_event(e)
+        y = x
+        for layer in layers:
+            y = layer(y)
+        keep.append(y)
 
     graph = torch.cuda.CUDAGraph()
-    with torch.cuda.stream(main):
-        body()                       # eager warm-up on the same streams
+    with torch.cuda.stream(stream):
+        body()
         torch.cuda.synchronize()
         keep.clear()
-        with torch.cuda.graph(graph, stream=main):
+        with torch.cuda.graph(graph, stream=stream):
             body()
     return graph, keep
 
 
 def time_graph(graph, steps):
-    for _ in range(5):
-        graph.replay()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        graph.replay()
-    e1.record()
-    torch.cuda.synchronize()
-    return e0.elapsed_time(e1) * 1e3 / (steps * bench.LAYERS)      # us per layer
+    return bench.time_graph_us_per_layer(graph, steps, bench.LAYERS)
 
 
 def main():
