@@ -1,6 +1,8 @@
 """Build libgemlite_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
 
     python -m gemlite_b200.build [--force] [--verbose]
+    python -m gemlite_b200.build --flavour NAME -DMACRO=1 [...]   # experiment build: libgemlite_b200_NAME.so
+                                                                  # (load it with GLB_LIB_PATH=...; never the default)
 """
 import hashlib
 import os
@@ -37,9 +39,13 @@ def _digest():
     return h.hexdigest()
 
 
-def build(force=False, verbose=False, timeline=False):
+def build(force=False, verbose=False, timeline=False, flavour=None, defines=()):
     """Compile every .cu to an object (parallel) and link the shared library. Returns the path.
-    timeline=True builds the diagnostic flavour (decode kernel records %globaltimer phase stamps) next to it."""
+    timeline=True builds the diagnostic flavour (decode kernel records %globaltimer phase stamps) next to it;
+    flavour=NAME + defines builds an experiment library libgemlite_b200_NAME.so with extra -D macros."""
+    if flavour:
+        return _build(True, verbose, os.path.join(HERE, f"libgemlite_b200_{flavour}.so"),
+                      os.path.join(CSRC, f"build_{flavour}"), list(defines), None)
     if timeline:
         return _build(True, verbose, os.path.join(HERE, "libgemlite_b200_timeline.so"), os.path.join(CSRC, "build_tl"),
                       ["-DGLB_GEMV_TIMELINE=1"], None)
@@ -80,4 +86,6 @@ def _build(force, verbose, LIB, objdir, extra, dig):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, timeline="--timeline" in sys.argv))
+    _flavour = sys.argv[sys.argv.index("--flavour") + 1] if "--flavour" in sys.argv else None
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, timeline="--timeline" in sys.argv,
+                flavour=_flavour, defines=[a for a in sys.argv[1:] if a.startswith("-D")]))

@@ -418,6 +418,22 @@ __device__ __forceinline__ unsigned long long gtimer() {
   return t;
 }
 
+// mbarrier wait for a whole warp.  With -DGLB_GEMV_LEADER_WAIT=1 lane 0 polls and the warp reconverges on
+// __syncwarp() (the leader's acquire + the warp barrier order the other lanes' reads after the TMA writes): one
+// try_wait stream per warp instead of 32 lanes hitting the same shared-memory word.  Compile-time experiment, not yet
+// measured; the default build polls with every lane.
+#ifndef GLB_GEMV_LEADER_WAIT
+#define GLB_GEMV_LEADER_WAIT 0
+#endif
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+#if GLB_GEMV_LEADER_WAIT
+  if ((threadIdx.x & 31) == 0) ptx::mbar_wait(bar, parity);
+  __syncwarp();
+#else
+  ptx::mbar_wait(bar, parity);
+#endif
+}
+
 struct GemvTmaParams {
   const void* x; void* y; const void* bias;
   int K, N, M, group_size, mode;
@@ -545,7 +561,7 @@ gemv_w4_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
     // the metadata wait does not depend on the previous layer either: take it (and the barrier-init visibility it
     // needs) before griddepcontrol.wait, off the x -> y critical path
     __syncthreads();
-    ptx::mbar_wait(&bars[GT_NCH], 0);
+    mbar_wait_warp(&bars[GT_NCH], 0);
   }
 
   // ---- 2. x depends on the previous kernel: wait for it only now, then stage it permuted ----
@@ -613,14 +629,14 @@ gemv_w4_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
   const unsigned char* xb = reinterpret_cast<const unsigned char*>(xs + (size_t)(tok_ok ? g8 : 0) * Kc) + (2 * t4) * 16;
   const unsigned char* wl = wbuf + (2 * t4) * 128;
   const int sw0 = (g8 ^ (2 * t4)) << 4, sw1 = (g8 ^ (2 * t4 + 1)) << 4;   // swizzled chunk offsets for a = 0 / 1
-  if (!META_REGS && !(P.issue_mode & 2)) ptx::mbar_wait(&bars[GT_NCH], 0);   // scales / zeros landed
+  if (!META_REGS && !(P.issue_mode & 2)) mbar_wait_warp(&bars[GT_NCH], 0);   // scales / zeros landed
   if (rec) ts[GLB_GEMV_TIMELINE ? 4 : 0] = gtimer();
 
 #pragma unroll
   for (int gi = 0; gi < (META_REGS ? GT_GPW : (1 << 20)); ++gi) {
     const int gl = warp + NW * gi;
     if (gl >= ((P.debug & 1) ? 0 : Gc)) break;
-    if (!(P.debug & 2)) ptx::mbar_wait(&bars[(gl * rpg) >> P.chunk_shift], 0);   // this group's weight chunk landed
+    if (!(P.debug & 2)) mbar_wait_warp(&bars[(gl * rpg) >> P.chunk_shift], 0);   // this group's weight chunk landed
     if (rec && gl == warp) ts[GLB_GEMV_TIMELINE ? 5 : 0] = gtimer();
     // four independent accumulator chains per run: [column pair][k half]
     float dacc[2][2][4];
