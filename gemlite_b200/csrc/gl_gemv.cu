@@ -425,6 +425,9 @@ __device__ __forceinline__ unsigned long long gtimer() {
 #ifndef GLB_GEMV_LEADER_WAIT
 #define GLB_GEMV_LEADER_WAIT 0
 #endif
+#ifndef GLB_GEMV_PREWAIT_ALL
+#define GLB_GEMV_PREWAIT_ALL 0      // 1: all mbarrier waits before griddepcontrol.wait (compile-time experiment, see the kernel)
+#endif
 __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
 #if GLB_GEMV_LEADER_WAIT
   if ((threadIdx.x & 31) == 0) ptx::mbar_wait(bar, parity);
@@ -557,7 +560,19 @@ gemv_w4_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
     }
   }
   if (P.late_trigger == 0) pdl_launch_dependents();  // everything this CTA can do ahead of its input has been issued
-  if ((P.issue_mode & 2) && !META_REGS) {
+#if GLB_GEMV_PREWAIT_ALL
+  {
+    // experiment: take EVERY mbarrier wait (metadata and all weight chunks) before griddepcontrol.wait.  In a chain of
+    // dependent launches the copies land long before the previous layer finishes, so the post-wait path then holds no
+    // barrier polls at all; an isolated call pays for it by not overlapping its first chunks' compute with the rest
+    // of the copy.
+    __syncthreads();
+    if (!META_REGS) mbar_wait_warp(&bars[GT_NCH], 0);
+    if (!(P.debug & 2))
+      for (int c = 0; c < nch; ++c) mbar_wait_warp(&bars[c], 0);
+  }
+#endif
+  if (!GLB_GEMV_PREWAIT_ALL && (P.issue_mode & 2) && !META_REGS) {
     // the metadata wait does not depend on the previous layer either: take it (and the barrier-init visibility it
     // needs) before griddepcontrol.wait, off the x -> y critical path
     __syncthreads();
@@ -629,14 +644,14 @@ gemv_w4_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
   const unsigned char* xb = reinterpret_cast<const unsigned char*>(xs + (size_t)(tok_ok ? g8 : 0) * Kc) + (2 * t4) * 16;
   const unsigned char* wl = wbuf + (2 * t4) * 128;
   const int sw0 = (g8 ^ (2 * t4)) << 4, sw1 = (g8 ^ (2 * t4 + 1)) << 4;   // swizzled chunk offsets for a = 0 / 1
-  if (!META_REGS && !(P.issue_mode & 2)) mbar_wait_warp(&bars[GT_NCH], 0);   // scales / zeros landed
+  if (!GLB_GEMV_PREWAIT_ALL && !META_REGS && !(P.issue_mode & 2)) mbar_wait_warp(&bars[GT_NCH], 0);   // scales / zeros landed
   if (rec) ts[GLB_GEMV_TIMELINE ? 4 : 0] = gtimer();
 
 #pragma unroll
   for (int gi = 0; gi < (META_REGS ? GT_GPW : (1 << 20)); ++gi) {
     const int gl = warp + NW * gi;
     if (gl >= ((P.debug & 1) ? 0 : Gc)) break;
-    if (!(P.debug & 2)) mbar_wait_warp(&bars[(gl * rpg) >> P.chunk_shift], 0);   // this group's weight chunk landed
+    if (!GLB_GEMV_PREWAIT_ALL && !(P.debug & 2)) mbar_wait_warp(&bars[(gl * rpg) >> P.chunk_shift], 0);   // this group's weight chunk landed
     if (rec && gl == warp) ts[GLB_GEMV_TIMELINE ? 5 : 0] = gtimer();
     // four independent accumulator chains per run: [column pair][k half]
     float dacc[2][2][4];
