@@ -78,6 +78,10 @@ int launch_gemv_mx(const glb_linear& L, const void* x, void* y, int64_t M, const
 bool gemm_a8_tc2_supported(const glb_linear& L, int64_t M);
 int launch_gemm_a8_tc2(const glb_linear& L, const void* x, const float* scales_x, void* y, int64_t M, const void* bias,
                        cudaStream_t stream);
+bool gemv_a8_enabled();
+bool gemv_a8_supported(const glb_linear& L, int64_t M);
+int launch_gemv_a8(const glb_linear& L, const void* x, const float* scales_x, void* y, int64_t M, const void* bias,
+                   cudaStream_t stream);
 size_t gemm_tc2_workspace(const glb_linear& L, int64_t M);
 int launch_gemm_tc2(const glb_linear& L, const void* x, void* y, int64_t M, void* workspace, size_t ws_bytes, const void* bias,
                     cudaStream_t stream);

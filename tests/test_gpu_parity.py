@@ -1,6 +1,8 @@
 """GPU parity: the CUDA path (through the public API -> C ABI) against (a) the golden fixtures written
 by the reference itself and (b) the CPU oracle on seeded inputs.  Integer / byte work is bit-exact;
 floating point uses the tolerances stated next to each check."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -17,6 +19,14 @@ from golden_io import from_bits, layer_cases, load, tdtype
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
+# opt-in A8W8 decode kernel (gl_gemv_a8.cu, read once by the library at its first A8W8 call)
+A8_GEMV = os.environ.get("GLB_A8_GEMV", "0") not in ("", "0")
+
+
+def a8_kernel_name(kind, M):
+    if A8_GEMV and M <= 16:
+        return f"gemv_a8w8_{kind}"
+    return f"gemm_a8w8_{kind}_tcgen05_2cta" if M > 128 else f"gemm_a8w8_{kind}_tcgen05"
 
 # |y_cuda - y_oracle| <= REL * max|y_oracle|: one output ulp of headroom plus fp32 summation-order noise
 REL = {torch.float16: 2.0e-3, torch.bfloat16: 1.6e-2, torch.float32: 2e-5}
@@ -347,7 +357,7 @@ def test_int8_matmul_bit_exact():
         xq, sx = scale_activations_per_token(x.to(DEV), torch.int8)
         y = layer(x.to(DEV))
         # M > 128 runs on the CTA-pair kernel (gl_gemm_a8_tc2.cu), below that on the single-CTA one: same bits required
-        assert _cabi.last_kernel() == ("gemm_a8w8_int8_tcgen05_2cta" if M > 128 else "gemm_a8w8_int8_tcgen05"), (M, _cabi.last_kernel())
+        assert _cabi.last_kernel() == a8_kernel_name("int8", M), (M, _cabi.last_kernel())
         y_or = O.forward(p, xq.cpu(), scales_x=sx.cpu())
         assert torch.equal(y.cpu(), y_or), (M, relerr(y, y_or))
         # raw int32 accumulator through an unscaled layer
@@ -369,13 +379,48 @@ def test_fp8_dynamic_and_weight_only_paths():
         x = xgen(M, K, torch.float16, 40 + M)
         xq, sx = scale_activations_per_token(x.to(DEV), torch.float8_e4m3fn)
         y = layer(x.to(DEV))
-        assert _cabi.last_kernel() == ("gemm_a8w8_fp8_tcgen05_2cta" if M > 128 else "gemm_a8w8_fp8_tcgen05"), (M, _cabi.last_kernel())
+        assert _cabi.last_kernel() == a8_kernel_name("fp8", M), (M, _cabi.last_kernel())
         assert relerr(y, O.forward(p, xq.cpu(), scales_x=sx.cpu())) <= REL[torch.float16]
     wl = A16W8_FP8(device=DEV, dtype=torch.float16).from_weights(W.clone())
     pw = oracle_from_layer(wl)
     assert (pw.W_group_mode, pw.channel_scale_mode) == (2, 0)
     x = xgen(3, K, torch.float16, 77)
     assert relerr(wl(x.to(DEV)), O.forward(pw, x)) <= REL[torch.float16]
+
+
+@pytest.mark.skipif(not A8_GEMV, reason="A8W8 decode kernel is opt-in (GLB_A8_GEMV=1) until validated")
+def test_a8w8_decode_kernel_vs_oracle():
+    """gl_gemv_a8.cu: M <= 16, every scaling mode / output type of the A8W8 path; INT8 bit-exact, FP8 within REL."""
+    N, K = 1024, 2048
+    g = torch.Generator().manual_seed(31)
+    W = (torch.randn(N, K, generator=g) / 10).half()
+    bias = (torch.randn(N, generator=g) / 10)
+    for odt in (torch.float16, torch.bfloat16):
+        for proc, wdt, kind in ((A8W8_INT8_dynamic, torch.int8, "int8"), (A8W8_FP8_dynamic, torch.float8_e4m3fn, "fp8")):
+            for b in (None, bias.to(odt)):
+                layer = proc(device=DEV, dtype=odt).from_weights(W.clone().to(odt), bias=None if b is None else b.clone())
+                p = oracle_from_layer(layer)
+                for M in (1, 2, 5, 8, 9, 16):
+                    x = xgen(M, K, odt, 300 + M)
+                    xq, sx = scale_activations_per_token(x.to(DEV), wdt)
+                    y = layer(x.to(DEV))
+                    assert _cabi.last_kernel() == f"gemv_a8w8_{kind}", (M, _cabi.last_kernel())
+                    y_or = O.forward(p, xq.cpu(), scales_x=sx.cpu())
+                    if kind == "int8":
+                        assert torch.equal(y.cpu(), y_or), (odt, M, b is not None, relerr(y, y_or))
+                    else:
+                        assert relerr(y, y_or) <= REL[odt], (odt, M, b is not None, relerr(y, y_or))
+    # raw INT32 accumulators, every M of both column tiles, ragged N / K multiples
+    for (Ni, Ki) in ((48, 512), (1024, 4096)):
+        acc_layer = GemLiteLinear(8, None, Ki, Ni, DType.INT8, DType.INT32)
+        Wi = torch.randint(-128, 128, (Ni, Ki), generator=torch.Generator().manual_seed(1), dtype=torch.int32).to(torch.int8)
+        acc_layer.pack(Wi.to(DEV), None, None)
+        for Mi in range(1, 17):
+            xi = torch.randint(-128, 128, (Mi, Ki), generator=torch.Generator().manual_seed(2 + Mi), dtype=torch.int32).to(torch.int8)
+            got = acc_layer(xi.to(DEV))
+            if Ni % 128 == 0:
+                assert _cabi.last_kernel() == "gemv_a8w8_int8", (Ni, Ki, Mi, _cabi.last_kernel())
+            assert got.dtype == torch.int32 and torch.equal(got.cpu(), xi.int() @ Wi.int().t()), (Ni, Ki, Mi)
 
 
 def test_mxfp_weight_only_vs_oracle_and_unquantised():
