@@ -39,7 +39,7 @@ class GlbLinear(ctypes.Structure):
 
 EXPORTS = [
     "glb_version", "glb_last_error", "glb_last_kernel", "glb_launch_count", "glb_pack_cols", "glb_unpack_cols",
-    "glb_quant_act_per_token", "glb_workspace_bytes", "glb_matmul", "glb_set_pdl", "glb_get_pdl", "glb_debug_timeline",
+    "glb_quant_act_per_token", "glb_quant_act_mx", "glb_workspace_bytes", "glb_matmul", "glb_set_pdl", "glb_get_pdl", "glb_debug_timeline",
 ]
 
 
@@ -71,6 +71,8 @@ def load():
         lib.glb_unpack_cols.restype = i32
         lib.glb_quant_act_per_token.argtypes = [vp, i64, i64, i32, i32, vp, vp, vp]
         lib.glb_quant_act_per_token.restype = i32
+        lib.glb_quant_act_mx.argtypes = [vp, i64, i64, i32, i32, vp, vp, vp]
+        lib.glb_quant_act_mx.restype = i32
         lib.glb_workspace_bytes.argtypes = [ctypes.POINTER(GlbLinear), i64, i32]
         lib.glb_workspace_bytes.restype = sz
         lib.glb_matmul.argtypes = [ctypes.POINTER(GlbLinear), vp, vp, vp, i64, i32, vp, sz, vp, vp]
@@ -84,6 +86,11 @@ def load():
             lib.glb_set_pdl(0)
         _lib = lib
     return _lib
+
+
+def experimental_enabled() -> bool:
+    """Paths written but not yet validated on a GPU are reachable only with GEMLITE_B200_EXPERIMENTAL=1."""
+    return os.environ.get("GEMLITE_B200_EXPERIMENTAL", "0") not in ("", "0")
 
 
 def check(rc: int, what: str):

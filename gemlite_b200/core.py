@@ -23,7 +23,8 @@ from torch import Tensor
 from . import _cabi
 from .bitpack import pack_weights_over_cols
 from .dtypes import (DType, DTYPE_TO_TORCH, TORCH_TO_DTYPE, FP8_INT8_DTYPES, is_mx_dtype)
-from .quant_utils import scale_activations_per_token
+from .quant_utils import (scale_activations_per_token, scale_activations_mxfp8, scale_activations_mxfp4,
+                          scale_activations_nvfp4)
 
 logger = logging.getLogger(__name__)
 _FILE_LOCK = threading.Lock()
@@ -213,10 +214,20 @@ def _forward_eager(x: Tensor, bias: Optional[Tensor], tensor_args, meta_args, ma
     scales_x = None
     if bool(meta_args[0]) and enable_activation_scaling(batch_size):
         csm = int(meta_args[9])
+        if input_dtype in (DType.MXFP8, DType.MXFP4, DType.NVFP4) and not _cabi.experimental_enabled():
+            raise NotImplementedError(
+                f"dynamic activation quantisation for {input_dtype} (channel_scale_mode={csm}) is not validated yet "
+                "(set GEMLITE_B200_EXPERIMENTAL=1 to try it)")
         if input_dtype in FP8_INT8_DTYPES:
             x, scales_x = scale_activations_per_token(x, w_dtype=DTYPE_TO_TORCH[input_dtype.value])
         elif input_dtype == DType.MXFP8 and csm == 2:
             x, scales_x = scale_activations_per_token(x, w_dtype=torch.float8_e4m3fn)
+        elif input_dtype == DType.MXFP8 and csm == 4:      # core.py:165-175: MX micro-scales for the activations
+            x, scales_x = scale_activations_mxfp8(x, w_dtype=torch.float8_e4m3fn)
+        elif input_dtype == DType.MXFP4 and csm == 4:
+            x, scales_x = scale_activations_mxfp4(x)
+        elif input_dtype == DType.NVFP4 and csm == 4:
+            x, scales_x = scale_activations_nvfp4(x)
         else:
             raise NotImplementedError(
                 f"dynamic activation quantisation for {input_dtype} (channel_scale_mode={csm}) is not implemented")

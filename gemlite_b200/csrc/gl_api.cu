@@ -137,8 +137,14 @@ static int validate(const glb_linear* L, int64_t M) {
       GLB_REQUIRE(L->scales_numel == L->N, GLB_ERR_INVALID, "channel-wise scaling needs N scales");
   } else {
     GLB_REQUIRE(L->scales_numel > 0 && L->group_size > 0, GLB_ERR_INVALID, "MX layer needs group scales");
-    GLB_REQUIRE(L->channel_scale_mode == 0, GLB_ERR_UNSUPPORTED,
-                "MX activation quantisation (channel_scale_mode %d) is not implemented yet", L->channel_scale_mode);
+    // weight-only MX layers (fp16 / bf16 activations): mode 0.  Dynamically quantised activations (helper.py:660-945):
+    // MXFP8 with per-token post-scale (2) or e8m0 micro-scales (4); MXFP4 / NVFP4 with micro-scales (4)
+    const int csm = L->channel_scale_mode;
+    const bool dyn = (L->input_dtype == GLB_MXFP8 || L->input_dtype == GLB_MXFP4 || L->input_dtype == GLB_NVFP4);
+    GLB_REQUIRE(csm == 0 || (dyn && csm == 4) || (L->input_dtype == GLB_MXFP8 && csm == 2), GLB_ERR_UNSUPPORTED,
+                "MX layer: channel_scale_mode %d is not valid for input dtype %d", csm, L->input_dtype);
+    if (dyn) GLB_REQUIRE(L->group_size == ((L->input_dtype == GLB_NVFP4) ? 16 : 32), GLB_ERR_UNSUPPORTED,
+                         "MX layer: group_size %d does not match input dtype %d", L->group_size, L->input_dtype);
   }
   return GLB_OK;
 }
@@ -177,7 +183,7 @@ extern "C" int glb_matmul(const glb_linear* L, const void* x, const void* scales
   if (rc != GLB_OK) return rc;
   GLB_REQUIRE(x && y, GLB_ERR_INVALID, "x / y is NULL");
   GLB_REQUIRE(matmul_type >= GLB_MM_AUTO && matmul_type <= GLB_MM_GEMM, GLB_ERR_INVALID, "bad matmul_type %d", matmul_type);
-  if (L->channel_scale_mode == 2 || L->channel_scale_mode == 3)
+  if (L->channel_scale_mode >= 2)
     GLB_REQUIRE(scales_x != nullptr, GLB_ERR_INVALID, "channel_scale_mode %d needs activation scales", L->channel_scale_mode);
   const bool was_auto = (matmul_type == GLB_MM_AUTO);
   if (was_auto) matmul_type = pick_matmul_type(*L, M);

@@ -183,6 +183,23 @@ __device__ __forceinline__ float dequant_one_mx(const GenParams& P, int64_t k, i
   return v * sc;
 }
 
+// MX / NV quantised activations (channel_scale_mode 4; tl.dot_scaled lhs semantics, gemm_kernels.py:508-524): e4m3
+// bytes (MXFP8) or e2m1 nibbles (MXFP4 / NVFP4; even k = low nibble) times the scale of (row m, group k / gs):
+// scales_x is (M padded, K/gs) e8m0 bytes, or e4m3 bytes for NVFP4.  fp32 holds the product exactly.
+__device__ __forceinline__ float load_act_mx(const GenParams& P, int64_t m, int64_t k) {
+  const glb_linear& L = P.L;
+  const uint8_t* xb = reinterpret_cast<const uint8_t*>(P.x);
+  float v;
+  if (L.input_dtype == GLB_MXFP8) {
+    v = fp8e4_to_float(xb[m * L.K + k]);
+  } else {
+    const uint8_t byte = xb[m * (L.K >> 1) + (k >> 1)];
+    v = fp4_e2m1_to_float((k & 1) ? (byte >> 4) : (byte & 15));
+  }
+  const uint8_t sb = reinterpret_cast<const uint8_t*>(P.scales_x)[m * (L.K / L.group_size) + k / L.group_size];
+  return v * ((L.input_dtype == GLB_NVFP4) ? fp8e4_to_float(sb) : e8m0_to_float(sb));
+}
+
 template <typename MT, int KIND /*0 float-meta, 1 int-meta, 2 mx*/, bool INT_ACC>
 __global__ void __launch_bounds__(GEN_COLS) generic_kernel(const GenParams P) {
   __shared__ float xs[GEN_ROWS][GEN_KC];
@@ -204,7 +221,12 @@ __global__ void __launch_bounds__(GEN_COLS) generic_kernel(const GenParams P) {
     __syncthreads();
     for (int i = threadIdx.x; i < GEN_ROWS * GEN_KC; i += GEN_COLS) {
       const int r = i / GEN_KC, c = i % GEN_KC;
-      xs[r][c] = (r < rows && c < kc) ? load_act(P.x, P.act_dtype, (m0 + r) * L.K + k0 + c) : 0.f;
+      float xv = 0.f;
+      if (r < rows && c < kc) {
+        if (KIND == 2 && L.channel_scale_mode == 4) xv = load_act_mx(P, m0 + r, k0 + c);
+        else xv = load_act(P.x, P.act_dtype, (m0 + r) * L.K + k0 + c);
+      }
+      xs[r][c] = xv;
     }
     __syncthreads();
     if (active) {
@@ -235,6 +257,8 @@ __global__ void __launch_bounds__(GEN_COLS) generic_kernel(const GenParams P) {
     if (KIND == 2) {
       if (L.group_size == 16) acc *= 0.0025f;          // NVFP4 meta scale 0.05^2 (gemm_kernels.py:461,530)
       out = acc;
+      // MXFP8 activations quantised per token: acc.to(out dtype) * scales_a in fp32 (gemm_kernels.py:533-537)
+      if (csm == 2 && P.scales_x) out = __fmul_rn(round_out(acc, P.out_dtype), P.scales_x[m0 + r]);
     } else if (csm == 0) {
       out = acc;
     } else if (csm == 1) {

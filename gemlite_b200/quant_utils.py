@@ -43,15 +43,43 @@ def scale_activations_per_token(tensor: Tensor, w_dtype: torch.dtype, fp32_scale
 scale_activations_per_token_cuda = scale_activations_per_token
 
 
-def _unsupported(name):
-    def fn(*a, **k):
-        raise NotImplementedError(f"{name}: MX/NV activation quantisation is not implemented in this build")
-    return fn
+def _quant_act_mx(tensor: Tensor, mx_tag: int, q_dtype: torch.dtype, group: int, scale_dtype: torch.dtype, what: str):
+    """x (..., K) -> (q (M, K or K/2), scales (M padded to `group` rows, K/group)) through glb_quant_act_mx.
+    Like the reference's *_triton_v2 functions the result is 2-D (quant_utils.py:546-591, 819-857, 917-954)."""
+    _cabi.require_cuda(tensor, what)
+    if not _cabi.experimental_enabled():
+        raise NotImplementedError(f"{what}: MX/NV activation quantisation is not validated yet "
+                                  "(set GEMLITE_B200_EXPERIMENTAL=1 to try it)")
+    x2 = tensor.reshape(-1, tensor.shape[-1])
+    if not x2.is_contiguous():
+        x2 = x2.contiguous()
+    M, K = x2.shape
+    M_pad = (M + group - 1) // group * group
+    q = torch.empty((M, K if q_dtype != torch.uint8 else K // 2), dtype=q_dtype, device=tensor.device)
+    scales = torch.empty((M_pad, K // group), dtype=scale_dtype, device=tensor.device)
+    if M > 0:
+        with torch.cuda.device(tensor.device):
+            rc = _cabi.load().glb_quant_act_mx(x2.data_ptr(), M, K, _cabi.dtype_tag(x2.dtype), mx_tag, q.data_ptr(),
+                                               scales.data_ptr(), _cabi.current_stream_ptr(tensor.device))
+        _cabi.check(rc, "glb_quant_act_mx")
+    return q, scales
 
 
-scale_activations_mxfp8 = _unsupported("scale_activations_mxfp8")
-scale_activations_mxfp4 = _unsupported("scale_activations_mxfp4")
-scale_activations_nvfp4 = _unsupported("scale_activations_nvfp4")
+def scale_activations_mxfp8(tensor: Tensor, w_dtype: torch.dtype = torch.float8_e4m3fn) -> Tuple[Tensor, Tensor]:
+    """(M, K) e4m3 + (M padded to 32, K/32) uint8 e8m0 exponents."""
+    if w_dtype != torch.float8_e4m3fn:
+        raise NotImplementedError("scale_activations_mxfp8: only float8_e4m3fn activations are supported")
+    return _quant_act_mx(tensor, 16, torch.float8_e4m3fn, 32, torch.uint8, "scale_activations_mxfp8")      # DType.MXFP8
+
+
+def scale_activations_mxfp4(tensor: Tensor) -> Tuple[Tensor, Tensor]:
+    """(M, K/2) e2m1 codes (even k = low nibble) + (M padded to 32, K/32) uint8 e8m0 exponents."""
+    return _quant_act_mx(tensor, 17, torch.uint8, 32, torch.uint8, "scale_activations_mxfp4")              # DType.MXFP4
+
+
+def scale_activations_nvfp4(tensor: Tensor) -> Tuple[Tensor, Tensor]:
+    """(M, K/2) e2m1 codes + (M padded to 16, K/16) float8_e4m3fn scales (effective scale = e4m3 * 0.05)."""
+    return _quant_act_mx(tensor, 18, torch.uint8, 16, torch.float8_e4m3fn, "scale_activations_nvfp4")      # DType.NVFP4
 
 
 # --------------------------------------------------------------------------------------------------

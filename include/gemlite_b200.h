@@ -8,6 +8,8 @@
  *                                       :146-205 (unpack_over_cols)          [called from core.py:384-392]
  *   glb_quant_act_per_token ........... gemlite/quant_utils.py:308-347 (scale_activations_per_token_triton)
  *                                                                           [called from core.py:162-163]
+ *   glb_quant_act_mx .................. gemlite/quant_utils.py:546-591, :819-857, :917-954 (scale_activations_mxfp8 /
+ *                                       _mxfp4 / _nvfp4, the *_triton_v2 kernels)  [called from core.py:165-175]
  *   glb_matmul ........................ the `.forward(...)` of the five kernel classes
  *                                       gemv_kernels.py:553, gemv_revsplitK_kernels.py:391,
  *                                       gemv_splitK_kernels.py:423, gemm_splitK_kernels.py:595,
@@ -129,6 +131,15 @@ GLB_API int glb_unpack_cols(const void* packed, int64_t rows, int64_t cols, int 
  * zero (INT8) or converted round-to-nearest-even (FP8E4 / FP8E5).  q is (M, K) of q_dtype, s is (M) fp32. */
 GLB_API int glb_quant_act_per_token(const void* x, int64_t M, int64_t K, int x_dtype, int q_dtype,
                             void* q, float* s, void* stream);
+
+/* MX / NV dynamic activation quantisation (gemlite/quant_utils.py:503-954, the *_triton_v2 functions): x (M, K;
+ * x_dtype in {FP16, BF16, FP32}; K % 32 == 0) is quantised per row and per group of 32 (mx_dtype GLB_MXFP8: q (M, K)
+ * e4m3 bytes; GLB_MXFP4: q (M, K/2) e2m1 codes, even k in the low nibble; scales = e8m0 exponent bytes) or 16
+ * (GLB_NVFP4: q (M, K/2) e2m1 codes; scales = e4m3 bytes, effective scale = e4m3 * 0.05) consecutive k.
+ * `scales` is (M_pad, K/group) with M_pad = M rounded up to the group size, as the reference allocates it; the rows
+ * M..M_pad-1 are written too (97 = 2^-30 for MX, 0 for NV).  fp32 arithmetic, IEEE division. */
+GLB_API int glb_quant_act_mx(const void* x, int64_t M, int64_t K, int x_dtype, int mx_dtype,
+                     void* q, void* scales, void* stream);
 
 /* Scratch the matmul needs for (layer, M, matmul_type); 0 when none.  Non-zero only for the split-K launches of
  * the CTA-pair tcgen05 kernel (16 < M <= 128 on layers with few 256-feature tiles): per-slice arrival counters

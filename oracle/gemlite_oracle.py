@@ -14,6 +14,7 @@ reference computes on the path `pack() -> forward()`:
                                          accumulate, channel-scale epilogue, cast) and
                                          gemlite/core.py:192-193 (bias)
   quantize_activations_per_token() ..... gemlite/quant_utils.py:231-305
+  quantize_activations_mxfp8/mxfp4/nvfp4  gemlite/quant_utils.py:381-391,503-591,770-954
   mx_* ................................. gemlite/quant_utils.py:27-37,126-163 (e2m1 table,
                                          MXFP4/MXFP8 weight quantiser) and
                                          gemlite/triton_kernels/gemm_kernels.py:482-531
@@ -338,6 +339,103 @@ def quantize_activations_per_token(x: torch.Tensor, w_dtype: torch.dtype):
     return q.to(w_dtype).view(x.shape), s
 
 
+# MX / NV activation quantisers: the *_triton_v2 functions forward_functional calls (quant_utils.py:381-391 bitwise
+# next-power-of-two, :503-591 mxfp8, :770-857 mxfp4, :860-954 nvfp4).  All arithmetic in fp32, IEEE division (the GPU
+# build of the reference divides with div.full.f32, <= 2 ulp -- it can land on the other side of an exact tie).
+FP4_THR_POS = np.array([0.25, 0.75, 1.25, 1.75, 2.5, 3.5, 5.0, 7.0], dtype=np.float32)   # quant_utils.py:61-67 (last = pad)
+
+
+def _next_pow2_exponent(val: np.ndarray, eps_exp: int = -30) -> np.ndarray:
+    """quant_utils.py:381-391: biased exponent of the smallest power of two >= val, clamped to [127 + eps_exp, 254]."""
+    xi = val.astype(np.float32).view(np.uint32)
+    exp = ((xi >> 23) & 0xFF).astype(np.int64)
+    exp = exp + ((xi & 0x7FFFFF) != 0)
+    return np.clip(exp, 127 + eps_exp, 254)
+
+
+def _rows_padded(x: torch.Tensor, group: int):
+    x2 = x.reshape(-1, x.shape[-1]).to(torch.float32).numpy()
+    M, K = x2.shape
+    Mp = M + (group - M % group) % group
+    xp = np.zeros((Mp, K), np.float32)                                # rows >= M load as 0 (masked load, other=0)
+    xp[:M] = x2
+    return xp, M, K
+
+
+def _fp4_codes(wq: np.ndarray) -> np.ndarray:
+    """index = #thresholds strictly below |wq| (ties go down), +8 when wq < 0 (so a negative that rounds to 0 is
+    code 8 and -0.0 is code 0), then two codes per byte, even k in the low nibble  (quant_utils.py:806-812)."""
+    idx = (np.abs(wq)[..., None] > FP4_THR_POS).sum(axis=-1).astype(np.uint8)
+    codes = np.where(wq >= 0, idx, idx + 8).astype(np.uint8)
+    return (codes[:, 0::2] | (codes[:, 1::2] << 4)).astype(np.uint8)
+
+
+def quantize_activations_mxfp8(x: torch.Tensor, w_dtype: torch.dtype = torch.float8_e4m3fn):
+    """-> (q (M, K) fp8, scales (M padded to 32, K/32) uint8 e8m0 exponents); rows >= M hold 97 (= 2^-30)."""
+    xp, M, K = _rows_padded(x, 32)
+    g = xp.reshape(xp.shape[0], K // 32, 32)
+    hi = np.float32(torch.finfo(w_dtype).max)
+    exp = _next_pow2_exponent(np.abs(g).max(axis=2) / hi)
+    sc = (exp.astype(np.uint32) << 23).view(np.float32)
+    q = np.clip(g / sc[..., None], -hi, hi).reshape(xp.shape)[:M]
+    return torch.from_numpy(q).to(w_dtype).view(*x.shape), torch.from_numpy(exp.astype(np.uint8))
+
+
+def quantize_activations_mxfp4(x: torch.Tensor):
+    """-> (codes (M, K/2) uint8, scales (M padded to 32, K/32) uint8 e8m0 exponents)."""
+    xp, M, K = _rows_padded(x, 32)
+    g = xp.reshape(xp.shape[0], K // 32, 32)
+    exp = _next_pow2_exponent(np.abs(g).max(axis=2) / np.float32(6.0))
+    sc = (exp.astype(np.uint32) << 23).view(np.float32)
+    wq = (g / sc[..., None]).reshape(xp.shape)[:M]
+    return torch.from_numpy(_fp4_codes(wq)), torch.from_numpy(exp.astype(np.uint8))
+
+
+NVFP4_META_SCALE = 0.05                                                  # quant_utils.py:21
+
+
+def quantize_activations_nvfp4(x: torch.Tensor):
+    """-> (codes (M, K/2) uint8, scales (M padded to 16, K/16) float8_e4m3fn); effective scale = e4m3 * 0.05."""
+    xp, M, K = _rows_padded(x, 16)
+    g = xp.reshape(xp.shape[0], K // 16, 16)
+    s = np.abs(g).max(axis=2) / np.float32(6.0 * NVFP4_META_SCALE)
+    s8 = torch.from_numpy(np.minimum(s, np.float32(448.0))).to(torch.float8_e4m3fn)
+    full = np.maximum(s8.to(torch.float32).numpy() * np.float32(NVFP4_META_SCALE), np.float32(1e-6))
+    wq = (g / full[..., None]).reshape(xp.shape)[:M]
+    return torch.from_numpy(_fp4_codes(wq)), s8
+
+
+def mx_dequantize_activations(q: torch.Tensor, scales: torch.Tensor, input_dtype: int) -> torch.Tensor:
+    """(M, K) float64 exact values of MX / NV quantised activations (tl.dot_scaled lhs semantics)."""
+    if input_dtype == MXFP8:
+        vals = q.reshape(-1, q.shape[-1]).to(torch.float32).numpy().astype(np.float64)
+    else:
+        b = q.reshape(-1, q.shape[-1]).numpy()
+        codes = np.stack([b & 15, b >> 4], axis=2).reshape(b.shape[0], -1)
+        vals = FP4_VALUES[codes].astype(np.float64)
+    M, K = vals.shape
+    if scales.dtype == torch.uint8:
+        sc = e8m0_to_float(scales.numpy()[:M])
+    else:
+        sc = scales.to(torch.float32).numpy().astype(np.float64)[:M]
+    return torch.from_numpy(vals * np.repeat(sc, K // sc.shape[1], axis=1))
+
+
+def quantize_activations_for(p: "Packed", x: torch.Tensor):
+    """The quantiser forward_functional picks from (input_dtype, channel_scale_mode)  (core.py:157-175)."""
+    if p.input_dtype in (INT8, FP8, FP8E5):
+        return quantize_activations_per_token(x, TORCH_OF[p.input_dtype])
+    if p.input_dtype == MXFP8 and p.channel_scale_mode == 4:
+        return quantize_activations_mxfp8(x)
+    if p.input_dtype == MXFP8 and p.channel_scale_mode == 2:
+        return quantize_activations_per_token(x, torch.float8_e4m3fn)
+    if p.input_dtype == MXFP4 and p.channel_scale_mode == 4:
+        return quantize_activations_mxfp4(x)
+    if p.input_dtype == NVFP4 and p.channel_scale_mode == 4:
+        return quantize_activations_nvfp4(x)
+    return x, None                                                    # no branch taken: x goes in as it is
+
+
 # ============================================================================================
 # forward  (core.py:128-195 + gemm_kernels.py:347-413)
 # ============================================================================================
@@ -348,15 +446,25 @@ def forward(p: Packed, x: torch.Tensor, scales_x: torch.Tensor | None = None) ->
     lead = x.shape[:-1]
     in_t = TORCH_OF[p.input_dtype]
     if p.scaled_activations and scales_x is None:
-        x, scales_x = quantize_activations_per_token(x, in_t)
+        x, scales_x = quantize_activations_for(p, x)
+        lead = lead if x.dim() == len(lead) + 1 else x.shape[:-1]
     x2 = x.reshape(-1, x.shape[-1])
     if p.input_dtype in MX_VALUES:
+        # gemm_kernels.py:482-547: acc (fp32) += dot_scaled(a, scales_a, b, scales_b); NVFP4: acc *= 0.05^2;
+        # channel_scale_mode 2: acc.to(out dtype) * scales_a (fp32), stored in the out dtype
         W = mx_dequantize_weights(p)
-        acc = x2.to(torch.float64) @ W
-        acc = acc.to(torch.float32)
+        if p.scaled_activations and p.channel_scale_mode == 4:
+            xv = mx_dequantize_activations(x2, scales_x, p.input_dtype)
+        else:
+            xv = x2.to(torch.float64) if x2.dtype != torch.float8_e4m3fn else x2.to(torch.float32).to(torch.float64)
+        acc = (xv @ W).to(torch.float32)
         if p.group_size == 16:
             acc = acc * (0.05 ** 2)
-        y = acc.to(out_t)
+        if p.scaled_activations and p.channel_scale_mode == 2:
+            sa = scales_x.reshape(-1, 1).to(torch.float32)
+            y = (acc.to(out_t).to(torch.float32) * sa).to(out_t)
+        else:
+            y = acc.to(out_t)
     else:
         W = dequantize_weights(p)                                     # (K, N) float64
         acc = x2.to(torch.float64) @ W                                # exact sum, then one rounding
@@ -420,6 +528,23 @@ def quantize_mxfp8(W: torch.Tensor, fp8=torch.float8_e4m3fn):
     sc = torch.pow(2.0, torch.ceil(torch.log2(ideal))).clamp_(min=2.0 ** -30)
     q = (Wf / sc).clamp_(-mx, mx).to(fp8)
     return q, sc.to(torch.float8_e8m0fnu)
+
+
+def quantize_nvfp4(W: torch.Tensor):
+    """quant_utils.py:165-211, window_size = 0: group 16, e4m3 scales, effective scale = e4m3 * 0.05 (>= 1e-6).
+    returns (codes uint8 (N*K/16, 16), scales float8_e4m3fn (N*K/16, 1))."""
+    Wf = W.reshape(-1, 16).to(torch.float32)
+    ideal = Wf.abs().amax(dim=1, keepdim=True)
+    ideal = ideal / 6
+    ideal = ideal / NVFP4_META_SCALE
+    sc = ideal.clamp(max=448.0).to(torch.float8_e4m3fn)
+    full = (sc.to(torch.float32) * NVFP4_META_SCALE).clamp(min=1e-6)
+    v = Wf / full
+    idx = torch.bucketize(v.abs(), torch.from_numpy(FP4_THRESHOLDS), right=False)
+    q = torch.from_numpy(FP4_VALUES[:8])[idx] * torch.sign(v)
+    table = torch.from_numpy(FP4_VALUES)
+    codes = (q.reshape(-1, 1) == table.reshape(1, -1)).to(torch.uint8).argmax(dim=1).to(torch.uint8)
+    return codes.view(Wf.shape), sc
 
 
 # ============================================================================================

@@ -69,3 +69,30 @@ def a16wn_mxfp(W, nbits, dtype, bias=None):
     p = O.prepare(codes, sc, None, W_nbits=nbits, group_size=32, in_features=K, out_features=N,
                   input_dtype=gd, output_dtype=gd, bias=bias)
     return p, codes, sc
+
+
+def mx_dynamic(W, kind, dtype, post_scale=False, bias=None):
+    """A8W8_MXFP_dynamic / A8W4_MXFP_dynamic / A4W4_MXFP_dynamic / A4W4_NVFP_dynamic .from_linear -> from_weights
+    (helper.py:660-945): MX / NV quantised weights, activations quantised on the fly.  kind: 'a8w8' | 'a8w4' |
+    'a4w4_mx' | 'a4w4_nv'.  Returns (packed layer, codes, scales) like a16wn_mxfp."""
+    N, K = W.shape
+    if kind == "a8w8":
+        codes, sc = O.quantize_mxfp8(W)
+        nbits, gs, in_dt = 8, 32, O.MXFP8
+    elif kind == "a8w4":
+        codes, sc = O.quantize_mxfp4(W)
+        nbits, gs, in_dt = 4, 32, O.MXFP8
+    elif kind == "a4w4_mx":
+        codes, sc = O.quantize_mxfp4(W)
+        nbits, gs, in_dt = 4, 32, O.MXFP4
+    elif kind == "a4w4_nv":
+        codes, sc = O.quantize_nvfp4(W)
+        nbits, gs, in_dt = 4, 16, O.NVFP4
+    else:
+        raise KeyError(kind)
+    codes, sc = codes.view(N, K), sc.view(N, K // gs)
+    p = O.prepare(codes, sc, None, W_nbits=nbits, group_size=gs, in_features=K, out_features=N,
+                  input_dtype=in_dt, output_dtype=O.DTYPE_OF[dtype], scaled_activations=True, bias=bias)
+    p.W_group_mode = 0
+    p.channel_scale_mode = (2 if post_scale else 4) if kind in ("a8w8", "a8w4") else 4
+    return p, codes, sc

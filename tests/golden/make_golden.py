@@ -8,7 +8,11 @@ There is no GPU here, so this script
   * installs a stub Triton driver and sets TRITON_INTERPRET=1, so that every `@triton.jit`
     kernel of the reference is *executed by Triton's CPU interpreter* (numpy), and
   * works around one interpreter bug (python `bool` launch arguments are mangled as int1 but
-    materialised as int32) without touching reference code.
+    materialised as int32) without touching reference code, and
+  * supplies numpy stand-ins for the two primitives the interpreter lacks: `libdevice.round` and `tl.dot_scaled`
+    (see the comments at their definitions; everything around them is the reference's code), and
+  * replaces the interpreter's float down-casts (fp32 -> bf16 truncates, fp32 -> fp8 mis-rounds) with the
+    round-to-nearest-even (fp8: saturating) conversions the GPU performs.
 Everything that is recorded in the fixtures is produced by reference code: `pack()`,
 `forward_manual()` of each kernel that the interpreter can execute, `bitpack`, the
 per-token activation quantiser and the MXFP weight quantiser.
@@ -87,6 +91,34 @@ class _StubDriver(DriverBase):
 
 triton.runtime.driver.set_active(_StubDriver())
 
+# The interpreter's float DOWN-casts are wrong for the types stored as raw bits: fp32 -> bf16 truncates, and
+# fp32 -> fp8 "rounds" by adding the cut-off bit without carrying into the exponent (0.485 -> 0.25, 31 -> 16, ties go
+# up).  The GPU converts with cvt.rn(.satfinite): round-to-nearest-even, fp8 saturating.  Replace the down-casts with
+# exactly that (torch's conversions are RNE); up-casts, which are exact, keep the interpreter's code.
+_TL2TORCH = {tl.float32: torch.float32, tl.float16: torch.float16, tl.bfloat16: torch.bfloat16,
+             tl.float8e4nv: torch.float8_e4m3fn, tl.float8e5: torch.float8_e5m2}
+_BITS_VIEW = {1: torch.uint8, 2: torch.int16, 4: torch.int32}
+_orig_convert_float = _interp._convert_float
+
+
+def _convert_float_rne(input, input_dtype, output_dtype, rounding_mode):
+    if (input_dtype in _TL2TORCH and output_dtype in _TL2TORCH
+            and input_dtype.primitive_bitwidth > output_dtype.primitive_bitwidth):
+        raw = np.ascontiguousarray(input)
+        ti, to = _TL2TORCH[input_dtype], _TL2TORCH[output_dtype]
+        src = torch.from_numpy(raw.view(getattr(np, f"uint{raw.dtype.itemsize * 8}")).astype(
+            {1: np.uint8, 2: np.int16, 4: np.int32}[raw.dtype.itemsize], copy=False)).view(ti).to(torch.float32)
+        if to in (torch.float8_e4m3fn, torch.float8_e5m2):
+            hi = torch.finfo(to).max
+            src = torch.where(torch.isfinite(src), src.clamp(-hi, hi), src)          # .satfinite
+        out = src.to(to)
+        out_bits = out.view(_BITS_VIEW[out.element_size()]).numpy()
+        return out_bits.view(getattr(np, f"uint{out.element_size() * 8}")).reshape(raw.shape)
+    return _orig_convert_float(input, input_dtype, output_dtype, rounding_mode)
+
+
+_interp._convert_float = _convert_float_rne
+
 _orig_cvt = _interp._implicit_cvt
 
 
@@ -123,6 +155,62 @@ class _LibdeviceShim:
 
 
 ref_qu.libdevice = _LibdeviceShim
+
+
+# tl.dot_scaled is not implemented by the CPU interpreter (its builder has no create_dot_scaled).  The MX GEMM kernels
+# of the reference are therefore run with a numpy stand-in for that ONE compiler primitive, following its documented
+# semantics: operands decoded exactly (e2m1 low nibble = even k, e4m3 / e5m2 / fp16 / bf16 bit patterns), each
+# 32- (or 16-) element group of K multiplied by its scale (uint8 = e8m0 -> 2^(e-127), float8 = e4m3 value), products
+# summed exactly (float64) and rounded once into the fp32 accumulator.  Everything around the primitive -- pointer
+# arithmetic, scale indexing, masks, the NVFP4 norm, the post-scale epilogue -- is the reference's own code.
+_FP4_TABLE = np.array([0, 0.5, 1, 1.5, 2, 3, 4, 6, -0.0, -0.5, -1, -1.5, -2, -3, -4, -6], dtype=np.float64)
+
+
+def _ds_decode(t, fmt, k_axis):
+    d = t.handle.data
+    if fmt == "e2m1":
+        d = d.astype(np.uint8)
+        st = np.stack([d & 15, d >> 4], axis=k_axis + 1)
+        shape = list(d.shape)
+        shape[k_axis] *= 2
+        return _FP4_TABLE[st.reshape(shape)]
+    if fmt == "e4m3":
+        return torch.from_numpy(d.view(np.uint8).copy()).view(torch.float8_e4m3fn).to(torch.float64).numpy()
+    if fmt == "e5m2":
+        return torch.from_numpy(d.view(np.uint8).copy()).view(torch.float8_e5m2).to(torch.float64).numpy()
+    if fmt == "bf16":
+        return torch.from_numpy(d.view(np.int16).copy()).view(torch.bfloat16).to(torch.float64).numpy()
+    if fmt == "fp16":
+        return d.astype(np.float64)
+    raise NotImplementedError(fmt)
+
+
+def _ds_scale(t):
+    d = t.handle.data
+    if t.dtype.scalar == tl.uint8:
+        return np.exp2(d.astype(np.float64) - 127.0)
+    return torch.from_numpy(d.view(np.uint8).copy()).view(torch.float8_e4m3fn).to(torch.float64).numpy()
+
+
+def _dot_scaled_standin(lhs, lhs_scale, lhs_format, rhs, rhs_scale, rhs_format, acc=None, **kw):
+    lf, rf = getattr(lhs_format, "value", lhs_format), getattr(rhs_format, "value", rhs_format)
+    A = _ds_decode(lhs, lf, 1)                      # (M, K)
+    B = _ds_decode(rhs, rf, 0)                      # (K, N)
+    K = A.shape[1]
+    assert B.shape[0] == K
+    if lhs_scale is not None and getattr(lhs_scale, "value", 0) is not None:
+        sa = _ds_scale(lhs_scale)                   # (M, K / gs)
+        A = A * np.repeat(sa, K // sa.shape[1], axis=1)
+    if rhs_scale is not None and getattr(rhs_scale, "value", 0) is not None:
+        sb = _ds_scale(rhs_scale)                   # (N, K / gs)
+        B = B * np.repeat(sb, K // sb.shape[1], axis=1).T
+    out = (A @ B).astype(np.float32)
+    if acc is not None:
+        out = out + acc.handle.data.astype(np.float32)
+    return tl.tensor(_interp.TensorHandle(out.astype(np.float32), tl.float32), tl.block_type(tl.float32, list(out.shape)))
+
+
+tl.dot_scaled = _dot_scaled_standin
 
 
 class _L(list):  # per-device LUT list indexed with device.index (None on CPU)
@@ -321,6 +409,63 @@ def case_mxfp(name, nbits, N=64, K=256, dtype=torch.bfloat16):
                {"in_W": bits(W), "q_codes": bits(W_qq), "q_scales": bits(sc)})
 
 
+def _edge_rows(x):
+    """Plant the cases the quantisers branch on into the first rows of x (in place): an all-zero group, a group whose
+    maximum is an exact power of two times 6 / 448 (scale mantissa == 0 -> exponent not bumped) with elements sitting
+    exactly on the e2m1 rounding thresholds (ties), a group of tiny values (exponent clamp at 2^-30) and a large one."""
+    K = x.shape[1]
+    x[0, 0:32] = 0
+    if K >= 64:
+        t = torch.tensor([6, 0.25, 0.75, 1.25, 1.75, 2.5, 3.5, 5.0, -0.25, -0.75, -1.25, -1.75, -2.5, -3.5, -5.0, -6,
+                          0.5, 1.0, 1.5, 2.0, 3.0, 4.0, 0.26, 0.74, 5.01, 4.99, -0.0, 0.1, 0.2, 0.3, 0.4, 0.6]) * 0.125
+        x[0, 32:64] = t.to(x.dtype)
+    if K >= 96:
+        x[0, 64:96] = (torch.arange(32) - 16).to(x.dtype) * 1e-7 if x.dtype != torch.float16 else (torch.arange(32) - 16).to(x.dtype) * 6e-8
+    if K >= 128:
+        x[0, 96:128] = (torch.arange(32) - 15.5).to(x.dtype) * (3000.0 if x.dtype == torch.float16 else 1e6)
+    if K >= 160:
+        x[0, 128:160] = torch.tensor([448.0] + [float(v) for v in range(1, 32)]).to(x.dtype) * 0.5
+    return x
+
+
+def case_actq_mx(name="actq_mx"):
+    """MX / NV activation quantisers (quant_utils.py:503-954, the *_triton_v2 functions forward_functional calls)."""
+    arrays, ok, failed = {}, [], {}
+    fns = {"mxfp8": lambda t: ref_qu.scale_activations_mxfp8_triton_v2(t, torch.float8_e4m3fn),
+           "mxfp4": ref_qu.scale_activations_mxfp4_triton_v2,
+           "nvfp4": ref_qu.scale_activations_nvfp4_triton_v2}
+    for dt, tag in ((torch.float16, "f16"), (torch.bfloat16, "bf16")):
+        for M in (1, 5, 33):
+            x = _edge_rows(xgen(M, 256, dt, 500 + M))
+            arrays[f"x_{tag}_M{M}"] = bits(x)
+            for kind, fn in fns.items():
+                key = f"{kind}_{tag}_M{M}"
+                try:
+                    q, sc = fn(x.clone())
+                    arrays["q_" + key] = bits(q)
+                    arrays["s_" + key] = bits(sc)
+                    ok.append(key)
+                except Exception as e:
+                    failed[key] = repr(e)[:200]
+    save(name, arrays, {"kernels_ok": ok, "kernels_failed": failed})
+
+
+def case_mx_dynamic(name, proc_name, kwargs, quant, N=64, K=256, dtype=torch.bfloat16):
+    """MXFP / NVFP weights with dynamically quantised activations (helper.py:660-945)."""
+    from gemlite import helper as ref_helper
+    g = torch.Generator().manual_seed(51)
+    W = (torch.randn(N, K, generator=g) / 10).to(dtype)
+    q = ref_qu.WeightQuantizerMXFP(compute_dtype=dtype, device="cpu")
+    with _dynamo.config.patch(disable=True):
+        W_qq, sc = getattr(q, quant)(W, index=True)
+    gs = 16 if quant == "quantize_nvfp4" else 32
+    W_qq, sc = W_qq.view(N, K), sc.view(N, K // gs)
+    layer = getattr(ref_helper, proc_name)(device="cpu", dtype=dtype, **kwargs).from_weights(W_qq, scales=sc)
+    xs = [_edge_rows(xgen(M, K, dtype, 600 + M)) for M in (1, 4, 33)]
+    layer_case(name, layer, xs, ["GEMM_SPLITK", "GEMM"],
+               {"in_W": bits(W), "q_codes": bits(W_qq), "q_scales": bits(sc)})
+
+
 def main():
     jobs = [
         ("bitpack", case_bitpack, ()),
@@ -340,6 +485,13 @@ def main():
         ("a8w8_fp8_dynamic", case_a8w8_dynamic, ("a8w8_fp8_dynamic", True)),
         ("a16w4_mxfp_bf16", case_mxfp, ("a16w4_mxfp_bf16", 4)),
         ("a16w8_mxfp_bf16", case_mxfp, ("a16w8_mxfp_bf16", 8)),
+        ("actq_mx", case_actq_mx, ()),
+        ("a8w8_mxfp_dynamic_post", case_mx_dynamic, ("a8w8_mxfp_dynamic_post", "A8W8_MXFP_dynamic", {"post_scale": True}, "quantize_mxfp8")),
+        ("a8w8_mxfp_dynamic", case_mx_dynamic, ("a8w8_mxfp_dynamic", "A8W8_MXFP_dynamic", {"post_scale": False}, "quantize_mxfp8")),
+        ("a8w4_mxfp_dynamic", case_mx_dynamic, ("a8w4_mxfp_dynamic", "A8W4_MXFP_dynamic", {"post_scale": False}, "quantize_mxfp4")),
+        ("a8w4_mxfp_dynamic_post", case_mx_dynamic, ("a8w4_mxfp_dynamic_post", "A8W4_MXFP_dynamic", {"post_scale": True}, "quantize_mxfp4")),
+        ("a4w4_mxfp_dynamic", case_mx_dynamic, ("a4w4_mxfp_dynamic", "A4W4_MXFP_dynamic", {}, "quantize_mxfp4")),
+        ("a4w4_nvfp_dynamic", case_mx_dynamic, ("a4w4_nvfp_dynamic", "A4W4_NVFP_dynamic", {}, "quantize_nvfp4")),
     ]
     only = set(sys.argv[1:])
     for name, fn, args in jobs:

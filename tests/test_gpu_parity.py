@@ -11,14 +11,17 @@ import gemlite_b200
 from gemlite_b200 import DType, GemLiteLinear, _cabi
 from gemlite_b200 import bitpack as B
 from gemlite_b200.helper import (A16W8_INT8, A16W4_HQQ_INT, A16W8_FP8, A8W8_INT8_dynamic, A8W8_FP8_dynamic,
-                                 A16W4_MXFP, A16W8_MXFP, A16W158_INT)
+                                 A16W4_MXFP, A16W8_MXFP, A16W158_INT, A8W8_MXFP_dynamic, A8W4_MXFP_dynamic,
+                                 A4W4_MXFP_dynamic, A4W4_NVFP_dynamic)
 from gemlite_b200.quant_utils import scale_activations_per_token
 from oracle import gemlite_oracle as O
 from oracle import recipes as R
-from golden_io import from_bits, layer_cases, load, tdtype
+from golden_io import MX_DYNAMIC, from_bits, layer_cases, load, tdtype
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
+# paths written without GPU time to validate them (MX / NV activation quantisers + dynamic MX layers): opt-in
+EXPERIMENTAL = os.environ.get("GEMLITE_B200_EXPERIMENTAL", "0") not in ("", "0")
 # opt-in A8W8 decode kernel (gl_gemv_a8.cu, read once by the library at its first A8W8 call)
 A8_GEMV = os.environ.get("GLB_A8_GEMV", "0") not in ("", "0")
 
@@ -144,6 +147,21 @@ def build_gpu_layer(name, z, info):
         layer = GemLiteLinear(4, K, K, N, DType.INT8, DType.FP32, scaled_activations=False)
         layer.pack(W_q, scales=sc, zeros=7, bias=None)
         return layer
+    if name in MX_DYNAMIC:
+        # the reference's own quantised weights and scales (pre-quantised branch of from_weights, helper.py:668-705)
+        kind, post = MX_DYNAMIC[name]
+        N, K = from_bits(z["in_W"], torch.bfloat16).shape
+        gs = 16 if kind == "a4w4_nv" else 32
+        if kind == "a8w8":
+            W_q = from_bits(z["q_codes"], torch.float8_e4m3fn).view(N, K)
+        else:
+            W_q = torch.from_numpy(z["q_codes"]).view(N, K)
+        sc = from_bits(z["q_scales"], torch.float8_e4m3fn if kind == "a4w4_nv" else torch.float8_e8m0fnu).view(N, K // gs)
+        proc = {"a8w8": lambda: A8W8_MXFP_dynamic(device=DEV, dtype=torch.bfloat16, post_scale=post),
+                "a8w4": lambda: A8W4_MXFP_dynamic(device=DEV, dtype=torch.bfloat16, post_scale=post),
+                "a4w4_mx": lambda: A4W4_MXFP_dynamic(device=DEV, dtype=torch.bfloat16),
+                "a4w4_nv": lambda: A4W4_NVFP_dynamic(device=DEV, dtype=torch.bfloat16)}[kind]()
+        return proc.from_weights(W_q, scales=sc)
     if "mxfp" in name:
         W = from_bits(z["in_W"], torch.bfloat16)
         lin = torch.nn.Linear(W.shape[1], W.shape[0], bias=False, dtype=torch.bfloat16, device=DEV)
@@ -157,6 +175,8 @@ def build_gpu_layer(name, z, info):
 def test_against_reference_fixtures(name):
     """pack() reproduces the reference's tensors/metadata bit for bit; forward() matches the reference
     kernels' recorded outputs (where the CPU interpreter executes them faithfully) and the oracle."""
+    if name in MX_DYNAMIC and not EXPERIMENTAL:
+        pytest.skip("dynamic MX / NV activation paths are opt-in (GEMLITE_B200_EXPERIMENTAL=1) until validated")
     z, info = load(name)
     layer = build_gpu_layer(name, z, info)
     assert layer.get_meta_args() == [int(v) for v in z["meta_args"]]
@@ -421,6 +441,60 @@ def test_a8w8_decode_kernel_vs_oracle():
             if Ni % 128 == 0:
                 assert _cabi.last_kernel() == "gemv_a8w8_int8", (Ni, Ki, Mi, _cabi.last_kernel())
             assert got.dtype == torch.int32 and torch.equal(got.cpu(), xi.int() @ Wi.int().t()), (Ni, Ki, Mi)
+
+
+@pytest.mark.skipif(not EXPERIMENTAL, reason="MX / NV activation quantisers are opt-in (GEMLITE_B200_EXPERIMENTAL=1) until validated")
+def test_mx_activation_quantisers_bit_exact():
+    """glb_quant_act_mx against (a) the reference's own outputs on the edge-case fixture and (b) the oracle on seeded
+    inputs: codes AND scales bit for bit (fp32 arithmetic with IEEE division on both sides)."""
+    from gemlite_b200.quant_utils import scale_activations_mxfp8, scale_activations_mxfp4, scale_activations_nvfp4
+    gpu = {"mxfp8": scale_activations_mxfp8, "mxfp4": scale_activations_mxfp4, "nvfp4": scale_activations_nvfp4}
+    cpu = {"mxfp8": O.quantize_activations_mxfp8, "mxfp4": O.quantize_activations_mxfp4, "nvfp4": O.quantize_activations_nvfp4}
+    z, info = load("actq_mx")
+    for tag, dt in (("f16", torch.float16), ("bf16", torch.bfloat16)):
+        for M in (1, 5, 33):
+            x = from_bits(z[f"x_{tag}_M{M}"], dt)
+            for kind in gpu:
+                q, sc = gpu[kind](x.to(DEV))
+                assert _cabi.last_kernel() == "act_quant_mx"
+                key = f"{kind}_{tag}_M{M}"
+                assert np.array_equal(q.cpu().view(torch.uint8).numpy(), z["q_" + key]), key
+                assert np.array_equal(sc.cpu().view(torch.uint8).numpy(), z["s_" + key]), key
+    for dt in (torch.float16, torch.bfloat16, torch.float32):
+        for (M, K) in ((1, 4096), (7, 1024), (64, 2048), (130, 512)):
+            x = xgen(M, K, dt, 900 + M) * (1 + 50 * torch.rand(M, 1, generator=torch.Generator().manual_seed(M)))
+            for kind in gpu:
+                q, sc = gpu[kind](x.to(DEV))
+                qo, so = cpu[kind](x)
+                assert q.shape == qo.shape and sc.shape == so.shape and q.dtype == qo.dtype and sc.dtype == so.dtype
+                assert torch.equal(q.cpu().view(torch.uint8), qo.view(torch.uint8)), (kind, dt, M, K)
+                assert torch.equal(sc.cpu().view(torch.uint8), so.view(torch.uint8)), (kind, dt, M, K)
+    # 3-d input: flattened like the reference's *_triton_v2 functions
+    q, sc = scale_activations_mxfp4(xgen(6, 256, torch.float16, 5).view(2, 3, 256).to(DEV))
+    assert tuple(q.shape) == (6, 128) and tuple(sc.shape) == (32, 8)
+
+
+@pytest.mark.skipif(not EXPERIMENTAL, reason="dynamic MX layers are opt-in (GEMLITE_B200_EXPERIMENTAL=1) until validated")
+def test_mx_dynamic_layers_vs_oracle():
+    """A8W8 / A8W4 / A4W4 MXFP and A4W4 NVFP with activations quantised on the fly, larger shapes than the fixtures,
+    through from_linear (GPU weight quantiser) -> forward, against the oracle fed with the layer's own tensors."""
+    N, K = 512, 1024
+    W = (torch.randn(N, K, generator=torch.Generator().manual_seed(61)) / 10).to(torch.bfloat16)
+    cases = [(A8W8_MXFP_dynamic, {"post_scale": True}), (A8W8_MXFP_dynamic, {"post_scale": False}),
+             (A8W4_MXFP_dynamic, {"post_scale": True}), (A8W4_MXFP_dynamic, {"post_scale": False}),
+             (A4W4_MXFP_dynamic, {}), (A4W4_NVFP_dynamic, {})]
+    for cls, kw in cases:
+        for dt in (torch.bfloat16, torch.float16):
+            lin = torch.nn.Linear(K, N, bias=True, dtype=dt, device=DEV)
+            lin.weight.data = W.to(device=DEV, dtype=dt)
+            layer = cls(device=DEV, dtype=dt, **kw).from_linear(lin, del_orig=False)
+            p = oracle_from_layer(layer)
+            for M in (1, 5, 40, 130):
+                x = xgen(M, K, dt, 700 + M)
+                y = layer(x.to(DEV))
+                assert _cabi.last_kernel() == "generic_cuda_core"
+                e = relerr(y, O.forward(p, x))
+                assert e <= max(REL[dt], 2e-3), (cls.__name__, kw, dt, M, e)
 
 
 def test_mxfp_weight_only_vs_oracle_and_unquantised():
