@@ -143,13 +143,24 @@ class WeightQuantizerMXFP:
         return W_q, scales.to(torch.float8_e8m0fnu)
 
     def quantize_nvfp4(self, W: Tensor, window_size: int = 0, index: bool = False):
-        if window_size != 0:
-            raise NotImplementedError("quantize_nvfp4: window search is not implemented")
         fp8 = torch.float8_e4m3fn
+        eps = 1e-6
         Wf = W.reshape(-1, 16).float()
         ideal = Wf.abs().amax(dim=1, keepdim=True) / 6.0 / NVFP4_META_SCALE
         scales = ideal.clamp_(max=torch.finfo(fp8).max).to(fp8)
-        full = (scales.to(Wf.dtype) * NVFP4_META_SCALE).clamp_(min=1e-6)
+        if window_size != 0:
+            # neighbouring e4m3 bit patterns of the ideal scale (quant_utils.py:186-205); the error is measured against
+            # candidate * q WITHOUT the 0.05 meta scale, as the reference does
+            offs = torch.arange(-window_size, window_size + 1, device=W.device, dtype=torch.int).view(1, -1)
+            cand = (scales.view(torch.int8) + offs).clamp_(-128, 127).to(torch.int8)
+            cand[cand == -1] = 1            # the two e4m3 NaN patterns
+            cand[cand == 127] = 1
+            cand = cand.view(fp8).float()
+            cand[cand < eps] = eps
+            q = self.round_to_closest_fp4(Wf.unsqueeze(1) / (cand * NVFP4_META_SCALE).unsqueeze(-1))
+            err = (Wf.unsqueeze(1) - q * cand.unsqueeze(-1)).abs().mean(dim=-1)
+            scales = torch.gather(cand, 1, torch.argmin(err, dim=1, keepdim=True)).to(fp8)
+        full = (scales.to(Wf.dtype) * NVFP4_META_SCALE).clamp_(min=eps)
         W_q = self.round_to_closest_fp4(Wf / full)
         if index:
             W_q = self.to_index(W_q)

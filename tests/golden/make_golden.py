@@ -450,6 +450,36 @@ def case_actq_mx(name="actq_mx"):
     save(name, arrays, {"kernels_ok": ok, "kernels_failed": failed})
 
 
+def case_weight_quant_mx(name="weight_quant_mx"):
+    """WeightQuantizerMXFP (quant_utils.py:70-225) incl. the window_size scale search: the reference's torch code on CPU."""
+    arrays, ok = {}, []
+    q = ref_qu.WeightQuantizerMXFP(compute_dtype=torch.bfloat16, device="cpu")
+    for dt, tag in ((torch.bfloat16, "bf16"), (torch.float16, "f16")):
+        g = torch.Generator().manual_seed(71)
+        W = (torch.randn(48, 128, generator=g) / 10).to(dt)
+        W[0, :32] = 0
+        W[1, :32] = (torch.tensor([6, 0.25, 0.75, 1.25, 1.75, 2.5, 3.5, 5.0] * 4) * 0.0625).to(dt)
+        arrays[f"W_{tag}"] = bits(W)
+        with _dynamo.config.patch(disable=True):
+            for ws in (0, 1, 2):
+                for fn in ("quantize_mxfp4", "quantize_nvfp4"):
+                    for index in (True, False):
+                        Wq, sc = getattr(q, fn)(W.clone(), window_size=ws, index=index)
+                        key = f"{fn}_{tag}_w{ws}_i{int(index)}"
+                        arrays["q_" + key] = bits(Wq)
+                        arrays["s_" + key] = bits(sc)
+                        ok.append(key)
+            for index in (True, False):
+                Wq, sc = q.quantize_mxfp8(W.clone(), index=index)
+                key = f"quantize_mxfp8_{tag}_i{int(index)}"
+                arrays["q_" + key] = bits(Wq)
+                arrays["s_" + key] = bits(sc)
+                ok.append(key)
+            Wq, sc = q.quantize_mxfp4(W.clone(), window_size=1, index=True)
+            arrays[f"deq_mxfp4_{tag}"] = bits(q.dequantize(Wq, sc, shape=W.shape, dtype=dt))
+    save(name, arrays, {"kernels_ok": ok})
+
+
 def case_mx_dynamic(name, proc_name, kwargs, quant, N=64, K=256, dtype=torch.bfloat16):
     """MXFP / NVFP weights with dynamically quantised activations (helper.py:660-945)."""
     from gemlite import helper as ref_helper
@@ -486,6 +516,7 @@ def main():
         ("a16w4_mxfp_bf16", case_mxfp, ("a16w4_mxfp_bf16", 4)),
         ("a16w8_mxfp_bf16", case_mxfp, ("a16w8_mxfp_bf16", 8)),
         ("actq_mx", case_actq_mx, ()),
+        ("weight_quant_mx", case_weight_quant_mx, ()),
         ("a8w8_mxfp_dynamic_post", case_mx_dynamic, ("a8w8_mxfp_dynamic_post", "A8W8_MXFP_dynamic", {"post_scale": True}, "quantize_mxfp8")),
         ("a8w8_mxfp_dynamic", case_mx_dynamic, ("a8w8_mxfp_dynamic", "A8W8_MXFP_dynamic", {"post_scale": False}, "quantize_mxfp8")),
         ("a8w4_mxfp_dynamic", case_mx_dynamic, ("a8w4_mxfp_dynamic", "A8W4_MXFP_dynamic", {"post_scale": False}, "quantize_mxfp4")),

@@ -35,7 +35,7 @@ def load(name):
     return np.load(os.path.join(GOLDEN_DIR, name + ".npz")), MANIFEST[name]
 
 
-NOT_LAYERS = ("bitpack", "actq_mx")          # fixtures that are not a packed layer + forward outputs
+NOT_LAYERS = ("bitpack", "actq_mx", "weight_quant_mx")          # fixtures that are not a packed layer + forward outputs
 # MXFP / NVFP weights with dynamically quantised activations
 MX_DYNAMIC = {"a8w8_mxfp_dynamic_post": ("a8w8", True), "a8w8_mxfp_dynamic": ("a8w8", False),
               "a8w4_mxfp_dynamic": ("a8w4", False), "a8w4_mxfp_dynamic_post": ("a8w4", True),
