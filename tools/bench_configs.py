@@ -10,7 +10,7 @@ Every line: cold-L2 median of CUDA-event times (256 MB flush between calls), the
 SURVEY.md 8d, the time floor max(bytes / measured HBM peak, flops / tensor peak) and the fraction floor / measured.
 Tensor peaks: bf16 = MEASURED_PEAKS.json; fp8 / int8 = 2 x that (nominal ratio, no measured number on this pool).
 
-    python tools/bench_configs.py [--quick] [--only C3,C4,...]  > profiles/configs_rN.txt
+    python tools/bench_configs.py [--quick] [--small] [--only=C3,C4,...]  > profiles/configs_rN.txt     (--small: C4 at M <= 32 only)
 """
 import json
 import os
@@ -96,7 +96,7 @@ def c4(quick):
     W = (torch.randn(N, K, generator=g, device=DEV) / 10).half()
     for name, proc in (("C4 A8W8 fp8 dynamic", A8W8_FP8_dynamic), ("C4 A8W8 int8 dynamic", A8W8_INT8_dynamic)):
         layer = proc(device=DEV, dtype=torch.float16).from_weights(W.clone())
-        for M in ([1, 64, 4096] if quick else [1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096]):
+        for M in ([1, 2, 4, 8, 16, 32] if "--small" in sys.argv else ([1, 64, 4096] if quick else [1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096])):
             x = (torch.randn(M, K, generator=g, device=DEV) / 10).half()
             t = timed(lambda: layer(x), 5 if quick else 20)
             # W K*N + 4N, x_q M*K + 4M, y 2*M*N, plus the quantiser pass (2*M*K read, M*K write)

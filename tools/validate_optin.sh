@@ -1,0 +1,36 @@
+#!/bin/bash
+# One GPU-box visit that validates everything written without GPU time at the end of round 1:
+#   1. the default suite (must stay green),
+#   2. GEMLITE_B200_EXPERIMENTAL=1: MX / NV activation quantisers + dynamic MX layers (gated tests),
+#   3. GLB_A8_GEMV=1: A8W8 decode kernel (gated tests + the A8W8 tests re-routed through it) and its C4 timings,
+#   4. decode flavours (leader-lane polling, pre-wait-all): parity of the decode tests + chained / 4-stream timings.
+# Flavour libraries must be built BEFORE the visit (nvcc cross-compiles here; the box only loads them):
+#   python -m gemlite_b200.build --flavour leaderwait -DGLB_GEMV_LEADER_WAIT=1
+#   python -m gemlite_b200.build --flavour prewait    -DGLB_GEMV_PREWAIT_ALL=1
+#   python -m gemlite_b200.build --flavour both       -DGLB_GEMV_LEADER_WAIT=1 -DGLB_GEMV_PREWAIT_ALL=1
+# Output: gpurun_out/optin_*.log (merged back by gpurun).
+set -u
+mkdir -p gpurun_out
+sum() { grep -E "^(FAILED|ERROR)|passed|failed" "$1" | cut -c1-240 | tail -12; }
+echo "== 1. default suite"
+timeout 1500 python -m pytest tests -m gpu -q --timeout=300 --tb=short > gpurun_out/optin_default.log 2>&1; sum gpurun_out/optin_default.log
+echo "== 2. MX / NV activation quantisers + dynamic MX layers"
+GEMLITE_B200_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q --timeout=300 --tb=short \
+    -k "mx_activation or mx_dynamic or fixtures" > gpurun_out/optin_mx.log 2>&1; sum gpurun_out/optin_mx.log
+echo "== 3. A8W8 decode kernel"
+GLB_A8_GEMV=1 timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q --timeout=300 --tb=short \
+    -k "a8w8 or int8 or fp8 or fixtures" > gpurun_out/optin_a8.log 2>&1; sum gpurun_out/optin_a8.log
+timeout 300 python tools/bench_configs.py --only=C4 --small > gpurun_out/optin_c4_default.txt 2>&1
+GLB_A8_GEMV=1 timeout 300 python tools/bench_configs.py --only=C4 --small > gpurun_out/optin_c4_gemv.txt 2>&1
+grep -E "M= +(1|2|4|8|16) " gpurun_out/optin_c4_default.txt | cut -c1-150
+grep -E "M= +(1|2|4|8|16) " gpurun_out/optin_c4_gemv.txt | cut -c1-150
+echo "== 4. decode flavours"
+for f in "" leaderwait prewait both; do
+  lib="gemlite_b200/libgemlite_b200${f:+_$f}.so"
+  [ -f "$lib" ] || { echo "($lib not built)"; continue; }
+  tag=${f:-default}
+  GLB_LIB_PATH=$PWD/$lib timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q --timeout=300 --tb=short \
+      -k "decode or fixtures" > gpurun_out/optin_decode_$tag.log 2>&1; echo "$tag: $(sum gpurun_out/optin_decode_$tag.log | tail -1)"
+  GLB_LIB_PATH=$PWD/$lib timeout 300 python tools/decode_streams.py --streams 1,4 --steps 40 2>&1 | sed "s/^/$tag /" | tee -a gpurun_out/optin_decode_streams.txt
+done
+ls -la gpurun_out | tail -15
