@@ -26,6 +26,10 @@ EXPERIMENTAL = os.environ.get("GEMLITE_B200_EXPERIMENTAL", "0") not in ("", "0")
 A8_GEMV = os.environ.get("GLB_A8_GEMV", "0") not in ("", "0")
 
 
+# opt-in tensor-path flavour of the MXFP4 decode kernel (GLB_MXV_VARIANT=1)
+MXV_NAME = "gemv_mxfp4_mma" if os.environ.get("GLB_MXV_VARIANT", "0") == "1" else "gemv_mxfp4"
+
+
 def a8_kernel_name(kind, M):
     if A8_GEMV and M <= 16:
         return f"gemv_a8w8_{kind}"
@@ -539,7 +543,7 @@ def test_mxfp4_pair_kernel_vs_oracle(dtype):
         x = xgen(M, K, dtype, 300 + M)
         y = layer(x.to(DEV))
         # M <= 4: streaming CUDA-core kernel (gl_gemv_mx.cu); above: CTA-pair tcgen05 kernel
-        assert _cabi.last_kernel() == ("gemv_mxfp4" if M <= 4 else "gemm_a16w4_mxfp4_tcgen05_2cta"), (M, _cabi.last_kernel())
+        assert _cabi.last_kernel() == (MXV_NAME if M <= 4 else "gemm_a16w4_mxfp4_tcgen05_2cta"), (M, _cabi.last_kernel())
         assert y.dtype == dtype and relerr(y, O.forward(p, x)) <= REL[dtype], (dtype, M)
         if M <= 4:   # forcing "GEMM" keeps the tensor-core kernel; both kernels must agree with the oracle
             yg = layer.forward_manual(x.to(DEV), "GEMM")
