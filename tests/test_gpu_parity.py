@@ -117,6 +117,21 @@ def test_pack_matches_reference_fixture():
 # ------------------------------------------------------------------------------------------------
 def build_gpu_layer(name, z, info):
     """Same construction as tests/golden/make_golden.py, on the GPU with gemlite_b200."""
+    if name in MX_DYNAMIC:
+        # the reference's own quantised weights and scales (pre-quantised branch of from_weights, helper.py:668-705)
+        kind, post = MX_DYNAMIC[name]
+        N, K = from_bits(z["in_W"], torch.bfloat16).shape
+        gs = 16 if kind == "a4w4_nv" else 32
+        if kind == "a8w8":
+            W_q = from_bits(z["q_codes"], torch.float8_e4m3fn).view(N, K)
+        else:
+            W_q = torch.from_numpy(z["q_codes"]).view(N, K)
+        sc = from_bits(z["q_scales"], torch.float8_e4m3fn if kind == "a4w4_nv" else torch.float8_e8m0fnu).view(N, K // gs)
+        proc = {"a8w8": lambda: A8W8_MXFP_dynamic(device=DEV, dtype=torch.bfloat16, post_scale=post),
+                "a8w4": lambda: A8W4_MXFP_dynamic(device=DEV, dtype=torch.bfloat16, post_scale=post),
+                "a4w4_mx": lambda: A4W4_MXFP_dynamic(device=DEV, dtype=torch.bfloat16),
+                "a4w4_nv": lambda: A4W4_NVFP_dynamic(device=DEV, dtype=torch.bfloat16)}[kind]()
+        return proc.from_weights(W_q, scales=sc)
     if name.startswith("a16w") and "in_W_q" in z.files:
         parts = name.split("_")
         nbits = int(parts[0][4:])
@@ -151,21 +166,6 @@ def build_gpu_layer(name, z, info):
         layer = GemLiteLinear(4, K, K, N, DType.INT8, DType.FP32, scaled_activations=False)
         layer.pack(W_q, scales=sc, zeros=7, bias=None)
         return layer
-    if name in MX_DYNAMIC:
-        # the reference's own quantised weights and scales (pre-quantised branch of from_weights, helper.py:668-705)
-        kind, post = MX_DYNAMIC[name]
-        N, K = from_bits(z["in_W"], torch.bfloat16).shape
-        gs = 16 if kind == "a4w4_nv" else 32
-        if kind == "a8w8":
-            W_q = from_bits(z["q_codes"], torch.float8_e4m3fn).view(N, K)
-        else:
-            W_q = torch.from_numpy(z["q_codes"]).view(N, K)
-        sc = from_bits(z["q_scales"], torch.float8_e4m3fn if kind == "a4w4_nv" else torch.float8_e8m0fnu).view(N, K // gs)
-        proc = {"a8w8": lambda: A8W8_MXFP_dynamic(device=DEV, dtype=torch.bfloat16, post_scale=post),
-                "a8w4": lambda: A8W4_MXFP_dynamic(device=DEV, dtype=torch.bfloat16, post_scale=post),
-                "a4w4_mx": lambda: A4W4_MXFP_dynamic(device=DEV, dtype=torch.bfloat16),
-                "a4w4_nv": lambda: A4W4_NVFP_dynamic(device=DEV, dtype=torch.bfloat16)}[kind]()
-        return proc.from_weights(W_q, scales=sc)
     if "mxfp" in name:
         W = from_bits(z["in_W"], torch.bfloat16)
         lin = torch.nn.Linear(W.shape[1], W.shape[0], bias=False, dtype=torch.bfloat16, device=DEV)
