@@ -17,6 +17,10 @@
 //     dot product does not see.
 //   * warp w owns K-eighth w; the 8 partial tiles are summed through shared memory in warp order (integer sums are
 //     exact in any order; the fp32 order is fixed, so the result is deterministic).
+// SASS (cuobjdump, sm_100a): the int8 flavour issues native IMMA.16832.S8.S8; there is NO legacy fp8 MMA on sm_100a -- ptxas
+// lowers mma.sync...e4m3/e5m2 to F2FP.F16.E4M3.UNPACK_B conversions + HMMA.16816.F32 (exact products, fp32 accumulate),
+// about 0.75 conversions per weight, so the fp8 flavour is expected to sit near the issue limit rather than at the HBM
+// floor.  Weights arrive by UBLKCP (cp.async.bulk).
 // STATUS: written at the end of round 1 without GPU time left to validate it -- reachable only with GLB_A8_GEMV=1.
 #include <cuda.h>
 #include <stdlib.h>
