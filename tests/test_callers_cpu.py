@@ -67,3 +67,27 @@ def test_default_batch_sizes_and_processor_surface():
                  "A8W2_HQQ_INT_dynamic", "A8W8_MXFP_dynamic", "A8Wn_MXFP_dynamic", "A8W4_MXFP_dynamic",
                  "A4W4_MXFP_dynamic", "A4W4_NVFP_dynamic", "A16W158_INT", "A8W158_INT_dynamic", "patch_model", "warmup"):
         assert hasattr(helper, name), name
+
+
+def test_forward_functional_traces_with_fake_tensors():
+    """The registered fake of `forward_functional` (core.py:197-206 in the reference) lets torch.compile / vLLM trace a
+    packed layer without running it: shape (..., N), dtype = the layer's OUTPUT dtype (the reference's fake returns
+    x.dtype, which is wrong for int8 / fp8 activations -- not reproduced)."""
+    import os
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    import gemlite_b200  # noqa: F401  (registers the op)
+    from gemlite_b200 import DType
+    ns = os.environ.get("GEMLITE_B200_OP_NAMESPACE", "gemlite")
+    op = getattr(torch.ops, ns).forward_functional
+    K, N = 256, 64
+    with FakeTensorMode():
+        W_q = torch.empty(K // 8, N, dtype=torch.int32)
+        scales = torch.empty(K // 64, N, dtype=torch.float16)
+        zeros = torch.empty(K // 64, N, dtype=torch.float16)
+        meta = [0, 4, 64, 15, 8, DType.FP16.value, DType.FP16.value, DType.FP32.value, DType.FP16.value, 0, 4, 1]
+        y = op(torch.empty(3, 5, K, dtype=torch.float16), None, [W_q, scales, zeros], meta, -1)
+        assert tuple(y.shape) == (3, 5, N) and y.dtype == torch.float16
+        meta8 = [1, 8, K, 255, 1, DType.INT8.value, DType.BF16.value, DType.INT32.value, DType.FP32.value, 3, 0, 0]
+        y8 = op(torch.empty(7, K, dtype=torch.bfloat16), torch.empty(N, dtype=torch.bfloat16),
+                [torch.empty(K, N, dtype=torch.int8), torch.empty(1, N, dtype=torch.float32), torch.empty(1, 0, dtype=torch.int32)], meta8, 4)
+        assert tuple(y8.shape) == (7, N) and y8.dtype == torch.bfloat16
