@@ -6,7 +6,9 @@
   C5  A16W4 MXFP4 gs=32 weight-only, K=N=16384, M in {1, 16, 4096}           (single GPU here; sharded: bench.py --gpus)
   Cx  A16W4 gs=128 small-batch sweep M=1..256, K=N=4096                       (decode <-> prefill transition)
 
-Every line: cold-L2 median of CUDA-event times (256 MB flush between calls), the algorithmic bytes / flops of
+Every line: cold-L2 median of CUDA-event times of single calls (256 MB flush between calls; includes the launch
+latency of an isolated call), and for M <= 64 additionally `steady=`: the sustained time per call over a rotating set of
+weight copies larger than L2 inside one CUDA graph (SURVEY 8d asks for both), the algorithmic bytes / flops of
 SURVEY.md 8d, the time floor max(bytes / measured HBM peak, flops / tensor peak) and the fraction floor / measured.
 Tensor peaks: bf16 = MEASURED_PEAKS.json; fp8 / int8 = 2 x that (nominal ratio, no measured number on this pool).
 
@@ -50,12 +52,54 @@ def timed(fn, iters):
     return ts[len(ts) // 2]
 
 
-def line(tag, M, K, N, t, nbytes, flops, tc_peak, kern):
+def timed_steady(layer, x, weight_bytes, replays=20):
+    """Sustained time per call: enough deep copies of the layer that one pass streams > 200 MB of distinct weights
+    (> the 126 MB L2), every copy called once with the same x inside ONE CUDA graph (launch overhead excluded the same
+    way for every contender; consecutive calls are independent, so weight prefetch under programmatic dependent launch
+    overlaps as it does in a serving loop).  SURVEY 8d asks for this next to the flushed single-call number."""
+    import copy
+    n = max(2, min(48, int(200e6 // max(weight_bytes, 1)) + 1))
+    copies = [layer] + [copy.deepcopy(layer) for _ in range(n - 1)]
+    stream = torch.cuda.Stream(device=DEV)
+    keep = []
+    with torch.cuda.stream(stream):
+        for c in copies:
+            c(x)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=stream):
+            for c in copies:
+                keep.append(c(x))
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(replays):
+        graph.replay()
+    b.record()
+    torch.cuda.synchronize()
+    del graph, keep, copies
+    return a.elapsed_time(b) * 1e-3 / (replays * n)
+
+
+def steady_if_small(layer, x, M, weight_bytes):
+    if M > 64 or "--no-steady" in sys.argv:
+        return None
+    try:
+        return timed_steady(layer, x, weight_bytes)
+    except Exception as e:   # a diagnostic column must not lose the line
+        print(f"# steady-state timing failed: {e!r}"[:200], flush=True)
+        return None
+
+
+def line(tag, M, K, N, t, nbytes, flops, tc_peak, kern, steady=None):
     floor_b, floor_f = nbytes / HBM, flops / tc_peak
     floor = max(floor_b, floor_f)
     bound = "hbm" if floor_b >= floor_f else "tensor"
+    extra = "" if steady is None else f"  steady={steady * 1e6:7.2f} us frac={floor / steady:5.3f}"
     print(f"{tag:26s} M={M:5d} K={K:5d} N={N:5d}  {t * 1e6:9.1f} us  {nbytes / t / 1e9:8.1f} GB/s  {flops / t / 1e12:8.1f} TFLOP/s  "
-          f"bound={bound:6s} floor={floor * 1e6:8.1f} us  frac={floor / t:6.3f}  kernel={kern}", flush=True)
+          f"bound={bound:6s} floor={floor * 1e6:8.1f} us  frac={floor / t:6.3f}  kernel={kern}{extra}", flush=True)
 
 
 def c3(quick):
@@ -87,7 +131,8 @@ def small_batch(quick):
         x = (torch.randn(M, K, generator=g, device=DEV) / 10).half()
         t = timed(lambda: layer(x), 5 if quick else 20)
         nbytes = K * N // 2 + 2 * (K // 128) * N * 2 + 2 * M * K + 2 * M * N
-        line("Cx A16W4 gs128 small-M", M, K, N, t, nbytes, 2.0 * M * K * N, TC16, _cabi.last_kernel())
+        kern = _cabi.last_kernel()
+        line("Cx A16W4 gs128 small-M", M, K, N, t, nbytes, 2.0 * M * K * N, TC16, kern, steady_if_small(layer, x, M, K * N // 2))
 
 
 def c4(quick):
@@ -101,7 +146,8 @@ def c4(quick):
             t = timed(lambda: layer(x), 5 if quick else 20)
             # W K*N + 4N, x_q M*K + 4M, y 2*M*N, plus the quantiser pass (2*M*K read, M*K write)
             nbytes = K * N + 4 * N + M * K + 4 * M + 2 * M * N + 3 * M * K
-            line(name, M, K, N, t, nbytes, 2.0 * M * K * N, 2 * TC16, _cabi.last_kernel())
+            kern = _cabi.last_kernel()
+            line(name, M, K, N, t, nbytes, 2.0 * M * K * N, 2 * TC16, kern, steady_if_small(layer, x, M, K * N))
         del layer
 
 
@@ -117,7 +163,8 @@ def c5(quick):
         x = (torch.randn(M, K, generator=g, device=DEV) / 10).bfloat16()
         t = timed(lambda: layer(x), 3 if M > 64 else (5 if quick else 10))
         nbytes = K * N // 2 + K * N // 32 + 2 * M * K + 2 * M * N
-        line("C5 A16W4 MXFP4 gs32", M, K, N, t, nbytes, 2.0 * M * K * N, TC16, _cabi.last_kernel())
+        kern = _cabi.last_kernel()
+        line("C5 A16W4 MXFP4 gs32", M, K, N, t, nbytes, 2.0 * M * K * N, TC16, kern, steady_if_small(layer, x, M, K * N // 2))
 
 
 if __name__ == "__main__":
