@@ -107,7 +107,9 @@ def _strides2(t: Tensor):
 
 
 def _make_desc(W_q: Tensor, scales: Tensor, zeros: Tensor, meta: List[int]) -> _cabi.GlbLinear:
-    key = (W_q.data_ptr(), scales.data_ptr(), zeros.data_ptr(), W_q.stride(), tuple(meta))
+    # pointers alone are not an identity: the allocator hands freed addresses to later layers of other shapes
+    key = (W_q.data_ptr(), scales.data_ptr(), zeros.data_ptr(), W_q.shape, W_q.stride(), W_q.dtype,
+           scales.shape, scales.stride(), scales.dtype, zeros.shape, zeros.stride(), zeros.dtype, tuple(meta))
     d = _DESC_CACHE.get(key)
     if d is not None:
         return d
@@ -132,6 +134,7 @@ def _make_desc(W_q: Tensor, scales: Tensor, zeros: Tensor, meta: List[int]) -> _
         [int(v) for v in meta]
     if len(_DESC_CACHE) > 4096:
         _DESC_CACHE.clear()
+        _WS_BYTES.clear()          # keyed by id(descriptor): ids are recycled once the descriptors are gone
     _DESC_CACHE[key] = d
     return d
 
