@@ -489,6 +489,7 @@ gemm_a16w4_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
 }
 
 // How a problem is cut into work items (shared by the launch and by glb_workspace_bytes).
+constexpr size_t T2_COUNTER_REGION = 64 * 1024;      // 16384 counters = 2048 tiles (8 per tile)
 struct Tc2Plan {
   int tiles_m, tiles_n, splits, kb_per_split, n_mma;
   size_t counter_bytes, partial_bytes;
@@ -502,11 +503,14 @@ Tc2Plan make_plan(const glb_linear& L, int64_t M) {
   p.splits = 1;
   // split K only for M <= 128: measured r1 (profiles/configs_r1.txt) 45 -> 22 us at M=32, 51 -> 39 us at M=128 on a 4096^2
   // layer, but 39 -> 61 us at M=256, where parking and re-reading 256-column fp32 partials costs more than the idle SMs
-  if (M <= 128)
+  if (M <= 128 && (size_t)tiles * 8 * sizeof(int) <= T2_COUNTER_REGION)
     for (int s = std::min(16, pairs / std::max(tiles, 1)); s >= 2; --s)
       if (kblocks % s == 0 && kblocks / s >= T2_STAGES) { p.splits = s; break; }   // fill the SM pairs, keep >= one ring of stages
   p.kb_per_split = kblocks / p.splits;
-  p.counter_bytes = (p.splits > 1) ? (((size_t)tiles * 8 * sizeof(int) + 255) & ~(size_t)255) : 0;
+  // The arrival counters sit in a FIXED region at the start of the workspace and the partial tiles behind it: one
+  // workspace serves every layer on a stream, and a layout that depended on the layer's tile count would let one
+  // layer's partial tiles land on the words another layer reads as (zero) counters.
+  p.counter_bytes = (p.splits > 1) ? T2_COUNTER_REGION : 0;
   p.partial_bytes = (p.splits > 1) ? (size_t)tiles * p.splits * 2 * T2_BM * p.n_mma * sizeof(float) : 0;
   return p;
 }

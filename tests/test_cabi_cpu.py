@@ -133,9 +133,14 @@ def test_workspace_plan_without_gpu():
     assert lib.glb_workspace_bytes(ctypes.byref(d), 4096, -1) == 0       # 256 tiles: no split
     assert lib.glb_workspace_bytes(ctypes.byref(d), 256, -1) == 0        # split-K is not used above M = 128
     w32 = lib.glb_workspace_bytes(ctypes.byref(d), 32, -1)
-    # 16 tiles x 4 splits x 2 CTAs x 128 rows x 64 columns fp32 + 16 x 8 counters (padded to 256 B)
-    assert w32 == 16 * 4 * 2 * 128 * 64 * 4 + 512, w32
+    # fixed 64 KB counter region (the same for every layer: one workspace serves all layers of a stream, so the
+    # partial tiles of one layer must never overlap the words another layer reads as counters)
+    # + 16 tiles x 4 splits x 2 CTAs x 128 rows x 64 columns fp32
+    assert w32 == 65536 + 16 * 4 * 2 * 128 * 64 * 4, w32
     w128 = lib.glb_workspace_bytes(ctypes.byref(d), 128, -1)
-    assert w128 == 16 * 4 * 2 * 128 * 128 * 4 + 512, w128
+    assert w128 == 65536 + 16 * 4 * 2 * 128 * 128 * 4, w128
+    # a layer with another tile count gets the same counter region
+    other = _a16w4_desc(2048, 4096)
+    assert lib.glb_workspace_bytes(ctypes.byref(other), 32, -1) == 65536 + 8 * 8 * 2 * 128 * 64 * 4
     wide = _a16w4_desc(16384, 4096)
     assert lib.glb_workspace_bytes(ctypes.byref(wide), 64, -1) == 0      # 64 tiles already fill the 74 SM pairs

@@ -324,6 +324,33 @@ def test_pair_kernel_split_k_small_batches(dtype):
             assert torch.equal(layer(xd), y)
 
 
+def test_split_k_layers_of_different_width_share_one_workspace():
+    """One per-stream workspace serves every layer.  Layers with different tile counts (q/o vs gate/up projections) take
+    turns in the split-K range: the arrival counters live in a fixed region of the workspace, so the partial tiles one
+    layer parks there can never be read as counters by the next (they could when the layout depended on the tile count)."""
+    dtype, gs, K = torch.float16, 128, 2048
+    layers = []
+    for i, N in enumerate((512, 1024, 256)):
+        W_q, scales, zeros = gen_int(N, K, 4, gs, dtype, seed=40 + i)
+        layer = GemLiteLinear(4, gs, K, N, DType.FP16, DType.FP16).pack(W_q.to(DEV), scales.to(DEV), zeros.to(DEV))
+        p = O.prepare(W_q, scales, zeros, W_nbits=4, group_size=gs, in_features=K, out_features=N)
+        layers.append((layer, p))
+    for M in (32, 100):
+        x = xgen(M, K, dtype, 800 + M)
+        want = [O.forward(p, x) for _, p in layers]
+        xd = x.to(DEV)
+        first = None
+        for rep in range(3):
+            got = [layer(xd) for layer, _ in layers]
+            assert _cabi.last_kernel() == "gemm_a16w4_tcgen05_2cta"
+            for (layer, p), y, w in zip(layers, got, want):
+                assert relerr(y, w) <= REL[dtype], (M, rep, p.out_features, relerr(y, w))
+            if first is None:
+                first = got
+            else:
+                assert all(torch.equal(a, b) for a, b in zip(first, got)), (M, rep)
+
+
 def test_decode_kernel_is_used_for_the_headline_shape():
     N = K = 4096
     W_q, scales, zeros = gen_int(N, K, 4, 128, torch.float16, seed=0)
