@@ -328,9 +328,9 @@ def test_split_k_layers_of_different_width_share_one_workspace():
     """One per-stream workspace serves every layer.  Layers with different tile counts (q/o vs gate/up projections) take
     turns in the split-K range: the arrival counters live in a fixed region of the workspace, so the partial tiles one
     layer parks there can never be read as counters by the next (they could when the layout depended on the tile count)."""
-    dtype, gs, K = torch.float16, 128, 2048
+    dtype, gs, K = torch.float16, 128, 1024
     layers = []
-    for i, N in enumerate((512, 1024, 256)):
+    for i, N in enumerate((4096, 2048, 256)):          # 16, 8 and 1 feature tiles: 512 / 256 / 32 bytes of counters
         W_q, scales, zeros = gen_int(N, K, 4, gs, dtype, seed=40 + i)
         layer = GemLiteLinear(4, gs, K, N, DType.FP16, DType.FP16).pack(W_q.to(DEV), scales.to(DEV), zeros.to(DEV))
         p = O.prepare(W_q, scales, zeros, W_nbits=4, group_size=gs, in_features=K, out_features=N)
