@@ -39,7 +39,7 @@ class GlbLinear(ctypes.Structure):
 
 EXPORTS = [
     "glb_version", "glb_last_error", "glb_last_kernel", "glb_launch_count", "glb_pack_cols", "glb_unpack_cols",
-    "glb_quant_act_per_token", "glb_quant_act_mx", "glb_workspace_bytes", "glb_matmul", "glb_set_pdl", "glb_get_pdl", "glb_debug_timeline",
+    "glb_quant_act_per_token", "glb_quant_act_mx", "glb_stream_capture_id", "glb_workspace_bytes", "glb_matmul", "glb_set_pdl", "glb_get_pdl", "glb_debug_timeline",
 ]
 
 
@@ -73,6 +73,8 @@ def load():
         lib.glb_quant_act_per_token.restype = i32
         lib.glb_quant_act_mx.argtypes = [vp, i64, i64, i32, i32, vp, vp, vp]
         lib.glb_quant_act_mx.restype = i32
+        lib.glb_stream_capture_id.argtypes = [vp]
+        lib.glb_stream_capture_id.restype = ctypes.c_ulonglong
         lib.glb_workspace_bytes.argtypes = [ctypes.POINTER(GlbLinear), i64, i32]
         lib.glb_workspace_bytes.restype = sz
         lib.glb_matmul.argtypes = [ctypes.POINTER(GlbLinear), vp, vp, vp, i64, i32, vp, sz, vp, vp]

@@ -97,6 +97,7 @@ def get_matmul_type(batch_size: int, W_nbits: int, mx_dtype: bool = False) -> st
 _DESC_CACHE = {}
 _WORKSPACE = {}
 _WORKSPACE_RETIRED = []
+_CAPTURE_WS = {}      # (device, stream) -> (capture id, buffer zeroed inside that capture)
 _WS_BYTES = {}       # (descriptor id, M, matmul_type) -> workspace bytes the C library asked for (descriptors are cached, ids are stable)
 
 
@@ -143,16 +144,29 @@ def _workspace(device, nbytes: int) -> Optional[Tensor]:
     """Per (device, stream) scratch for the split-K launches.  Zero-initialised once (the kernels keep arrival counters
     in it and leave them at zero).  Sized so that it never has to grow (the largest request is < 10 MB: at most one
     work item per SM pair); should it grow anyway, the old buffer stays alive because captured CUDA graphs may still
-    point at it."""
+    point at it.
+    Under CUDA-graph capture a buffer allocated here is zeroed by a memset NODE of that graph, i.e. only when that graph
+    replays: it is therefore used by that capture alone (keyed by the capture id) -- a second graph captured on the same
+    stream, or eager calls, never see it, whichever of them runs first."""
     if nbytes == 0:
         return None
-    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    stream = torch.cuda.current_stream(device).cuda_stream
+    key = (device, stream)
     ws = _WORKSPACE.get(key)
-    if ws is None or ws.numel() < nbytes:
-        if ws is not None:
-            _WORKSPACE_RETIRED.append(ws)
-        ws = torch.zeros(max(nbytes, 16 << 20), dtype=torch.uint8, device=device)
-        _WORKSPACE[key] = ws
+    if ws is not None and ws.numel() >= nbytes:
+        return ws                    # zeroed eagerly (warm-up on this stream): valid inside and outside any capture
+    if torch.cuda.is_current_stream_capturing():
+        cap = int(_cabi.load().glb_stream_capture_id(stream))
+        if cap:
+            held = _CAPTURE_WS.get(key)
+            if held is None or held[0] != cap or held[1].numel() < nbytes:
+                held = (cap, torch.zeros(max(nbytes, 4 << 20), dtype=torch.uint8, device=device))
+                _CAPTURE_WS[key] = held                       # the graph's pool keeps earlier captures' buffers alive
+            return held[1]
+    if ws is not None:
+        _WORKSPACE_RETIRED.append(ws)
+    ws = torch.zeros(max(nbytes, 16 << 20), dtype=torch.uint8, device=device)
+    _WORKSPACE[key] = ws
     return ws
 
 

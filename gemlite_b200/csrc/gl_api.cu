@@ -169,6 +169,16 @@ extern "C" void glb_set_pdl(int enabled) { g_pdl_enabled.store(enabled ? 1 : 0);
 extern "C" int glb_get_pdl(void) { return g_pdl_enabled.load(); }
 extern "C" int glb_debug_timeline(unsigned long long* out, int max_words) { return debug_read_timeline(out, max_words); }
 
+extern "C" unsigned long long glb_stream_capture_id(void* stream_) {
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  unsigned long long id = 0;
+  if (cudaStreamGetCaptureInfo((cudaStream_t)stream_, &st, &id) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return (st == cudaStreamCaptureStatusActive) ? id : 0;
+}
+
 extern "C" size_t glb_workspace_bytes(const glb_linear* L, int64_t M, int matmul_type) {
   if (!L || M <= 0) return 0;
   if (matmul_type == GLB_MM_AUTO) matmul_type = pick_matmul_type(*L, M);

@@ -141,6 +141,12 @@ GLB_API int glb_quant_act_per_token(const void* x, int64_t M, int64_t K, int x_d
 GLB_API int glb_quant_act_mx(const void* x, int64_t M, int64_t K, int x_dtype, int mx_dtype,
                      void* q, void* scales, void* stream);
 
+/* Unique id of the CUDA-graph capture `stream` is recording, 0 when it is not capturing.  The workspace contract
+ * ("zero-initialised once") needs it on the caller's side: a buffer first allocated and zeroed INSIDE a capture is only
+ * zero when that graph replays, so a caller must not hand it to launches outside that capture (gemlite_b200/core.py
+ * keeps one workspace per capture id). */
+GLB_API unsigned long long glb_stream_capture_id(void* stream);
+
 /* Scratch the matmul needs for (layer, M, matmul_type); 0 when none.  Non-zero only for the split-K launches of
  * the CTA-pair tcgen05 kernel (16 < M <= 128 on layers with few 256-feature tiles): per-slice arrival counters
  * followed by fp32 partial tiles.  The buffer must be ZERO-INITIALISED once by the caller (the reference's Triton

@@ -621,3 +621,30 @@ def test_error_behaviour():
     with pytest.raises(AssertionError):
         B.pack_weights_over_cols(W_q.to(DEV), 3, 32, True)
     assert layer(torch.zeros(0, 256, dtype=torch.float16, device=DEV)).shape == (0, 64)
+
+
+def test_split_k_under_graph_capture_without_warmup_on_the_capture_stream():
+    """The split-K workspace must be zero before its first use.  When the first split-K call on a stream happens INSIDE a
+    CUDA-graph capture (torch.cuda.graph's own capture stream, warm-up done elsewhere), the buffer is zeroed by a memset
+    node of that graph, i.e. only when that graph replays -- so every capture gets its own buffer.  Two graphs are
+    captured back to back and the SECOND is replayed first; both must reproduce the eager result bit for bit.
+    (Kept last in the file: it is the only test of the capture-id path.)"""
+    dtype, gs, K, N = torch.float16, 128, 1024, 2048
+    W_q, scales, zeros = gen_int(N, K, 4, gs, dtype, seed=77)
+    layer = GemLiteLinear(4, gs, K, N, DType.FP16, DType.FP16).pack(W_q.to(DEV), scales.to(DEV), zeros.to(DEV))
+    xs = [xgen(M, K, dtype, 880 + M).to(DEV) for M in (32, 100)]
+    side = torch.cuda.Stream(device=DEV)
+    with torch.cuda.stream(side):                 # warm-up and eager reference on ANOTHER stream
+        want = [layer(x) for x in xs]
+        assert _cabi.last_kernel() == "gemm_a16w4_tcgen05_2cta"
+    torch.cuda.synchronize()
+    graphs, outs = [], []
+    for x in xs:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):                 # torch's default capture stream: no eager workspace exists for it
+            outs.append(layer(x))
+        graphs.append(g)
+    for i in (1, 0, 1, 0):
+        graphs[i].replay()
+        torch.cuda.synchronize()
+        assert torch.equal(outs[i], want[i]), i
