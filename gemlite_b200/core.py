@@ -174,6 +174,8 @@ def _matmul(x2d: Tensor, bias: Optional[Tensor], tensor_args: List[Tensor], meta
             matmul_type: int) -> Tensor:
     W_q, scales, zeros = tensor_args
     _cabi.require_cuda(x2d, "forward")
+    if W_q.device != x2d.device:
+        raise RuntimeError(f"forward: activations are on {x2d.device}, the layer's weights on {W_q.device}")
     lib = _cabi.load()
     desc = _make_desc(W_q, scales, zeros, meta_args)
     M = x2d.shape[0]

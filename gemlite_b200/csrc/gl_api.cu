@@ -7,7 +7,9 @@
 
 #include <string.h>
 #include <mutex>
+#include <map>
 #include <unordered_map>
+#include <utility>
 
 #include "gl_common.cuh"
 
@@ -103,6 +105,35 @@ int make_tmap_2d(void* out_tmap, int dt, const void* base, uint64_t inner, uint6
     memcpy(v.b, out_tmap, 128);
     g_tmap_cache[key] = v;
   }
+  return GLB_OK;
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to ONE device: a process that drives several GPUs from one
+// thread must opt in on each of them.  Remembered per (kernel, device); the per-thread one-entry cache keeps the mutex off
+// the path of a decode loop that launches the same kernel over and over.
+int ensure_dyn_smem(const void* func, size_t bytes) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  static thread_local const void* last_func = nullptr;
+  static thread_local int last_dev = -1;
+  static thread_local size_t last_bytes = 0;
+  if (func == last_func && dev == last_dev && bytes <= last_bytes) return GLB_OK;
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, size_t> done;      // (kernel, device) -> bytes configured
+  const std::pair<const void*, int> key(func, dev);
+  size_t have = 0;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = done.find(key);
+    if (it != done.end()) have = it->second;
+  }
+  if (have < bytes) {
+    GLB_CHECK_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    std::lock_guard<std::mutex> lk(mu);
+    done[key] = bytes;
+    have = bytes;
+  }
+  last_func = func; last_dev = dev; last_bytes = have;
   return GLB_OK;
 }
 

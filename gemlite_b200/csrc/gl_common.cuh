@@ -59,6 +59,13 @@ inline int dtype_bytes(int dt) {
 int make_tmap_2d(void* out_tmap /*CUtensorMap*/, int glb_elem_dtype, const void* base, uint64_t inner, uint64_t outer,
                  uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer, int swizzle128);
 int num_sms();
+// opt the kernel `func` in to `bytes` of dynamic shared memory on the CURRENT device (remembered per kernel and device)
+int ensure_dyn_smem(const void* func, size_t bytes);
+#define GLB_ENSURE_SMEM(kern, bytes)                                                       \
+  do {                                                                                     \
+    const int _rc = glb::ensure_dyn_smem(reinterpret_cast<const void*>(kern), (size_t)(bytes)); \
+    if (_rc != GLB_OK) return _rc;                                                         \
+  } while (0)
 
 // sub-kernel entry points (one translation unit each)
 int launch_generic(const glb_linear& L, const void* x, const float* scales_x, void* y, int64_t M,

@@ -268,11 +268,7 @@ int launch_a8(const glb_linear& L, const void* x, const float* scales_x, void* y
     P.idesc = ptx::make_idesc(1u, wf, xf, 2 * A8_BM, A8_BT);                            // f32 accumulate, e4m3 = 0 / e5m2 = 1
   }
   auto kern = gemm_a8w8_tc2_kernel<IS_INT>;
-  static thread_local bool configured = false;
-  if (!configured) {
-    GLB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, A8_SMEM));
-    configured = true;
-  }
+  GLB_ENSURE_SMEM(kern, A8_SMEM);
   const int pairs = std::min(num_sms() / 2, P.tiles_m * P.tiles_n);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(2 * pairs));

@@ -494,11 +494,7 @@ int launch_tc(const glb_linear& L, const void* x, void* y, int64_t M, const void
   P.group_size = L.group_size; P.mode = L.W_group_mode;
   P.tiles_m = (int)((M + BT - 1) / BT); P.tiles_n = (int)(L.N / TC_BM);
   auto kern = gemm_a16w4_tc_kernel<BF16, BT>;
-  static thread_local bool configured = false;
-  if (!configured) {
-    GLB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-    configured = true;
-  }
+  GLB_ENSURE_SMEM(kern, S::TOTAL);
   const int grid = std::min(num_sms(), P.tiles_m * P.tiles_n);
   kern<<<grid, TC_THREADS, S::TOTAL, stream>>>(tx, tw, P);
   count_launch();
@@ -528,11 +524,7 @@ int launch_t8(const glb_linear& L, const void* x, const float* scales_x, void* y
     idesc = ptx::make_idesc(1u, wf, xf, TC_BM, BT);                                    // f32 accumulate, e4m3 = 0 / e5m2 = 1
   }
   auto kern = gemm_a8w8_tc_kernel<IS_INT, BT>;
-  static thread_local bool configured = false;
-  if (!configured) {
-    GLB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-    configured = true;
-  }
+  GLB_ENSURE_SMEM(kern, S::TOTAL);
   const int grid = std::min(num_sms(), P.tiles_m * P.tiles_n);
   kern<<<grid, T8_THREADS, S::TOTAL, stream>>>(tx, tw, P, idesc);
   count_launch();

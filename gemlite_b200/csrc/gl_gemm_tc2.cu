@@ -547,11 +547,7 @@ int launch_tc2(const glb_linear& L, const void* x, void* y, int64_t M, void* wor
     P.prefetch = pf;
   }
   auto kern = gemm_a16w4_tc2_kernel<BF16, WFMT>;
-  static thread_local bool configured = false;
-  if (!configured) {
-    GLB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM));
-    configured = true;
-  }
+  GLB_ENSURE_SMEM(kern, T2_SMEM);
   const int pairs = std::min(num_sms() / 2, P.tiles_m * P.tiles_n * P.splits);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(2 * pairs));

@@ -367,13 +367,7 @@ template <bool BF16, int MT, int RPG, int KSPLIT, bool FAST>
 int launch_w4(const GemvParams& P, cudaStream_t stream) {
   const size_t smem = gemv_smem_bytes<MT, KSPLIT>(P.K);
   auto kern = gemv_w4_mma_kernel<BF16, MT, RPG, KSPLIT, FAST>;
-  if (smem > 48 * 1024) {
-    static thread_local size_t configured = 0;
-    if (configured < smem) {
-      GLB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = smem;
-    }
-  }
+  if (smem > 48 * 1024) GLB_ENSURE_SMEM(kern, smem);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(P.N / GV_COLS) * KSPLIT);
   cfg.blockDim = dim3(GV_THREADS);
@@ -795,13 +789,7 @@ int launch_w4_tma(const glb_linear& L, const GemvParams& P0, int late_trigger, c
   }
   const size_t smem = gemv_tma_smem_bytes<MT, KSPLIT, NW, META_REGS>(P0.K, P0.group_size);
   auto kern = gemv_w4_tma_kernel<BF16, MT, RPG, KSPLIT, FAST, NW, META_REGS>;
-  if (smem > 48 * 1024) {
-    static thread_local size_t configured = 0;
-    if (configured < smem) {
-      GLB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = smem;
-    }
-  }
+  if (smem > 48 * 1024) GLB_ENSURE_SMEM(kern, smem);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(P0.N / GV_COLS) * KSPLIT);
   cfg.blockDim = dim3(NW * 32);

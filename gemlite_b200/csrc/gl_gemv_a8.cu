@@ -218,11 +218,7 @@ template <int FMT, int NT>
 int launch_a8v(const A8vParams& P, cudaStream_t stream) {
   const size_t smem = a8v_smem_bytes(P.K, NT);
   auto kern = gemv_a8w8_kernel<FMT, NT>;
-  static thread_local size_t configured = 0;
-  if (smem > 48 * 1024 && configured < smem) {
-    GLB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  if (smem > 48 * 1024) GLB_ENSURE_SMEM(kern, smem);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(P.N / A8V_ROWS));
   cfg.blockDim = dim3(A8V_WARPS * 32);

@@ -342,11 +342,7 @@ int launch_mxv_mma(const glb_linear& L, const void* x, void* y, int64_t M, const
   P.x = x; P.y = y; P.bias = bias; P.M = (int)M; P.N = (int)L.N; P.K = (int)L.K;
   const size_t smem = (size_t)MXV_STAGES * MXV_TILE + (size_t)MT * L.K * 2 + (size_t)4 * MT * MXV_ROWS * 4 + 2 * MXV_STAGES * 8 + 64;
   auto kern = gemv_mxfp4_mma_kernel<BF16, MT>;
-  static thread_local size_t configured = 0;
-  if (configured < smem) {
-    GLB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  GLB_ENSURE_SMEM(kern, smem);
   kern<<<dim3((unsigned)(L.N / MXV_ROWS)), dim3(MXV_THREADS), smem, stream>>>(tw, P);
   count_launch();
   GLB_CHECK_CUDA(cudaGetLastError());
@@ -363,11 +359,7 @@ int launch_mxv(const glb_linear& L, const void* x, void* y, int64_t M, const voi
   P.x = x; P.y = y; P.bias = bias; P.M = (int)M; P.N = (int)L.N; P.K = (int)L.K;
   const size_t smem = (size_t)MXV_STAGES * MXV_TILE + (size_t)MT * L.K * 2 + (size_t)8 * MT * MXV_ROWS * 4 + 2 * MXV_STAGES * 8 + 64;
   auto kern = gemv_mxfp4_kernel<BF16, MT>;
-  static thread_local size_t configured = 0;
-  if (configured < smem) {
-    GLB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  GLB_ENSURE_SMEM(kern, smem);
   kern<<<dim3((unsigned)(L.N / MXV_ROWS)), dim3(MXV_THREADS), smem, stream>>>(tw, P);
   count_launch();
   GLB_CHECK_CUDA(cudaGetLastError());
