@@ -333,6 +333,11 @@ struct T8Params {
   int csm;                 // channel_scale_mode 0..3
   int out_dtype;           // GLB_FP16 / BF16 / FP32 / INT32
   int tiles_m, tiles_n;
+  // split-K (SPLIT instantiation only): K is cut into `splits` ranges of kb_per_split stages, one work item each;
+  // raw accumulators are parked in ws_partial and summed in split order by the last warp to arrive (ws_counter)
+  int splits, kb_per_split;
+  int* ws_counter;         // [tile][lane quarter], zero on entry and on exit
+  uint32_t* ws_partial;    // [tile][split][128 feature rows][BT] raw int32 / fp32 bits
 };
 
 template <int BT> struct T8Smem {
@@ -343,7 +348,11 @@ template <int BT> struct T8Smem {
   static constexpr int TOTAL = STAGES * STAGE + 1024 + 1024;
 };
 
-template <bool IS_INT, int BT>
+// SPLIT = true: split-K flavour for 16 < M <= 128 (opt-in, GLB_A8_SPLITK=1; STATUS: written at the end of round 1 without
+// GPU time left to validate it).  The 128-feature tile gives only N / 128 CTAs (32 at N = 4096) for one token block, so a
+// small batch streams its weights through a fraction of the SMs; with split-K every (tile, K range) is a work item.
+// SPLIT = false compiles to exactly the kernel measured in round 1 (every difference is behind `if constexpr` / SPLIT ?:).
+template <bool IS_INT, int BT, bool SPLIT = false>
 __global__ void __launch_bounds__(T8_THREADS, 1)
 gemm_a8w8_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const T8Params P,
                     const uint32_t idesc) {
@@ -359,8 +368,8 @@ gemm_a8w8_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S::STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kblocks = P.K / T8_BK;
-  const int ntiles = P.tiles_m * P.tiles_n;
+  const int kblocks = SPLIT ? P.kb_per_split : P.K / T8_BK;
+  const int ntiles = P.tiles_m * P.tiles_n * (SPLIT ? P.splits : 1);
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_x);
@@ -379,13 +388,15 @@ gemm_a8w8_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const int tm = t % P.tiles_m, tn = t / P.tiles_m;
+        const int tt = SPLIT ? t / P.splits : t;
+        const int kb0 = SPLIT ? (t % P.splits) * P.kb_per_split : 0;
+        const int tm = tt % P.tiles_m, tn = tt / P.tiles_m;
         for (int kb = 0; kb < kblocks; ++kb) {
           ptx::mbar_wait(&empty[s], ph ^ 1);
           unsigned char* st = smem + s * S::STAGE;
           ptx::mbar_arrive_expect_tx(&full[s], S::X_BYTES + S::W_BYTES);
-          ptx::tma_load_2d(st, &tmap_x, &full[s], kb * T8_BK, tm * BT);
-          ptx::tma_load_2d(st + S::X_BYTES, &tmap_w, &full[s], kb * T8_BK, tn * TC_BM);
+          ptx::tma_load_2d(st, &tmap_x, &full[s], (kb0 + kb) * T8_BK, tm * BT);
+          ptx::tma_load_2d(st + S::X_BYTES, &tmap_w, &full[s], (kb0 + kb) * T8_BK, tn * TC_BM);
           if (++s == S::STAGES) { s = 0; ph ^= 1; }
         }
       }
@@ -423,7 +434,9 @@ gemm_a8w8_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     const int row = q4 * 32 + lane;
     int it = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-      const int tm = t % P.tiles_m, tn = t / P.tiles_m;
+      const int tt = SPLIT ? t / P.splits : t;
+      const int split = SPLIT ? t % P.splits : 0;
+      const int tm = tt % P.tiles_m, tn = tt / P.tiles_m;
       const int buf = it & 1;
       const uint32_t bph = (it >> 1) & 1;
       const int n = tn * TC_BM + row;
@@ -436,41 +449,113 @@ gemm_a8w8_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       }
       ptx::mbar_wait(&tfull[buf], bph);
       ptx::tc_fence_after_sync();
+      if constexpr (!SPLIT) {
 #pragma unroll 1
-      for (int c0 = 0; c0 < BT; c0 += 32) {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * BT + c0), r);
-        ptx::tmem_ld_wait();
+        for (int c0 = 0; c0 < BT; c0 += 32) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * BT + c0), r);
+          ptx::tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int m = tm * BT + c0 + j;
-          if (m < P.M) {
-            const int64_t oi = (int64_t)m * P.N + n;
-            if (IS_INT && P.out_dtype == GLB_INT32 && P.csm == 0 && !P.bias) {
-              reinterpret_cast<int32_t*>(P.y)[oi] = (int32_t)r[j];
-              continue;
-            }
-            float v = IS_INT ? (float)(int32_t)r[j] : __uint_as_float(r[j]);     // cvt.rn.f32.s32
-            if (P.csm == 1) v = __fmul_rn(v, sb);
-            else if (P.csm == 2) v = __fmul_rn(v, P.scales_x[m]);
-            else if (P.csm == 3) v = __fmul_rn(v, __fmul_rn(P.scales_x[m], sb));
-            if (P.out_dtype == GLB_FP16) {
-              if (P.bias) v = __half2float(__float2half_rn(v)) + bv;
-              reinterpret_cast<__half*>(P.y)[oi] = __float2half_rn(v);
-            } else if (P.out_dtype == GLB_BF16) {
-              if (P.bias) v = __bfloat162float(__float2bfloat16_rn(v)) + bv;
-              reinterpret_cast<__nv_bfloat16*>(P.y)[oi] = __float2bfloat16_rn(v);
-            } else if (P.out_dtype == GLB_FP32) {
-              reinterpret_cast<float*>(P.y)[oi] = v + bv;
-            } else {
-              reinterpret_cast<int32_t*>(P.y)[oi] = (int32_t)(v + bv);
+          for (int j = 0; j < 32; ++j) {
+            const int m = tm * BT + c0 + j;
+            if (m < P.M) {
+              const int64_t oi = (int64_t)m * P.N + n;
+              if (IS_INT && P.out_dtype == GLB_INT32 && P.csm == 0 && !P.bias) {
+                reinterpret_cast<int32_t*>(P.y)[oi] = (int32_t)r[j];
+                continue;
+              }
+              float v = IS_INT ? (float)(int32_t)r[j] : __uint_as_float(r[j]);     // cvt.rn.f32.s32
+              if (P.csm == 1) v = __fmul_rn(v, sb);
+              else if (P.csm == 2) v = __fmul_rn(v, P.scales_x[m]);
+              else if (P.csm == 3) v = __fmul_rn(v, __fmul_rn(P.scales_x[m], sb));
+              if (P.out_dtype == GLB_FP16) {
+                if (P.bias) v = __half2float(__float2half_rn(v)) + bv;
+                reinterpret_cast<__half*>(P.y)[oi] = __float2half_rn(v);
+              } else if (P.out_dtype == GLB_BF16) {
+                if (P.bias) v = __bfloat162float(__float2bfloat16_rn(v)) + bv;
+                reinterpret_cast<__nv_bfloat16*>(P.y)[oi] = __float2bfloat16_rn(v);
+              } else if (P.out_dtype == GLB_FP32) {
+                reinterpret_cast<float*>(P.y)[oi] = v + bv;
+              } else {
+                reinterpret_cast<int32_t*>(P.y)[oi] = (int32_t)(v + bv);
+              }
             }
           }
         }
+        ptx::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tempty[buf]);
+      } else {
+        // one output element from its summed raw accumulator: the arithmetic of the branch above
+        auto emit = [&](int m, uint32_t raw) {
+          const int64_t oi = (int64_t)m * P.N + n;
+          if (IS_INT && P.out_dtype == GLB_INT32 && P.csm == 0 && !P.bias) {
+            reinterpret_cast<int32_t*>(P.y)[oi] = (int32_t)raw;
+            return;
+          }
+          float v = IS_INT ? (float)(int32_t)raw : __uint_as_float(raw);
+          if (P.csm == 1) v = __fmul_rn(v, sb);
+          else if (P.csm == 2) v = __fmul_rn(v, P.scales_x[m]);
+          else if (P.csm == 3) v = __fmul_rn(v, __fmul_rn(P.scales_x[m], sb));
+          if (P.out_dtype == GLB_FP16) {
+            if (P.bias) v = __half2float(__float2half_rn(v)) + bv;
+            reinterpret_cast<__half*>(P.y)[oi] = __float2half_rn(v);
+          } else if (P.out_dtype == GLB_BF16) {
+            if (P.bias) v = __bfloat162float(__float2bfloat16_rn(v)) + bv;
+            reinterpret_cast<__nv_bfloat16*>(P.y)[oi] = __float2bfloat16_rn(v);
+          } else if (P.out_dtype == GLB_FP32) {
+            reinterpret_cast<float*>(P.y)[oi] = v + bv;
+          } else {
+            reinterpret_cast<int32_t*>(P.y)[oi] = (int32_t)(v + bv);
+          }
+        };
+        // park this K range's raw accumulators (128 B per thread and 32-column chunk), release the accumulator buffer,
+        // count in; the last of the `splits` warps serving this (tile, lane quarter) sums them in split order
+        const int mrem = min(BT, P.M - tm * BT);                          // live token columns of this tile
+        uint32_t* mine = P.ws_partial + (((size_t)tt * P.splits + split) * TC_BM + row) * (size_t)BT;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BT; c0 += 32) {
+          if (c0 >= mrem) break;
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * BT + c0), r);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<uint4*>(mine + c0 + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+        }
+        ptx::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tempty[buf]);
+        __threadfence();                                                  // partial visible device-wide before the count
+        __syncwarp();
+        int* ctr = P.ws_counter + tt * 4 + q4;
+        int old = 0;
+        if (lane == 0) old = atomicAdd(ctr, 1);
+        old = __shfl_sync(0xffffffffu, old, 0);
+        if (old == P.splits - 1) {
+          __threadfence();
+          const uint32_t* base = P.ws_partial + (((size_t)tt * P.splits) * TC_BM + row) * (size_t)BT;
+          const size_t sstride = (size_t)TC_BM * BT;                      // between consecutive splits
+#pragma unroll 1
+          for (int c0 = 0; c0 < BT; c0 += 4) {
+            if (c0 >= mrem) break;
+            int32_t ai[4] = {0, 0, 0, 0};
+            float af[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int sp = 0; sp < P.splits; ++sp) {                       // fixed order -> deterministic (int32: exact anyway)
+              const uint4 v = __ldcg(reinterpret_cast<const uint4*>(base + sp * sstride + c0));
+              const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if (IS_INT) ai[j] += (int32_t)w[j]; else af[j] += __uint_as_float(w[j]);
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (c0 + j < mrem) emit(tm * BT + c0 + j, IS_INT ? (uint32_t)ai[j] : __float_as_uint(af[j]));
+          }
+          if (lane == 0) *ctr = 0;                                        // self-cleaning: ready for the next launch
+        }
       }
-      ptx::tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tempty[buf]);
     }
   }
   ptx::tc_fence_before_sync();
@@ -503,8 +588,36 @@ int launch_tc(const glb_linear& L, const void* x, void* y, int64_t M, const void
 }
 
 
+// Work decomposition of the single-CTA A8W8 kernel (shared by the launch and by glb_workspace_bytes).  Split-K is
+// opt-in (GLB_A8_SPLITK=1) and only used for one token block (16 < M <= 128) when the feature tiles leave SMs idle.  The
+// counters share the fixed region at the start of the workspace with the pair kernel's (gl_gemm_tc2.cu).
+constexpr size_t T8_COUNTER_REGION = 64 * 1024;
+struct T8Plan {
+  int splits, kb_per_split;
+  size_t counter_bytes, partial_bytes;
+};
+bool a8_splitk_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GLB_A8_SPLITK"); v = (e && atoi(e) != 0) ? 1 : 0; }
+  return v == 1;
+}
+int t8_token_block(int64_t M) { return (M <= 32) ? 32 : ((M <= 64) ? 64 : ((M <= 128) ? 128 : 256)); }
+T8Plan t8_plan(const glb_linear& L, int64_t M, int BT) {
+  T8Plan p;
+  const int kblocks = (int)(L.K / T8_BK), tiles = (int)(L.N / TC_BM) * (int)((M + BT - 1) / BT);
+  p.splits = 1;
+  if (a8_splitk_enabled() && M > 16 && M <= 128 && (size_t)tiles * 4 * sizeof(int) <= T8_COUNTER_REGION)
+    for (int s = std::min(8, num_sms() / std::max(tiles, 1)); s >= 2; --s)
+      if (kblocks % s == 0 && kblocks / s >= 4) { p.splits = s; break; }
+  p.kb_per_split = kblocks / p.splits;
+  p.counter_bytes = (p.splits > 1) ? T8_COUNTER_REGION : 0;
+  p.partial_bytes = (p.splits > 1) ? (size_t)tiles * p.splits * TC_BM * BT * sizeof(uint32_t) : 0;
+  return p;
+}
+
 template <bool IS_INT, int BT>
-int launch_t8(const glb_linear& L, const void* x, const float* scales_x, void* y, int64_t M, const void* bias, cudaStream_t stream) {
+int launch_t8(const glb_linear& L, const void* x, const float* scales_x, void* y, int64_t M, void* workspace, size_t ws_bytes,
+              const void* bias, cudaStream_t stream) {
   using S = T8Smem<BT>;
   CUtensorMap tx, tw;
   int rc = make_tmap_2d(&tx, GLB_UINT8, x, (uint64_t)L.K, (uint64_t)M, (uint64_t)L.K, T8_BK, BT, 1);
@@ -517,11 +630,28 @@ int launch_t8(const glb_linear& L, const void* x, const float* scales_x, void* y
   P.scales_x = scales_x; P.y = y; P.bias = bias;
   P.M = (int)M; P.N = (int)L.N; P.K = (int)L.K; P.csm = L.channel_scale_mode; P.out_dtype = L.output_dtype;
   P.tiles_m = (int)((M + BT - 1) / BT); P.tiles_n = (int)(L.N / TC_BM);
+  P.splits = 1; P.kb_per_split = (int)(L.K / T8_BK); P.ws_counter = nullptr; P.ws_partial = nullptr;
   uint32_t idesc;
   if (IS_INT) idesc = ptx::make_idesc(2u, 1u, 1u, TC_BM, BT);                         // s32 accumulate, signed 8-bit A/B
   else {
     const uint32_t wf = (L.wq_dtype == GLB_FP8E5) ? 1u : 0u, xf = (act_storage_dtype(L.input_dtype) == GLB_FP8E5) ? 1u : 0u;
     idesc = ptx::make_idesc(1u, wf, xf, TC_BM, BT);                                    // f32 accumulate, e4m3 = 0 / e5m2 = 1
+  }
+  const T8Plan plan = t8_plan(L, M, BT);
+  if (plan.splits > 1) {
+    GLB_REQUIRE(workspace != nullptr && ws_bytes >= plan.counter_bytes + plan.partial_bytes, GLB_ERR_WORKSPACE,
+                "A8W8 split-K needs %zu bytes of (zero-initialised) workspace, got %zu", plan.counter_bytes + plan.partial_bytes, ws_bytes);
+    GLB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, GLB_ERR_INVALID, "workspace must be 16-byte aligned");
+    P.splits = plan.splits; P.kb_per_split = plan.kb_per_split;
+    P.ws_counter = reinterpret_cast<int*>(workspace);
+    P.ws_partial = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(workspace) + plan.counter_bytes);
+    auto kern_split = gemm_a8w8_tc_kernel<IS_INT, BT, true>;
+    GLB_ENSURE_SMEM(kern_split, S::TOTAL);
+    const int grid_split = std::min(num_sms(), P.tiles_m * P.tiles_n * P.splits);
+    kern_split<<<grid_split, T8_THREADS, S::TOTAL, stream>>>(tx, tw, P, idesc);
+    count_launch();
+    GLB_CHECK_CUDA(cudaGetLastError());
+    return GLB_OK;
   }
   auto kern = gemm_a8w8_tc_kernel<IS_INT, BT>;
   GLB_ENSURE_SMEM(kern, S::TOTAL);
@@ -586,6 +716,11 @@ static bool use_pair_kernel(const glb_linear& L, int64_t M) {
 
 size_t gemm_tc_workspace(const glb_linear& L, int64_t M) {
   if (!gemm_tc_supported(L, M)) return 0;
+  if (a8w8_tc_supported(L, M)) {
+    if (M > 128) return 0;                                  // pair kernel or the 256-token block: no split-K
+    const T8Plan p = t8_plan(L, M, t8_token_block(M));
+    return p.counter_bytes + p.partial_bytes;
+  }
   return use_pair_kernel(L, M) ? gemm_tc2_workspace(L, M) : 0;
 }
 
@@ -601,7 +736,8 @@ int launch_gemm_tc(const glb_linear& L, const void* x, const float* scales_x, vo
     }
     const bool is_int = (act_storage_dtype(L.input_dtype) == GLB_INT8);
     set_kernel_name(is_int ? "gemm_a8w8_int8_tcgen05" : "gemm_a8w8_fp8_tcgen05");
-#define GLB_T8(BT) (is_int ? launch_t8<true, BT>(L, x, scales_x, y, M, bias, stream) : launch_t8<false, BT>(L, x, scales_x, y, M, bias, stream))
+#define GLB_T8(BT) (is_int ? launch_t8<true, BT>(L, x, scales_x, y, M, workspace, ws_bytes, bias, stream) \
+                           : launch_t8<false, BT>(L, x, scales_x, y, M, workspace, ws_bytes, bias, stream))
     if (M <= 32) return GLB_T8(32);
     if (M <= 64) return GLB_T8(64);
     if (M <= 128) return GLB_T8(128);

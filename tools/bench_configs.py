@@ -141,7 +141,7 @@ def c4(quick):
     W = (torch.randn(N, K, generator=g, device=DEV) / 10).half()
     for name, proc in (("C4 A8W8 fp8 dynamic", A8W8_FP8_dynamic), ("C4 A8W8 int8 dynamic", A8W8_INT8_dynamic)):
         layer = proc(device=DEV, dtype=torch.float16).from_weights(W.clone())
-        for M in ([1, 2, 4, 8, 16, 32] if "--small" in sys.argv else ([1, 64, 4096] if quick else [1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096])):
+        for M in ([32, 64, 128] if "--mid" in sys.argv else [1, 2, 4, 8, 16, 32] if "--small" in sys.argv else ([1, 64, 4096] if quick else [1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096])):
             x = (torch.randn(M, K, generator=g, device=DEV) / 10).half()
             t = timed(lambda: layer(x), 5 if quick else 20)
             # W K*N + 4N, x_q M*K + 4M, y 2*M*N, plus the quantiser pass (2*M*K read, M*K write)
