@@ -144,3 +144,44 @@ def test_workspace_plan_without_gpu():
     assert lib.glb_workspace_bytes(ctypes.byref(other), 32, -1) == 65536 + 8 * 8 * 2 * 128 * 64 * 4
     wide = _a16w4_desc(16384, 4096)
     assert lib.glb_workspace_bytes(ctypes.byref(wide), 64, -1) == 0      # 64 tiles already fill the 74 SM pairs
+
+
+def _mx_desc(N, K, input_dtype, nbits, gs, csm, scales_dtype):
+    """A descriptor shaped like an MX layer with dynamically quantised activations (fake addresses, never dereferenced)."""
+    d = _cabi.GlbLinear()
+    eps = 2 if nbits == 4 else 1
+    d.W_q = 0x7f0000000000; d.wq_rows, d.wq_cols = K // eps, N; d.wq_stride0, d.wq_stride1 = 1, K // eps
+    d.wq_dtype = (DType.UINT8 if nbits == 4 else DType.FP8).value
+    d.scales = 0x7f0100000000; d.scales_numel = (K // gs) * N; d.s_stride0, d.s_stride1 = 1, N
+    d.scales_dtype = scales_dtype
+    d.zeros = None; d.zeros_numel = 0
+    d.zeros_dtype = DType.INT32.value
+    d.K, d.N = K, N
+    (d.scaled_activations, d.W_nbits, d.group_size, d.unpack_mask, d.elements_per_sample, d.input_dtype, d.output_dtype,
+     d.acc_dtype, d.meta_dtype, d.channel_scale_mode, d.W_group_mode, d.data_contiguous) = (
+        1, nbits, gs, 2 ** nbits - 1, eps, input_dtype, DType.BF16.value, DType.FP32.value, scales_dtype, csm, 0, 0)
+    return d
+
+
+def test_mx_dynamic_descriptor_validation_without_gpu():
+    """glb_matmul validates before it touches the device: which (input dtype, channel_scale_mode, group size) an MX
+    layer may carry (helper.py:660-945) and that modes 2 / 4 come with activation scales."""
+    lib = _cabi.load()
+    fake = 0x7f0300000000
+    u8 = DType.UINT8.value
+
+    def call(d, scales_x):
+        return lib.glb_matmul(ctypes.byref(d), fake, scales_x, fake, 1, -1, None, 0, None, None), lib.glb_last_error()
+
+    # micro-scaled activations without their scales: invalid argument (-1)
+    rc, msg = call(_mx_desc(256, 512, DType.MXFP8.value, 8, 32, 4, u8), None)
+    assert rc == -1 and b"activation scales" in msg, (rc, msg)
+    rc, msg = call(_mx_desc(256, 512, DType.MXFP8.value, 4, 32, 2, u8), None)
+    assert rc == -1 and b"activation scales" in msg, (rc, msg)
+    # combinations the reference cannot produce: unsupported (-2)
+    for d in (_mx_desc(256, 512, DType.MXFP4.value, 4, 32, 2, u8),          # per-token post-scale exists for MXFP8 only
+              _mx_desc(256, 512, DType.MXBF16.value, 4, 32, 4, u8),         # weight-only MX has no activation scales
+              _mx_desc(256, 512, DType.MXFP4.value, 4, 16, 4, u8),          # MXFP4 groups are 32 wide
+              _mx_desc(256, 512, DType.NVFP4.value, 4, 32, 4, DType.FP8.value)):   # NVFP4 groups are 16 wide
+        rc, msg = call(d, fake)
+        assert rc == -2, (rc, msg)
