@@ -539,7 +539,8 @@ def main():
         old = json.load(open(mpath))
     old.update(MANIFEST)
     old["_reference"] = {"version": gemlite.__version__, "triton": triton.__version__, "torch": torch.__version__,
-                         "mode": "TRITON_INTERPRET=1 (CPU), stub driver, unmodified reference sources"}
+                         "mode": "TRITON_INTERPRET=1 (CPU), stub driver, unmodified reference sources; interpreter float "
+                                 "down-casts replaced by RNE / satfinite, numpy stand-ins for libdevice.round and tl.dot_scaled"}
     json.dump(old, open(mpath, "w"), indent=1, sort_keys=True)
 
 
