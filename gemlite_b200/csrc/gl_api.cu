@@ -19,6 +19,7 @@ static thread_local char tl_error[512] = "";
 static thread_local const char* tl_kernel = "";
 static std::atomic<uint64_t> g_launches{0};
 std::atomic<int> g_pdl_enabled{1};
+std::atomic<uint64_t> g_chained_launches{0};
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -196,6 +197,7 @@ extern "C" int glb_version(void) { return GLB_ABI_VERSION; }
 extern "C" const char* glb_last_error(void) { return tl_error; }
 extern "C" const char* glb_last_kernel(void) { return tl_kernel; }
 extern "C" uint64_t glb_launch_count(void) { return g_launches.load(); }
+extern "C" uint64_t glb_chained_launch_count(void) { return g_chained_launches.load(); }
 extern "C" void glb_set_pdl(int enabled) { g_pdl_enabled.store(enabled ? 1 : 0); }
 extern "C" int glb_get_pdl(void) { return g_pdl_enabled.load(); }
 extern "C" int glb_debug_timeline(unsigned long long* out, int max_words) { return debug_read_timeline(out, max_words); }
@@ -212,8 +214,13 @@ extern "C" unsigned long long glb_stream_capture_id(void* stream_) {
 
 extern "C" size_t glb_workspace_bytes(const glb_linear* L, int64_t M, int matmul_type) {
   if (!L || M <= 0) return 0;
-  if (matmul_type == GLB_MM_AUTO) matmul_type = pick_matmul_type(*L, M);
-  if (gemm_tc_supported(*L, M)) return gemm_tc_workspace(*L, M);
+  const bool was_auto = (matmul_type == GLB_MM_AUTO);
+  if (was_auto) matmul_type = pick_matmul_type(*L, M);
+  // same routing as glb_matmul: the decode kernel first (its chained hand-off keeps arrival counters in the workspace)
+  const bool gemv_name = (matmul_type <= GLB_MM_GEMV_SPLITK);
+  const bool can_gemv = gemv_supported(*L, M), can_tc = gemm_tc_supported(*L, M);
+  if (can_gemv && (gemv_name || (was_auto && M <= 16) || !can_tc)) return gemv_workspace(*L, M);
+  if (can_tc) return gemm_tc_workspace(*L, M);
   return 0;
 }
 
@@ -244,7 +251,7 @@ extern "C" int glb_matmul(const glb_linear* L, const void* x, const void* scales
   if (matmul_type != GLB_MM_GEMM && gemv_a8_enabled() && gemv_a8_supported(*L, M))
     return launch_gemv_a8(*L, x, sx, y, M, bias, stream);
   const bool prefer_gemv = can_gemv && (gemv_name || (was_auto && M <= 16) || !can_tc);
-  if (prefer_gemv) return launch_gemv(*L, x, sx, y, M, bias, stream);
+  if (prefer_gemv) return launch_gemv(*L, x, sx, y, M, bias, workspace, workspace_bytes, stream);
   if (can_tc) {
     const size_t need = gemm_tc_workspace(*L, M);
     GLB_REQUIRE(need == 0 || (workspace && workspace_bytes >= need), GLB_ERR_WORKSPACE,

@@ -17,6 +17,7 @@ void set_error(const char* fmt, ...);
 void set_kernel_name(const char* name);
 void count_launch();
 extern std::atomic<int> g_pdl_enabled;
+extern std::atomic<uint64_t> g_chained_launches;
 
 #define GLB_CHECK_CUDA(expr)                                                        \
   do {                                                                              \
@@ -72,7 +73,8 @@ int launch_generic(const glb_linear& L, const void* x, const float* scales_x, vo
                    const void* bias, cudaStream_t stream);
 bool gemv_supported(const glb_linear& L, int64_t M);
 int launch_gemv(const glb_linear& L, const void* x, const float* scales_x, void* y, int64_t M,
-                const void* bias, cudaStream_t stream);
+                const void* bias, void* workspace, size_t ws_bytes, cudaStream_t stream);
+size_t gemv_workspace(const glb_linear& L, int64_t M);
 int debug_read_timeline(unsigned long long* out, int max_words);
 bool gemm_tc_supported(const glb_linear& L, int64_t M);
 size_t gemm_tc_workspace(const glb_linear& L, int64_t M);

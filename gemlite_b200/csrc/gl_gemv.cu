@@ -26,6 +26,8 @@
 // The same kernel handles 1 <= M <= 16 rows of x (rows of the MMA A operand).
 #include <cuda.h>
 #include <stdlib.h>
+#include <mutex>
+#include <unordered_map>
 
 #include "gl_common.cuh"
 #include "gl_ptx.cuh"
@@ -108,6 +110,22 @@ template <bool BF16, bool FAST> __device__ __forceinline__ void nibbles_to_f16x2
       __nv_bfloat162 r = __hsub2(*reinterpret_cast<const __nv_bfloat162*>(&v), k128);
       h[i] = *reinterpret_cast<uint32_t*>(&r);
     }
+  }
+}
+
+
+// Same unpack with the one shift per word issued as mul.hi (FMA pipe) instead of SHF (ALU pipe, which the four
+// LOP3 already saturate: both pipes issue one warp instruction every two cycles per scheduler).
+template <bool BF16, bool FAST> __device__ __forceinline__ void nibbles_to_f16x2_m1(uint32_t q, uint32_t (&h)[4]) {
+  if (!BF16 && FAST) {
+    uint32_t t;
+    asm("mul.hi.u32 %0, %1, 0x01000000;" : "=r"(t) : "r"(q));     // q >> 8
+    h[0] = lop3_and_or(q, 0x000F000Fu, 0x64006400u);
+    h[1] = lop3_and_or(q, 0x00F000F0u, 0x64006400u);
+    h[2] = lop3_and_or(t, 0x000F000Fu, 0x64006400u);
+    h[3] = lop3_and_or(t, 0x00F000F0u, 0x64006400u);
+  } else {
+    nibbles_to_f16x2<BF16, FAST>(q, h);
   }
 }
 
@@ -814,6 +832,350 @@ int launch_w4_tma(const glb_linear& L, const GemvParams& P0, int late_trigger, c
   return GLB_OK;
 }
 
+
+// =================================================================================================
+// M == 1 decode kernel, round 2 ("v7"): same slab / TMA / swizzle scheme as gemv_w4_tma_kernel, rebuilt around the
+// two things the round-1 timeline showed on the critical path of a CHAIN of dependent layers
+// (profiles/decode_timeline_v52_r1.txt): the kernel-boundary hand-off (1.0-1.25 us) and a post-wait path of
+// ~2.3 us (block-wide x staging + barrier 0.85, main loop 1.45 at ~215 issued instructions per group and warp).
+//   * hand-off: when the library can PROVE during stream capture that this launch's x is the y of the decode launch
+//     captured right before it (cudaStreamGetCaptureInfo: the stream's only dependency is that kernel node), the
+//     consumer does not wait for kernel completion (griddepcontrol.wait) but for an arrival counter: every producer
+//     CTA stores its 32 outputs, fences, and adds 1 to a flag word; one thread per consumer CTA spins on
+//     ld.acquire.gpu until all producer CTAs have arrived.  griddepcontrol.wait is still executed before the kernel
+//     exits, so completion stays transitive along the stream.  Eager launches (and anything the library cannot prove
+//     adjacent) use griddepcontrol.wait as before.
+//   * x staging is per warp: a warp only ever touches the x words of its own groups, so it loads them itself
+//     (one 16-byte word per lane and group), permutes / pre-scales them in registers, reduces the group sums with
+//     shuffles and parks the words in its private rows of the x buffer -- no block barrier between the hand-off and
+//     the first HMMA.
+//   * main loop: two accumulator chains per group, the nibble shift on the FMA pipe (mul.hi), x fragments only in
+//     the 4 lanes of token 0, scale / zero vectors read once per group; all mbarrier waits are taken BEFORE the
+//     hand-off (in a chain the copies landed long ago), so the loop holds no polls.
+// =================================================================================================
+struct GemvM1Params {
+  const void* x; void* y; const void* bias;
+  int K, N, group_size, mode;
+  unsigned int* flag_in;     // producer's arrival counter (null: griddepcontrol.wait)
+  unsigned int expect;       // producer CTAs
+  unsigned int* flag_out;    // this launch's arrival counter (null: do not publish)
+  int trigger;               // dependents are signalled 0: at kernel start, 2: right after the hand-off
+  int debug;                 // bit 0: skip main loop, bit 1: skip weight copies (timing experiments only)
+};
+
+constexpr int M1_NW = 16;
+constexpr int M1_MAXGPW = 8;     // groups per warp (K / group_size / 16)
+
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 ld_relaxed_gpu_v4(const void* p) {
+  uint4 r;
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  return r;
+}
+
+template <bool BF16, int RPG, bool FAST, int GPW>
+__global__ void __launch_bounds__(M1_NW * 32, 2)
+gemv_w4_m1_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_s,
+                  const __grid_constant__ CUtensorMap tmap_z, const GemvM1Params P) {
+  static_assert(!(BF16 && FAST), "the offset-carrying unpack needs fp16's 10-bit mantissa");
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  constexpr int rpg = RPG * 4;                     // packed rows (= 8-element x words) per group
+  const int K = P.K, N = P.N;
+  const int G = K / P.group_size, rows = K >> 3;
+  const int col0 = blockIdx.x * GV_COLS;
+  const int nch = (rows % (GT_NCH * rpg) == 0 && rows / GT_NCH >= 8) ? GT_NCH : 1;
+  const int chunk_rows = rows / nch;
+
+  unsigned char* wbuf = smem_raw;                                        // rows x 128 B, TMA 128B swizzle
+  if ((ptx::smem_u32(smem_raw) & 1023u) != 0u) __trap();
+  const size_t meta_bytes = ((size_t)G * 64 + 127) & ~(size_t)127;
+  unsigned char* sbuf = wbuf + (size_t)rows * 128;                       // G x 64 B
+  unsigned char* zbuf = sbuf + meta_bytes;
+  unsigned char* xs = zbuf + meta_bytes;                                 // rows x 16 B: permuted x words (warp-private rows)
+  float* red = reinterpret_cast<float*>(xs + (size_t)rows * 16);         // [M1_NW][32]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(red + M1_NW * GV_COLS);   // [GT_NCH] weights, [1] metadata, [1] hand-off result
+  volatile unsigned int* okw = reinterpret_cast<volatile unsigned int*>(&bars[GT_NCH + 1]);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g8 = lane >> 2, t4 = lane & 3;
+
+  // ---- 1. everything that does not depend on the previous layer ----
+  if (threadIdx.x == 0) {
+    if (P.flag_out) {                      // fresh counter for this launch; visible before any dependent can start
+      *reinterpret_cast<volatile unsigned int*>(P.flag_out) = 0u;
+      __threadfence();
+    }
+    ptx::prefetch_tmap(&tmap_w);
+    ptx::prefetch_tmap(&tmap_s);
+    for (int c = 0; c <= GT_NCH; ++c) ptx::mbar_init(&bars[c], 1);
+    ptx::fence_mbar_init();
+    const uint32_t mb = (uint32_t)G * 64u * (P.mode != 2 ? 2u : 1u);
+    ptx::mbar_arrive_expect_tx(&bars[GT_NCH], mb);
+    ptx::tma_load_2d(sbuf, &tmap_s, &bars[GT_NCH], col0, 0);
+    if (P.mode != 2) ptx::tma_load_2d(zbuf, &tmap_z, &bars[GT_NCH], col0, 0);
+    for (int c = 0; c < ((P.debug & 2) ? 0 : nch); ++c) {
+      ptx::mbar_arrive_expect_tx(&bars[c], (uint32_t)chunk_rows * 128u);
+      ptx::tma_load_2d(wbuf + (size_t)c * chunk_rows * 128, &tmap_w, &bars[c], col0, c * chunk_rows);
+    }
+  }
+  if (P.trigger == 0) pdl_launch_dependents();
+  __syncthreads();                                   // barrier initialisation visible to every thread
+  ptx::mbar_wait(&bars[GT_NCH], 0);
+  if (!(P.debug & 2))
+    for (int c = 0; c < nch; ++c) ptx::mbar_wait(&bars[c], 0);
+
+  // ---- 2. hand-off: the previous layer's y is this layer's x ----
+  bool flagged = false;
+  if (P.flag_in) {
+    if (threadIdx.x == 0) {
+      const unsigned long long t0 = gtimer();
+      unsigned int ok = 0, spins = 0;
+      while (true) {
+        if (ld_acquire_gpu(P.flag_in) >= P.expect) { ok = 1; break; }
+        if ((++spins & 63u) == 0u && gtimer() - t0 > 200000ull) break;   // 200 us: a lost arrival only costs the fallback below
+      }
+      *okw = ok;
+    }
+    __syncthreads();
+    flagged = (*okw != 0u);
+  }
+  if (!flagged) pdl_wait_prior_grids();
+  if (P.trigger == 2) pdl_launch_dependents();
+
+  // ---- 3. this warp's x words: load, permute, pre-scale, group sums ----
+  float sxv[GPW], offv[GPW];
+  {
+    const uint16_t* xg = reinterpret_cast<const uint16_t*>(P.x);
+    uint4 v[GPW];
+#pragma unroll
+    for (int gi = 0; gi < GPW; ++gi) {
+      const int gl = warp + M1_NW * gi;
+      v[gi] = make_uint4(0u, 0u, 0u, 0u);
+      if (gl < G && lane < rpg) v[gi] = ld_relaxed_gpu_v4(xg + ((size_t)gl * rpg + lane) * 8);
+    }
+#pragma unroll
+    for (int gi = 0; gi < GPW; ++gi) {
+      const int gl = warp + M1_NW * gi;
+      uint4 o;
+      o.x = __byte_perm(v[gi].x, v[gi].z, 0x5410);   // (k0,k4)
+      o.y = __byte_perm(v[gi].x, v[gi].z, 0x7632);   // (k1,k5)
+      o.z = __byte_perm(v[gi].y, v[gi].w, 0x5410);   // (k2,k6)
+      o.w = __byte_perm(v[gi].y, v[gi].w, 0x7632);   // (k3,k7)
+      if (FAST) {
+        const __half2 k16th = __half2half2(__ushort_as_half((unsigned short)0x2C00));
+        __half2 a = __hmul2(*reinterpret_cast<__half2*>(&o.y), k16th), b2 = __hmul2(*reinterpret_cast<__half2*>(&o.w), k16th);
+        o.y = *reinterpret_cast<uint32_t*>(&a); o.w = *reinterpret_cast<uint32_t*>(&b2);
+      }
+      if (gl < G && lane < rpg) *reinterpret_cast<uint4*>(xs + ((size_t)gl * rpg + lane) * 16) = o;
+      float slo = cvt_meta<BF16>((uint16_t)(o.x & 0xffffu)) + cvt_meta<BF16>((uint16_t)(o.x >> 16)) +
+                  cvt_meta<BF16>((uint16_t)(o.z & 0xffffu)) + cvt_meta<BF16>((uint16_t)(o.z >> 16));
+      float shi = cvt_meta<BF16>((uint16_t)(o.y & 0xffffu)) + cvt_meta<BF16>((uint16_t)(o.y >> 16)) +
+                  cvt_meta<BF16>((uint16_t)(o.w & 0xffffu)) + cvt_meta<BF16>((uint16_t)(o.w >> 16));
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {       // lanes >= rpg carry zeros
+        slo += __shfl_xor_sync(0xffffffffu, slo, off);
+        shi += __shfl_xor_sync(0xffffffffu, shi, off);
+      }
+      sxv[gi] = FAST ? fmaf(16.f, shi, slo) : (slo + shi);      // sum_k x_k
+      offv[gi] = FAST ? 1024.f * (slo + shi) : 0.f;             // 1024 * sum_k x'_k
+    }
+  }
+  __syncwarp();
+
+  // ---- 4. main loop ----
+  float out[4] = {0.f, 0.f, 0.f, 0.f};
+  const bool tok_ok = (g8 == 0);
+  const unsigned char* xb = xs + (2 * t4) * 16;
+  const unsigned char* wl = wbuf + (2 * t4) * 128;
+  const int sw0 = (g8 ^ (2 * t4)) << 4, sw1 = (g8 ^ (2 * t4 + 1)) << 4;
+#pragma unroll
+  for (int gi = 0; gi < GPW; ++gi) {
+    const int gl = warp + M1_NW * gi;
+    if (gl >= ((P.debug & 1) ? 0 : G)) break;
+    float dacc[2][4];
+#pragma unroll
+    for (int pr = 0; pr < 2; ++pr) dacc[pr][0] = dacc[pr][1] = dacc[pr][2] = dacc[pr][3] = 0.f;
+#pragma unroll
+    for (int r = 0; r < RPG; ++r) {
+      const int blk = gl * (RPG / 2) + (r >> 1), a = r & 1;
+      const uint4 q = *reinterpret_cast<const uint4*>(wl + (size_t)blk * 1024 + a * 128 + (a ? sw1 : sw0));
+      uint4 xv = make_uint4(0u, 0u, 0u, 0u);
+      if (tok_ok) xv = *reinterpret_cast<const uint4*>(xb + (size_t)blk * 128 + a * 16);
+      uint32_t ha[4], hb[4];
+      nibbles_to_f16x2_m1<BF16, FAST>(q.x, ha);
+      nibbles_to_f16x2_m1<BF16, FAST>(q.y, hb);
+      {
+        const uint32_t a0[4] = {ha[0], hb[0], ha[1], hb[1]}, a1[4] = {ha[2], hb[2], ha[3], hb[3]};
+        mma16816<BF16>(dacc[0], a0, xv.x, xv.y);
+        mma16816<BF16>(dacc[0], a1, xv.z, xv.w);
+      }
+      nibbles_to_f16x2_m1<BF16, FAST>(q.z, ha);
+      nibbles_to_f16x2_m1<BF16, FAST>(q.w, hb);
+      {
+        const uint32_t a0[4] = {ha[0], hb[0], ha[1], hb[1]}, a1[4] = {ha[2], hb[2], ha[3], hb[3]};
+        mma16816<BF16>(dacc[1], a0, xv.x, xv.y);
+        mma16816<BF16>(dacc[1], a1, xv.z, xv.w);
+      }
+    }
+    const uint2 sw = *reinterpret_cast<const uint2*>(sbuf + (size_t)gl * 64 + g8 * 8);
+    uint2 zw = make_uint2(0u, 0u);
+    if (P.mode != 2) zw = *reinterpret_cast<const uint2*>(zbuf + (size_t)gl * 64 + g8 * 8);
+    const uint32_t swa[2] = {sw.x, sw.y}, zwa[2] = {zw.x, zw.y};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float sc = cvt_meta<BF16>((uint16_t)((c & 1) ? (swa[c >> 1] >> 16) : (swa[c >> 1] & 0xffffu)));
+      float zc = cvt_meta<BF16>((uint16_t)((c & 1) ? (zwa[c >> 1] >> 16) : (zwa[c >> 1] & 0xffffu)));
+      if (P.mode == 3) zc = -zc * sc;
+      // c0,c2 -> rows 0-7 of the tile (d0); c1,c3 -> rows 8-15 (d2); token 0 = accumulator column 0 (lanes t4 == 0)
+      const float d = dacc[c >> 1][(c & 1) * 2];
+      out[c] = fmaf(sc, d - offv[gi], fmaf(zc, sxv[gi], out[c]));
+    }
+  }
+
+  // ---- 5. cross-warp reduction, bias, store, publish ----
+  if (t4 == 0) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) red[warp * GV_COLS + 4 * g8 + c] = out[c];
+  }
+  __syncthreads();
+  if (threadIdx.x < GV_COLS) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < M1_NW; ++w) v += red[w * GV_COLS + threadIdx.x];
+    if (P.bias) v = rnd_out<BF16>(v) + cvt_meta<BF16>(reinterpret_cast<const uint16_t*>(P.bias)[col0 + threadIdx.x]);
+    st_out<BF16>(P.y, (int64_t)col0 + threadIdx.x, v);
+    if (P.flag_out) {
+      __threadfence();                                // each lane's store is performed gpu-wide ...
+      __syncwarp();
+      if (threadIdx.x == 0) asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(P.flag_out) : "memory");   // ... before the arrival
+    }
+  }
+  if (flagged) pdl_wait_prior_grids();                // kernel completion stays transitive along the stream
+}
+
+template <int GPW> size_t gemv_m1_smem_bytes(int K, int group_size) {
+  const int G = K / group_size;
+  const size_t meta = ((size_t)G * 64 + 127) & ~(size_t)127;
+  return (size_t)(K / 8) * 128 + 2 * meta + (size_t)(K / 8) * 16 + (size_t)M1_NW * GV_COLS * 4 + (GT_NCH + 2) * 8 + 64;
+}
+
+bool gemv_m1_ok(const GemvParams& P) {
+  if (P.M != 1) return false;
+  const int G = P.K / P.group_size, rows = P.K / 8, rpg = P.group_size / 8;
+  if (rows * 128 > 64 * 1024 || rows < 32) return false;
+  if (G > M1_NW * M1_MAXGPW || G > 256) return false;
+  const int nch = (rows % (GT_NCH * rpg) == 0 && rows / GT_NCH >= 8) ? GT_NCH : 1;
+  if (rows / nch > 256 || (rows / nch) % 8 != 0) return false;
+  if (rpg % 8 != 0 || rpg > 32) return false;           // swizzled 8-row blocks must not straddle groups
+  return true;
+}
+
+// ---- per-stream chain tracking: which decode launch was captured last, and where it publishes ----
+constexpr int M1_SLOTS = 16;
+constexpr size_t M1_SLOT_BYTES = 128;
+constexpr size_t M1_FLAG_OFFSET = 64 * 1024 - M1_SLOTS * M1_SLOT_BYTES;   // tail of the workspace's counter region
+struct ChainState {
+  unsigned long long capture_id = 0;
+  cudaGraphNode_t node = nullptr;
+  const void* y = nullptr;
+  int N = 0, slot = -1;
+  unsigned int grid = 0;
+  const void* ws = nullptr;
+};
+std::mutex g_chain_mu;
+std::unordered_map<cudaStream_t, ChainState> g_chain;
+int chain_mode() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GLB_GEMV_FLAGS"); v = e ? atoi(e) : 1; }
+  return v;
+}
+
+template <bool BF16, int RPG, bool FAST, int GPW>
+int launch_w4_m1(const glb_linear& L, const GemvParams& P0, void* workspace, size_t ws_bytes, cudaStream_t stream) {
+  const int rows = P0.K / 8, G = P0.K / P0.group_size;
+  constexpr int rpg = RPG * 4;
+  const int nch = (rows % (GT_NCH * rpg) == 0 && rows / GT_NCH >= 8) ? GT_NCH : 1;
+  CUtensorMap tw, ts, tz;
+  int rc = make_tmap_2d(&tw, GLB_INT32, L.W_q, (uint64_t)L.N, (uint64_t)rows, (uint64_t)L.N * 4, GV_COLS, rows / nch, 1);
+  if (rc != GLB_OK) return rc;
+  rc = make_tmap_2d(&ts, GLB_FP16, L.scales, (uint64_t)L.N, (uint64_t)G, (uint64_t)L.N * 2, GV_COLS, G, 0);
+  if (rc != GLB_OK) return rc;
+  rc = make_tmap_2d(&tz, GLB_FP16, (P0.mode != 2) ? L.zeros : L.scales, (uint64_t)L.N, (uint64_t)G, (uint64_t)L.N * 2, GV_COLS, G, 0);
+  if (rc != GLB_OK) return rc;
+  GemvM1Params P;
+  P.x = P0.x; P.y = P0.y; P.bias = P0.bias; P.K = P0.K; P.N = P0.N; P.group_size = P0.group_size; P.mode = P0.mode;
+  P.flag_in = nullptr; P.expect = 0; P.flag_out = nullptr;
+  {
+    static int dbg = -1, trig = -1;
+    if (dbg < 0) { const char* e = getenv("GLB_GEMV_DEBUG"); dbg = e ? atoi(e) : 0; }
+    if (trig < 0) { const char* e = getenv("GLB_GEMV_TRIGGER"); trig = e ? atoi(e) : 2; }
+    P.debug = dbg; P.trigger = trig;
+  }
+  const unsigned int grid = (unsigned)(P0.N / GV_COLS);
+  // Flag hand-off only inside a stream capture, where adjacency can be proven from the capture's dependency set.
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  unsigned long long cap_id = 0;
+  const cudaGraphNode_t* deps = nullptr;
+  size_t ndeps = 0;
+  bool capturing = false;
+  const bool pdl = g_pdl_enabled.load() != 0;
+  if (chain_mode() && pdl && workspace && ws_bytes >= 64 * 1024 &&
+      cudaStreamGetCaptureInfo_v3(stream, &st, &cap_id, nullptr, &deps, nullptr, &ndeps) == cudaSuccess)
+    capturing = (st == cudaStreamCaptureStatusActive);
+  else
+    cudaGetLastError();
+  int slot = -1;
+  if (capturing) {
+    std::lock_guard<std::mutex> lk(g_chain_mu);
+    ChainState& cs = g_chain[stream];
+    unsigned int* flags = reinterpret_cast<unsigned int*>(reinterpret_cast<unsigned char*>(workspace) + M1_FLAG_OFFSET);
+    if (cs.capture_id == cap_id && cs.node != nullptr && ndeps == 1 && deps[0] == cs.node && cs.y == P0.x &&
+        cs.N == P0.K && cs.ws == workspace && cs.slot >= 0) {
+      P.flag_in = flags + (size_t)cs.slot * (M1_SLOT_BYTES / 4);
+      P.expect = cs.grid;
+    }
+    slot = (cs.capture_id == cap_id) ? (cs.slot + 1) % M1_SLOTS : 0;
+    P.flag_out = flags + (size_t)slot * (M1_SLOT_BYTES / 4);
+  }
+  const size_t smem = gemv_m1_smem_bytes<GPW>(P0.K, P0.group_size);
+  auto kern = gemv_w4_m1_kernel<BF16, RPG, FAST, GPW>;
+  if (smem > 48 * 1024) GLB_ENSURE_SMEM(kern, smem);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(M1_NW * 32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  int na = 0;
+  if (pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  GLB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tw, ts, tz, P));
+  count_launch();
+  if (P.flag_in) g_chained_launches.fetch_add(1, std::memory_order_relaxed);
+  if (capturing) {
+    // the node this launch became = the stream's only dependency now
+    std::lock_guard<std::mutex> lk(g_chain_mu);
+    ChainState& cs = g_chain[stream];
+    cs = ChainState();
+    if (cudaStreamGetCaptureInfo_v3(stream, &st, &cap_id, nullptr, &deps, nullptr, &ndeps) == cudaSuccess &&
+        st == cudaStreamCaptureStatusActive && ndeps == 1) {
+      cs.capture_id = cap_id; cs.node = deps[0]; cs.y = P0.y; cs.N = P0.N; cs.slot = slot; cs.grid = grid; cs.ws = workspace;
+    } else {
+      cudaGetLastError();
+    }
+  }
+  return GLB_OK;
+}
+
 // Kernel flavour (GLB_GEMV_VARIANT, read once): 3 = register prefetch + 2-CTA cluster; 4 = TMA + 2-CTA cluster,
 // 256 threads (default); 41 = same with the dependent-launch trigger after the main loop; 5 / 51 = TMA, one
 // 512-thread CTA per slab over the full K (exactly two CTAs per SM), early / late trigger; 6 / 62 = TMA, one
@@ -822,7 +1184,7 @@ int gemv_variant() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("GLB_GEMV_VARIANT");
-    v = e ? atoi(e) : 52;
+    v = e ? atoi(e) : 7;
   }
   return v;
 }
@@ -842,7 +1204,7 @@ bool gemv_tma_ok(const GemvParams& P, int ksplit) {
 }
 
 template <bool BF16, int MT>
-int dispatch_w4(const glb_linear& L, const GemvParams& P, cudaStream_t stream) {
+int dispatch_w4(const glb_linear& L, const GemvParams& P, void* workspace, size_t ws_bytes, cudaStream_t stream) {
   const int G = P.K / P.group_size;
   const int rpgi = P.group_size / 32;
   // split K over a 2-CTA cluster when that still leaves whole groups per warp-batch
@@ -853,13 +1215,22 @@ int dispatch_w4(const glb_linear& L, const GemvParams& P, cudaStream_t stream) {
     constexpr int MT8 = (MT <= 8) ? MT : 8;                                                           \
     const bool split = (G % (2 * GPB) == 0 && P.N / GV_COLS < 296);                                   \
     const int variant = gemv_variant();                                                               \
+    if (MT == 1 && RPG >= 2 && variant == 7 && gemv_m1_ok(P) && (reinterpret_cast<uintptr_t>(L.scales) & 15) == 0 && \
+        (P.mode == 2 || (reinterpret_cast<uintptr_t>(L.zeros) & 15) == 0) && (P.N * 2) % 16 == 0) {   \
+      constexpr int R2 = (RPG >= 2) ? RPG : 2;                                                        \
+      const int gpw = (G + M1_NW - 1) / M1_NW;                                                        \
+      if (gpw <= 1) return launch_w4_m1<BF16, R2, F, 1>(L, P, workspace, ws_bytes, stream);           \
+      if (gpw <= 2) return launch_w4_m1<BF16, R2, F, 2>(L, P, workspace, ws_bytes, stream);           \
+      if (gpw <= 4) return launch_w4_m1<BF16, R2, F, 4>(L, P, workspace, ws_bytes, stream);           \
+      return launch_w4_m1<BF16, R2, F, 8>(L, P, workspace, ws_bytes, stream);                         \
+    }                                                                                                 \
     if (MT <= 8 && variant != 3 && (reinterpret_cast<uintptr_t>(L.scales) & 15) == 0 &&               \
         (P.mode == 2 || (reinterpret_cast<uintptr_t>(L.zeros) & 15) == 0) && (P.N * 2) % 16 == 0) {   \
       /* x1: late trigger, x2: trigger after wait, x3: bulk1d + trigger after wait */               \
-      const int late = (variant % 10 == 1 && variant > 10) ? 1 : ((variant % 10 == 2 && variant > 10) ? 2 : ((variant % 10 == 3 && variant > 10) ? 12 : 0)); \
+      const int late = (variant == 7) ? 2 : (variant % 10 == 1 && variant > 10) ? 1 : ((variant % 10 == 2 && variant > 10) ? 2 : ((variant % 10 == 3 && variant > 10) ? 12 : 0)); \
       if ((variant == 6 || variant / 10 == 6) && MT8 == 1 && gemv_tma_ok(P, 1) && G <= GT_GPW * 8)     \
         return launch_w4_tma<BF16, MT8, RPG, 1, F, 8, true>(L, P, late, stream);                      \
-      if ((variant == 5 || variant / 10 == 5 || variant == 6 || variant / 10 == 6) && gemv_tma_ok(P, 1)) \
+      if ((variant == 7 || variant == 5 || variant / 10 == 5 || variant == 6 || variant / 10 == 6) && gemv_tma_ok(P, 1)) \
         return launch_w4_tma<BF16, MT8, RPG, 1, F, 16>(L, P, late, stream);                           \
       if (split && gemv_tma_ok(P, 2)) return launch_w4_tma<BF16, MT8, RPG, 2, F, 8>(L, P, late, stream); \
       if (gemv_tma_ok(P, 1)) return launch_w4_tma<BF16, MT8, RPG, 1, F, 8>(L, P, late, stream);       \
@@ -918,8 +1289,15 @@ bool gemv_supported(const glb_linear& L, int64_t M) {
   return true;
 }
 
+// The M == 1 kernel keeps the chained hand-off's arrival counters in the tail of the workspace's 64 KB counter region
+// (zero-initialised by the caller like the split-K counters; the kernels re-zero their own slot).
+size_t gemv_workspace(const glb_linear& L, int64_t M) {
+  (void)L;
+  return (M == 1 && chain_mode() && gemv_variant() == 7) ? (size_t)64 * 1024 : 0;
+}
+
 int launch_gemv(const glb_linear& L, const void* x, const float* scales_x, void* y, int64_t M, const void* bias,
-                cudaStream_t stream) {
+                void* workspace, size_t ws_bytes, cudaStream_t stream) {
   (void)scales_x;
   GLB_REQUIRE(gemv_supported(L, M), GLB_ERR_UNSUPPORTED, "decode kernel: unsupported layer configuration");
   GLB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, GLB_ERR_INVALID, "decode kernel: x must be 16-byte aligned");
@@ -931,9 +1309,9 @@ int launch_gemv(const glb_linear& L, const void* x, const float* scales_x, void*
   P.group_size = L.group_size; P.mode = L.W_group_mode;
   const bool bf = (L.input_dtype == GLB_BF16);
   set_kernel_name("gemv_w4_mma");
-  if (M == 1) return bf ? dispatch_w4<true, 1>(L, P, stream) : dispatch_w4<false, 1>(L, P, stream);
-  if (M <= 8) return bf ? dispatch_w4<true, 8>(L, P, stream) : dispatch_w4<false, 8>(L, P, stream);
-  return bf ? dispatch_w4<true, 16>(L, P, stream) : dispatch_w4<false, 16>(L, P, stream);
+  if (M == 1) return bf ? dispatch_w4<true, 1>(L, P, workspace, ws_bytes, stream) : dispatch_w4<false, 1>(L, P, workspace, ws_bytes, stream);
+  if (M <= 8) return bf ? dispatch_w4<true, 8>(L, P, workspace, ws_bytes, stream) : dispatch_w4<false, 8>(L, P, workspace, ws_bytes, stream);
+  return bf ? dispatch_w4<true, 16>(L, P, workspace, ws_bytes, stream) : dispatch_w4<false, 16>(L, P, workspace, ws_bytes, stream);
 }
 
 }  // namespace glb

@@ -173,6 +173,9 @@ GLB_API int glb_get_pdl(void);
 /* Diagnostics (GLB_GEMV_DEBUG=4): copies the decode kernel's recorded phase timestamps (9 x uint64 per record:
  * CTA index, then 8 %globaltimer stamps in ns) to host memory `out`, clears the buffer, returns the word count. */
 GLB_API int glb_debug_timeline(unsigned long long* out, int max_words);
+/* Number of decode launches so far whose hand-off from the previous decode launch uses the device-side arrival counter
+ * instead of kernel completion (only inside a stream capture where adjacency is proven; see csrc/gl_gemv.cu). */
+GLB_API uint64_t glb_chained_launch_count(void);
 
 #ifdef __cplusplus
 }

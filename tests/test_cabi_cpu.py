@@ -124,11 +124,12 @@ def _a16w4_desc(N, K, gs=128):
 
 
 def test_workspace_plan_without_gpu():
-    """glb_workspace_bytes is pure host logic: zero for the decode kernel and for full-size prefill, counters + fp32
+    """glb_workspace_bytes is pure host logic: the 64 KB counter region for the M = 1 decode kernel (its chained
+    hand-off keeps arrival counters in the tail of that region), zero for full-size prefill, counters + fp32
     partial tiles for the split-K range 16 < M <= 128 of a narrow layer (tiles * splits <= SM pairs)."""
     lib = _cabi.load()
     d = _a16w4_desc(4096, 4096)
-    assert lib.glb_workspace_bytes(ctypes.byref(d), 1, -1) == 0          # decode kernel
+    assert lib.glb_workspace_bytes(ctypes.byref(d), 1, -1) == 65536      # decode kernel: hand-off counters only
     assert lib.glb_workspace_bytes(ctypes.byref(d), 16, -1) == 0
     assert lib.glb_workspace_bytes(ctypes.byref(d), 4096, -1) == 0       # 256 tiles: no split
     assert lib.glb_workspace_bytes(ctypes.byref(d), 256, -1) == 0        # split-K is not used above M = 128

@@ -648,3 +648,48 @@ def test_split_k_under_graph_capture_without_warmup_on_the_capture_stream():
         graphs[i].replay()
         torch.cuda.synchronize()
         assert torch.equal(outs[i], want[i]), i
+
+
+# ------------------------------------------------------------------------------------------------
+def test_chained_decode_graph_uses_flag_handoff_and_matches_eager():
+    """A chain of M = 1 layers captured in one CUDA graph: every launch after the first proves (from the capture's
+    dependency set) that its x is the y of the launch before it and waits on that launch's arrival counter instead of
+    kernel completion.  The result must equal the eager chain bit for bit, on every replay; a foreign kernel between two
+    layers (in-place activation on y) must switch that link back to the kernel-boundary wait."""
+    K = N = 4096
+    dt = torch.float16
+    layers = []
+    for i in range(6):
+        W_q, s, z = gen_int(N, K, 4, 128, dt, seed=900 + i)
+        s = (s.float() * 0.3).to(dt)           # keep a 6-deep chain in range
+        layers.append(GemLiteLinear(4, 128, K, N, DType.FP16, DType.FP16).pack(W_q.to(DEV), s.to(DEV), z.to(DEV)))
+    x = xgen(1, K, dt, 77).to(DEV)
+
+    def chain(h, act_after=None):
+        for i, L in enumerate(layers):
+            h = L(h)
+            if act_after is not None and i == act_after:
+                h.mul_(0.5)                    # foreign in-place kernel on y
+        return h
+
+    y_ref, y_ref_act = chain(x).clone(), chain(x, 2).clone()
+    torch.cuda.synchronize()
+    assert _cabi.last_kernel() == "gemv_w4_mma"
+    for act_after, want in ((None, y_ref), (2, y_ref_act)):
+        st = torch.cuda.Stream()
+        st.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(st):
+            chain(x, act_after)
+            torch.cuda.synchronize()
+            c0 = _cabi.chained_launch_count()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=st):
+                y = chain(x, act_after)
+            n_flag = _cabi.chained_launch_count() - c0
+            for _ in range(25):
+                g.replay()
+                torch.cuda.synchronize()
+                assert torch.equal(y, want), (act_after, (y != want).sum().item())
+        if os.environ.get("GLB_GEMV_FLAGS", "1") != "0" and os.environ.get("GLB_GEMV_VARIANT", "7") == "7":
+            assert n_flag == (5 if act_after is None else 4), (act_after, n_flag)
+    torch.cuda.current_stream().wait_stream(st)
