@@ -91,11 +91,6 @@ def load():
     return _lib
 
 
-def experimental_enabled() -> bool:
-    """Paths written but not yet validated on a GPU are reachable only with GEMLITE_B200_EXPERIMENTAL=1."""
-    return os.environ.get("GEMLITE_B200_EXPERIMENTAL", "0") not in ("", "0")
-
-
 def check(rc: int, what: str):
     if rc != 0:
         msg = load().glb_last_error().decode("utf-8", "replace")

@@ -95,6 +95,7 @@ def get_matmul_type(batch_size: int, W_nbits: int, mx_dtype: bool = False) -> st
 # descriptor plumbing
 # ---------------------------------------------------------------------------------------------------
 _DESC_CACHE = {}
+_DESC_CACHE_MAX = int(os.environ.get("GEMLITE_B200_DESC_CACHE", "65536"))
 _WORKSPACE = {}
 _WORKSPACE_RETIRED = []
 _CAPTURE_WS = {}      # (device, stream) -> (capture id, buffer zeroed inside that capture)
@@ -113,6 +114,8 @@ def _make_desc(W_q: Tensor, scales: Tensor, zeros: Tensor, meta: List[int]) -> _
            scales.shape, scales.stride(), scales.dtype, zeros.shape, zeros.stride(), zeros.dtype, tuple(meta))
     d = _DESC_CACHE.get(key)
     if d is not None:
+        if len(_DESC_CACHE) >= _DESC_CACHE_MAX // 2:     # keep recently used entries at the young end
+            _DESC_CACHE[key] = _DESC_CACHE.pop(key)
         return d
     d = _cabi.GlbLinear()
     eps = int(meta[4])
@@ -133,9 +136,13 @@ def _make_desc(W_q: Tensor, scales: Tensor, zeros: Tensor, meta: List[int]) -> _
     (d.scaled_activations, d.W_nbits, d.group_size, d.unpack_mask, d.elements_per_sample, d.input_dtype,
      d.output_dtype, d.acc_dtype, d.meta_dtype, d.channel_scale_mode, d.W_group_mode, d.data_contiguous) = \
         [int(v) for v in meta]
-    if len(_DESC_CACHE) > 4096:
-        _DESC_CACHE.clear()
-        _WS_BYTES.clear()          # keyed by id(descriptor): ids are recycled once the descriptors are gone
+    if len(_DESC_CACHE) >= _DESC_CACHE_MAX:
+        # evict the oldest quarter (dicts keep insertion order; a hit re-inserts, see above) instead of dropping the
+        # whole cache: a model with more layers than the bound would otherwise rebuild every descriptor every step
+        for old in list(_DESC_CACHE)[: _DESC_CACHE_MAX // 4]:
+            dd = _DESC_CACHE.pop(old)
+            for wk in [k for k in _WS_BYTES if k[0] == id(dd)]:
+                _WS_BYTES.pop(wk, None)
     _DESC_CACHE[key] = d
     return d
 
@@ -164,7 +171,8 @@ def _workspace(device, nbytes: int) -> Optional[Tensor]:
                 _CAPTURE_WS[key] = held                       # the graph's pool keeps earlier captures' buffers alive
             return held[1]
     if ws is not None:
-        _WORKSPACE_RETIRED.append(ws)
+        _WORKSPACE_RETIRED.append(ws)             # captured graphs may still point at it
+        del _WORKSPACE_RETIRED[:-8]                # bounded: a buffer is only ever replaced by a larger one (<= 8 doublings)
     ws = torch.zeros(max(nbytes, 16 << 20), dtype=torch.uint8, device=device)
     _WORKSPACE[key] = ws
     return ws
@@ -233,10 +241,6 @@ def _forward_eager(x: Tensor, bias: Optional[Tensor], tensor_args, meta_args, ma
     scales_x = None
     if bool(meta_args[0]) and enable_activation_scaling(batch_size):
         csm = int(meta_args[9])
-        if input_dtype in (DType.MXFP8, DType.MXFP4, DType.NVFP4) and not _cabi.experimental_enabled():
-            raise NotImplementedError(
-                f"dynamic activation quantisation for {input_dtype} (channel_scale_mode={csm}) is not validated yet "
-                "(set GEMLITE_B200_EXPERIMENTAL=1 to try it)")
         if input_dtype in FP8_INT8_DTYPES:
             x, scales_x = scale_activations_per_token(x, w_dtype=DTYPE_TO_TORCH[input_dtype.value])
         elif input_dtype == DType.MXFP8 and csm == 2:
@@ -254,6 +258,14 @@ def _forward_eager(x: Tensor, bias: Optional[Tensor], tensor_args, meta_args, ma
     expected = DTYPE_TO_TORCH[input_dtype.value]
     if x2d.dtype != expected:
         raise TypeError(f"activations are {x2d.dtype}, layer expects {expected}")
+    # the kernels (and their TMA maps) take the row length of x from the layer: a narrower / wider activation would be
+    # read out of bounds, so refuse it here.  Packed fp4 activations carry two codes per byte.
+    in_features = tensor_args[0].shape[0] * int(meta_args[4])
+    k_have = x2d.shape[1] * (2 if input_dtype in (DType.MXFP4, DType.NVFP4) else 1)
+    if k_have != in_features:
+        raise RuntimeError(f"forward: activations have {k_have} input features, the layer expects {in_features}")
+    if x2d.data_ptr() % 16 != 0:       # a contiguous slice of a flat buffer: the TMA / 128-bit paths need 16-byte rows
+        x2d = x2d.clone()
     out = _matmul(x2d, bias, tensor_args, meta_args, scales_x, int(matmul_type))
     return out.view(out_shape)
 

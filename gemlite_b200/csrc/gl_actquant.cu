@@ -176,8 +176,8 @@ int launch_aq(const void* x, int64_t M, int64_t K, int q_dtype, void* q, float* 
 // One thread owns 8 consecutive k of one row: 4 threads form an MX group, 2 an NV group (shuffle max); the scale
 // rows of the padding (M rounded up to the group size, as the reference allocates them) are written too: 97 = 2^-30
 // for MX, 0 for NV, what the reference's masked loads (other = 0) produce there.
-// STATUS: written at the end of round 1 without GPU time left to validate it; the Python layer exposes it only
-// with GEMLITE_B200_EXPERIMENTAL=1.
+// STATUS: validated on a B200 in round 2 against the reference's fixture and the oracle (MXFP8 / MXFP4 bit for bit at the
+// first visit; NVFP4 after the uint8 carry semantics of the code packing were reproduced, see below).
 // =================================================================================================
 __device__ __forceinline__ uint32_t next_pow2_exponent(float val) {          // quant_utils.py:381-391, eps_exp = -30
   const uint32_t xi = __float_as_uint(val);
@@ -246,9 +246,16 @@ __global__ void __launch_bounds__(256) act_quant_mx_kernel(const XT* __restrict_
     }
     *reinterpret_cast<uint2*>(q + r * K + t * 8) = make_uint2(w[0], w[1]);
   } else {
+    // two codes per byte, even k = low nibble, in the reference's uint8 arithmetic (`lo | (hi << 4)`,
+    // quant_utils.py:810-812 / 903-905): a saturated NVFP4 group (e4m3 scale clamped at 448) can produce |wq| > 7,
+    // i.e. index 8 (16 for negatives) -- the carry of an even code lands in the odd nibble of the SAME byte, the carry
+    // of an odd code falls off the byte.  Reproduced as is (found on hardware against the reference fixture).
     uint32_t w = 0u;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) w |= e2m1_code(__fdiv_rn(v[j], inv_den)) << (4 * j);     // even k = low nibble
+    for (int j = 0; j < 8; j += 2) {
+      const uint32_t lo = e2m1_code(__fdiv_rn(v[j], inv_den)), hi = e2m1_code(__fdiv_rn(v[j + 1], inv_den));
+      w |= ((lo | (hi << 4)) & 0xffu) << (4 * j);
+    }
     *reinterpret_cast<uint32_t*>(q + r * (K >> 1) + t * 4) = w;
   }
 }

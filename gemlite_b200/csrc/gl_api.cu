@@ -247,7 +247,7 @@ extern "C" int glb_matmul(const glb_linear* L, const void* x, const void* scales
   // 0. MXFP4 weight-only layers at M <= 4: streaming CUDA-core kernel (the reference sends every MX dtype at M == 1 to
   //    GEMM_SPLITK, core.py:100-114); an explicit "GEMM" request keeps the tensor-core kernel
   if (matmul_type != GLB_MM_GEMM && gemv_mx_supported(*L, M)) return launch_gemv_mx(*L, x, y, M, bias, stream);
-  // 0b. A8W8 at M <= 16: 16-feature-row streaming kernel (gl_gemv_a8.cu) -- opt-in (GLB_A8_GEMV=1) until validated
+  // 0b. A8W8 at M <= 16: 16-feature-row streaming kernel (gl_gemv_a8.cu) (validated in round 2)
   if (matmul_type != GLB_MM_GEMM && gemv_a8_enabled() && gemv_a8_supported(*L, M))
     return launch_gemv_a8(*L, x, sx, y, M, bias, stream);
   const bool prefer_gemv = can_gemv && (gemv_name || (was_auto && M <= 16) || !can_tc);

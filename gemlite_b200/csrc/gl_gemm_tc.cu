@@ -348,7 +348,7 @@ template <int BT> struct T8Smem {
   static constexpr int TOTAL = STAGES * STAGE + 1024 + 1024;
 };
 
-// SPLIT = true: split-K flavour for 16 < M <= 128 (opt-in, GLB_A8_SPLITK=1; STATUS: written at the end of round 1 without
+// SPLIT = true: split-K flavour for 16 < M <= 128 (not instantiated: validated in round 2, slower than unsplit; written without
 // GPU time left to validate it).  The 128-feature tile gives only N / 128 CTAs (32 at N = 4096) for one token block, so a
 // small batch streams its weights through a fraction of the SMs; with split-K every (tile, K range) is a work item.
 // SPLIT = false compiles to exactly the kernel measured in round 1 (every difference is behind `if constexpr` / SPLIT ?:).
@@ -589,26 +589,22 @@ int launch_tc(const glb_linear& L, const void* x, void* y, int64_t M, const void
 
 
 // Work decomposition of the single-CTA A8W8 kernel (shared by the launch and by glb_workspace_bytes).  Split-K is
-// opt-in (GLB_A8_SPLITK=1) and only used for one token block (16 < M <= 128) when the feature tiles leave SMs idle.  The
+// not used (see t8_plan) -- it would only apply to one token block (16 < M <= 128) when the feature tiles leave SMs idle.  The
 // counters share the fixed region at the start of the workspace with the pair kernel's (gl_gemm_tc2.cu).
 constexpr size_t T8_COUNTER_REGION = 64 * 1024;
 struct T8Plan {
   int splits, kb_per_split;
   size_t counter_bytes, partial_bytes;
 };
-bool a8_splitk_enabled() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("GLB_A8_SPLITK"); v = (e && atoi(e) != 0) ? 1 : 0; }
-  return v == 1;
-}
 int t8_token_block(int64_t M) { return (M <= 32) ? 32 : ((M <= 64) ? 64 : ((M <= 128) ? 128 : 256)); }
 T8Plan t8_plan(const glb_linear& L, int64_t M, int BT) {
   T8Plan p;
   const int kblocks = (int)(L.K / T8_BK), tiles = (int)(L.N / TC_BM) * (int)((M + BT - 1) / BT);
   p.splits = 1;
-  if (a8_splitk_enabled() && M > 16 && M <= 128 && (size_t)tiles * 4 * sizeof(int) <= T8_COUNTER_REGION)
-    for (int s = std::min(8, num_sms() / std::max(tiles, 1)); s >= 2; --s)
-      if (kblocks % s == 0 && kblocks / s >= 4) { p.splits = s; break; }
+  // Split-K of this kernel was validated on hardware in round 2 (bit-exact) and measured SLOWER than the unsplit
+  // launch (profiles/optin_validation_r2.txt: M = 64 37.9 vs 27.6 us, M = 128 58.4 vs 33.8 us), so it is never planned;
+  // small batches go to the streaming kernel in gl_gemv_a8.cu instead.
+  (void)tiles; (void)kblocks;
   p.kb_per_split = kblocks / p.splits;
   p.counter_bytes = (p.splits > 1) ? T8_COUNTER_REGION : 0;
   p.partial_bytes = (p.splits > 1) ? (size_t)tiles * p.splits * TC_BM * BT * sizeof(uint32_t) : 0;
@@ -645,13 +641,8 @@ int launch_t8(const glb_linear& L, const void* x, const float* scales_x, void* y
     P.splits = plan.splits; P.kb_per_split = plan.kb_per_split;
     P.ws_counter = reinterpret_cast<int*>(workspace);
     P.ws_partial = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(workspace) + plan.counter_bytes);
-    auto kern_split = gemm_a8w8_tc_kernel<IS_INT, BT, true>;
-    GLB_ENSURE_SMEM(kern_split, S::TOTAL);
-    const int grid_split = std::min(num_sms(), P.tiles_m * P.tiles_n * P.splits);
-    kern_split<<<grid_split, T8_THREADS, S::TOTAL, stream>>>(tx, tw, P, idesc);
-    count_launch();
-    GLB_CHECK_CUDA(cudaGetLastError());
-    return GLB_OK;
+    set_error("A8W8 split-K is not planned by t8_plan()");
+    return GLB_ERR_UNSUPPORTED;
   }
   auto kern = gemm_a8w8_tc_kernel<IS_INT, BT>;
   GLB_ENSURE_SMEM(kern, S::TOTAL);

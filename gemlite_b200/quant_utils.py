@@ -47,9 +47,6 @@ def _quant_act_mx(tensor: Tensor, mx_tag: int, q_dtype: torch.dtype, group: int,
     """x (..., K) -> (q (M, K or K/2), scales (M padded to `group` rows, K/group)) through glb_quant_act_mx.
     Like the reference's *_triton_v2 functions the result is 2-D (quant_utils.py:546-591, 819-857, 917-954)."""
     _cabi.require_cuda(tensor, what)
-    if not _cabi.experimental_enabled():
-        raise NotImplementedError(f"{what}: MX/NV activation quantisation is not validated yet "
-                                  "(set GEMLITE_B200_EXPERIMENTAL=1 to try it)")
     x2 = tensor.reshape(-1, tensor.shape[-1])
     if not x2.is_contiguous():
         x2 = x2.contiguous()

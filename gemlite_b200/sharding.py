@@ -28,32 +28,42 @@ def column_range(n_features: int, rank: int, world: int, align: int = 32) -> Tup
 
 
 def shard_tensors(W_q: Tensor, scales: Tensor, zeros: Tensor, bias: Optional[Tensor], n_features: int, rank: int,
-                  world: int, contiguous: bool = True):
+                  world: int, contiguous: bool = True, mx: Optional[bool] = None):
     """Slice the tensors `get_tensor_args()` returns (+ bias) down to one column shard.
 
     W_q is `(K/eps, N)` (packed, or the `(K, N)` strided view of unpacked weights); scales / zeros are `(K/gs, N)`,
     `(1, N)` per-channel, MX scales `(N, K/gs)`, or the reference's placeholders (0-d scalar zero, empty `[[]]`),
-    which are passed through untouched (core.py:470-475)."""
+    which are passed through untouched (core.py:470-475).
+
+    `mx` says which axis of `scales` is the feature axis: MX layers store scales as the `(N, K/gs)` view with strides
+    `(1, N)` (core.py:490-497), everything else as `(K/gs, N)`.  A shape test alone is ambiguous when K/gs == N
+    (e.g. N = 256, K = 8192, gs = 32); with `mx=None` the storage order decides (strides `(1, N)` = MX view)."""
     b, e = column_range(n_features, rank, world)
 
-    def cols(t: Tensor) -> Tensor:
+    def cols(t: Tensor, feature_axis: int) -> Tensor:
         if t is None or t.dim() < 2 or t.numel() <= 1:
             return t                                     # scalar zero-point / empty placeholder
-        if t.shape[-1] == n_features:
-            out = t[..., b:e]
-        elif t.shape[0] == n_features:                   # MX scales: (N, K/gs) view with strides (1, N)
-            out = t[b:e]
-        else:
-            raise ValueError(f"cannot column-shard a tensor of shape {tuple(t.shape)} for N={n_features}")
-        return out
+        if t.shape[feature_axis] != n_features:
+            raise ValueError(f"cannot column-shard a tensor of shape {tuple(t.shape)} for N={n_features} "
+                             f"along axis {feature_axis}")
+        return t[b:e] if feature_axis == 0 else t[..., b:e]
 
-    Wl = cols(W_q)
+    def meta_axis(t: Tensor) -> int:
+        if t is None or t.dim() < 2 or t.numel() <= 1:
+            return 1
+        if mx is not None:
+            return 0 if mx else 1
+        if t.shape[0] == n_features and t.shape[-1] == n_features:
+            return 0 if (t.stride(0) == 1 and t.stride(1) == n_features) else 1
+        return 0 if (t.shape[0] == n_features and t.shape[-1] != n_features) else 1
+
+    Wl = cols(W_q, 1)
     if contiguous and W_q.is_contiguous():
         Wl = Wl.contiguous()                             # packed (K/eps, N/g) row-major, what the kernels assume
     elif not W_q.is_contiguous():
         # unpacked 8/16-bit weights are the transposed view of an (N, K) row-major matrix: keep that storage order
         Wl = Wl.t().contiguous().t()
-    sl, zl = cols(scales), cols(zeros)
+    sl, zl = cols(scales, meta_axis(scales)), cols(zeros, 1)
     if sl is not None and sl.dim() >= 2 and sl.numel() > 1:
         sl = sl.contiguous() if scales.is_contiguous() else sl.t().contiguous().t()
     if zl is not None and zl.dim() >= 2 and zl.numel() > 1:
@@ -85,10 +95,12 @@ class ColumnShardedLinear(torch.nn.Module):
     def __init__(self, layer, rank: int, world: int, group=None):
         super().__init__()
         from .core import GemLiteLinear
+        from .dtypes import is_mx_dtype
         N = layer.out_features
         W_q, scales, zeros = layer.get_tensor_args()
         Wl, sl, zl, bl = shard_tensors(W_q.data, scales.data, zeros.data, None if layer.bias is None else layer.bias.data,
-                                       N, rank, world, contiguous=bool(layer.data_contiguous))
+                                       N, rank, world, contiguous=bool(layer.data_contiguous),
+                                       mx=is_mx_dtype(layer.input_dtype))
         n_local = N // world
         local = GemLiteLinear.__new__(GemLiteLinear)
         torch.nn.Module.__init__(local)

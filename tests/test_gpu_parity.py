@@ -20,18 +20,11 @@ from golden_io import MX_DYNAMIC, from_bits, layer_cases, load, tdtype
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
-# paths written without GPU time to validate them (MX / NV activation quantisers + dynamic MX layers): opt-in
-EXPERIMENTAL = os.environ.get("GEMLITE_B200_EXPERIMENTAL", "0") not in ("", "0")
-# opt-in A8W8 decode kernel (gl_gemv_a8.cu, read once by the library at its first A8W8 call)
-A8_GEMV = os.environ.get("GLB_A8_GEMV", "0") not in ("", "0")
-
-
-# opt-in tensor-path flavour of the MXFP4 decode kernel (GLB_MXV_VARIANT=1)
-MXV_NAME = "gemv_mxfp4_mma" if os.environ.get("GLB_MXV_VARIANT", "0") == "1" else "gemv_mxfp4"
+MXV_NAME = "gemv_mxfp4"
 
 
 def a8_kernel_name(kind, M):
-    if A8_GEMV and M <= 16:
+    if M <= 16:                 # streaming kernel (gl_gemv_a8.cu), validated in round 2
         return f"gemv_a8w8_{kind}"
     return f"gemm_a8w8_{kind}_tcgen05_2cta" if M > 128 else f"gemm_a8w8_{kind}_tcgen05"
 
@@ -179,8 +172,6 @@ def build_gpu_layer(name, z, info):
 def test_against_reference_fixtures(name):
     """pack() reproduces the reference's tensors/metadata bit for bit; forward() matches the reference
     kernels' recorded outputs (where the CPU interpreter executes them faithfully) and the oracle."""
-    if name in MX_DYNAMIC and not EXPERIMENTAL:
-        pytest.skip("dynamic MX / NV activation paths are opt-in (GEMLITE_B200_EXPERIMENTAL=1) until validated")
     z, info = load(name)
     layer = build_gpu_layer(name, z, info)
     assert layer.get_meta_args() == [int(v) for v in z["meta_args"]]
@@ -439,7 +430,6 @@ def test_fp8_dynamic_and_weight_only_paths():
     assert relerr(wl(x.to(DEV)), O.forward(pw, x)) <= REL[torch.float16]
 
 
-@pytest.mark.skipif(not A8_GEMV, reason="A8W8 decode kernel is opt-in (GLB_A8_GEMV=1) until validated")
 def test_a8w8_decode_kernel_vs_oracle():
     """gl_gemv_a8.cu: M <= 16, every scaling mode / output type of the A8W8 path; INT8 bit-exact, FP8 within REL."""
     N, K = 1024, 2048
@@ -474,7 +464,6 @@ def test_a8w8_decode_kernel_vs_oracle():
             assert got.dtype == torch.int32 and torch.equal(got.cpu(), xi.int() @ Wi.int().t()), (Ni, Ki, Mi)
 
 
-@pytest.mark.skipif(not EXPERIMENTAL, reason="MX / NV activation quantisers are opt-in (GEMLITE_B200_EXPERIMENTAL=1) until validated")
 def test_mx_activation_quantisers_bit_exact():
     """glb_quant_act_mx against (a) the reference's own outputs on the edge-case fixture and (b) the oracle on seeded
     inputs: codes AND scales bit for bit (fp32 arithmetic with IEEE division on both sides)."""
@@ -505,7 +494,6 @@ def test_mx_activation_quantisers_bit_exact():
     assert tuple(q.shape) == (6, 128) and tuple(sc.shape) == (32, 8)
 
 
-@pytest.mark.skipif(not EXPERIMENTAL, reason="dynamic MX layers are opt-in (GEMLITE_B200_EXPERIMENTAL=1) until validated")
 def test_mx_dynamic_layers_vs_oracle():
     """A8W8 / A8W4 / A4W4 MXFP and A4W4 NVFP with activations quantised on the fly, larger shapes than the fixtures,
     through from_linear (GPU weight quantiser) -> forward, against the oracle fed with the layer's own tensors."""
@@ -524,7 +512,15 @@ def test_mx_dynamic_layers_vs_oracle():
                 x = xgen(M, K, dt, 700 + M)
                 y = layer(x.to(DEV))
                 assert _cabi.last_kernel() == "generic_cuda_core"
-                e = relerr(y, O.forward(p, x))
+                if layer.channel_scale_mode == 2:
+                    # per-token fp8 activations: the GPU quantiser divides with div.full.f32 like the reference's Triton
+                    # build (codes / scales bit-equal to it: test_gpu_vs_reference.py), the CPU oracle with the IEEE
+                    # divide -- a code on an exact tie can differ.  Feed the oracle the product's own codes.
+                    q, sx = scale_activations_per_token(x.to(DEV), w_dtype=torch.float8_e4m3fn)
+                    yo = O.forward(p, q.cpu(), scales_x=sx.cpu())
+                else:
+                    yo = O.forward(p, x)
+                e = relerr(y, yo)
                 assert e <= max(REL[dt], 2e-3), (cls.__name__, kw, dt, M, e)
 
 

@@ -6,9 +6,14 @@ tests/refdual.py.  Bars:
   * packed tensors + meta_args: bit-equal;
   * INT8 x INT8: outputs `torch.equal` the reference's GEMM and GEMV_SPLITK outputs; per-token int8 / fp8 codes and
     scales `torch.equal` the reference's Triton quantiser;
-  * floating point: mean|ours - ref| < 1e-3 (the reference's own test bar, test_gemlitelineartriton.py), and -- because
-    the reference GEMVs accumulate in fp16 with atomics -- both implementations are also compared with the fp32 CPU
-    oracle: our max / mean error must not exceed the reference's (5 % + 1 output-ulp slack).
+  * floating point: every output within the stated tolerance of the fp32 CPU oracle (REL / REL_DECODE of
+    test_gpu_parity.py) whether or not the reference ran; where it ran: mean|ours - ref| < 1e-3 (the reference's own test
+    bar, test_gemlitelineartriton.py) -- unless the REFERENCE is the outlier against the oracle (its GEMVs accumulate in
+    fp16 with atomics; its default GEMV_SPLITK / GEMV_REVSPLITK configs break on grouped 8-bit / 1-bit weights), which
+    is recorded as `reference_outlier`; and our max / mean error against the oracle must not exceed the reference's
+    (5 % + 1 output-ulp slack).  The factorised decode kernel is judged, with the reference, against the exact fp64
+    product of the stored parameters instead (it skips the fp16 rounding of every dequantised weight that the oracle
+    and the reference's GEMM perform, so it is closer to that product and further from the oracle).
 A JSON report of every number goes to gpurun_out/vs_reference.json (copied to profiles/ by hand)."""
 import json
 import os
@@ -24,7 +29,7 @@ import gemlite_b200.helper  # noqa: F401
 from gemlite_b200 import _cabi
 from oracle import gemlite_oracle as O
 import refdual
-from test_gpu_parity import oracle_from_layer
+from test_gpu_parity import REL, REL_DECODE, oracle_from_layer
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -136,6 +141,24 @@ def _oracle_rows(layer, case, M, i, rows):
     return O.forward(p, x[rows]).double()
 
 
+def _exact_rows(layer, x, rows):
+    """x[rows] @ W with W = the stored parameters dequantised in fp64 WITHOUT rounding (A16W4 grouped INT layers)."""
+    from gemlite_b200 import bitpack as B
+    K, N, gs = layer.in_features, layer.out_features, layer.group_size
+    codes = B.unpack_over_cols(layer.W_q.data, layer.W_nbits, K, transpose=True).double()        # (N, K)
+    s = layer.scales.data.double().t().repeat_interleave(gs, dim=1)                              # (N, K)
+    mode = layer.W_group_mode
+    if mode == 2:
+        W = codes * s
+    else:
+        z = layer.zeros.data.double().t().repeat_interleave(gs, dim=1)
+        W = codes * s + z if mode == 4 else (codes - z) * s
+    out = x[rows.to(x.device)].double() @ W.t()
+    if layer.bias is not None:
+        out = out + layer.bias.data.double()
+    return out.cpu()
+
+
 def _err(y, yo):
     d = (y.double() - yo).abs()
     return d.max().item() / (yo.abs().max().item() + 1e-30), d.mean().item()
@@ -169,34 +192,60 @@ def test_same_inputs_same_outputs_as_reference(both, name):
         x = refdual.x_for(case, M, i)
         rows = torch.arange(M) if M <= case.get("sample_rows", 10 ** 9) else \
             torch.randperm(M, generator=torch.Generator().manual_seed(M))[:case["sample_rows"]].sort().values
-        yo = None
+        yo = yx = None
         for k in case["kernels"]:
             if k != "AUTO" and M > 1 and "GEMV" in k:
                 continue
             key = f"{k}:{M}"
-            if key not in r["y"]:
-                rep["calls"][key] = {"reference_failed": r["err"].get(key, "missing")}
-                continue                                   # the reference itself raised: nothing to compare with
             y = (layer(x) if k == "AUTO" else layer.forward_manual(x, matmul_type=k))
             torch.cuda.synchronize()
             kern = _cabi.last_kernel()
-            y, yr = y.cpu(), r["y"][key]
-            assert y.dtype == yr.dtype and y.shape == yr.shape
+            y = y.cpu()
+            assert torch.isfinite(y.float()).all()
             if yo is None:
                 yo = _oracle_rows(layer, case, M, i, rows)
             e_max, e_mean = _err(y[rows], yo)
+            tol_o = (REL_DECODE if kern == "gemv_w4_mma" else REL)[out_dt]
+            if layer.scaled_activations and not is_int8:
+                tol_o = max(tol_o, 2e-2)       # a dynamically quantised activation code on an exact tie (see test_gpu_parity)
+            assert e_max <= tol_o, (name, key, kern, "vs oracle", e_max, tol_o)
+            if key not in r["y"]:
+                # the reference itself raised on this GPU (recorded): the oracle comparison above is all there is
+                rep["calls"][key] = dict(kernel=kern, ours_vs_oracle=(e_max, e_mean), reference_failed=r["err"].get(key, "missing"))
+                continue
+            yr = r["y"][key]
+            assert y.dtype == yr.dtype and y.shape == yr.shape
             r_max, r_mean = _err(yr[rows], yo)
             d_mean = (y.double() - yr.double()).abs().mean().item()
             equal = bool(torch.equal(y, yr))
-            rep["calls"][key] = dict(kernel=kern, ours_vs_oracle=(e_max, e_mean), ref_vs_oracle=(r_max, r_mean),
-                                     mean_abs_ours_minus_ref=d_mean, bit_equal=equal)
-            assert torch.isfinite(y.float()).all()
+            call = dict(kernel=kern, ours_vs_oracle=(e_max, e_mean), ref_vs_oracle=(r_max, r_mean),
+                        mean_abs_ours_minus_ref=d_mean, bit_equal=equal)
+            rep["calls"][key] = call
             if is_int8 and k in case.get("exact", ()) and (k != "GEMV_SPLITK" or M == 1):
                 # INT8 x INT8 -> INT32 is exact; epilogue cvt.rn.f32.s32(acc) * (s_x * s_w) -> fp16 is one rounding
                 assert equal, (name, key, kern, (y != yr).sum().item(), d_mean)
-            assert d_mean < 1e-3, (name, key, kern, d_mean)
-            assert e_max <= r_max * 1.05 + 2 * ulp, (name, key, kern, "max", e_max, r_max)
-            assert e_mean <= r_mean * 1.05 + 1e-5, (name, key, kern, "mean", e_mean, r_mean)
+            if d_mean >= 1e-3:
+                # the reference's own test bar (mean |diff| < 1e-3) is missed: acceptable only if the REFERENCE is the
+                # outlier w.r.t. the fp32 oracle (its GEMV kernels accumulate in fp16 with atomics; its default
+                # GEMV_SPLITK / GEMV_REVSPLITK configs read one scale row per BLOCK_K and break on grouped weights)
+                call["reference_outlier"] = True
+                assert e_mean < 1e-4 and r_mean > 0.5 * d_mean, (name, key, kern, d_mean, e_mean, r_mean)
+                continue
+            if kern == "gemv_w4_mma":
+                # The decode kernel applies scale / zero per group to fp32 partial sums instead of rounding every
+                # dequantised weight to fp16 first, so it deviates from the fp16-dequant oracle by weight-rounding noise
+                # while being CLOSER to the exact product of the stored parameters.  Judge both implementations against
+                # that exact product (fp64, no intermediate rounding).
+                if yx is None:
+                    yx = _exact_rows(layer, x, rows)
+                ex_max, ex_mean = _err(y[rows], yx)
+                rx_max, rx_mean = _err(yr[rows], yx)
+                call["vs_exact_product"] = dict(ours=(ex_max, ex_mean), ref=(rx_max, rx_mean))
+                assert ex_max <= rx_max * 1.05 + 2 * ulp, (name, key, kern, "max vs exact", ex_max, rx_max)
+                assert ex_mean <= rx_mean * 1.05 + 1e-5, (name, key, kern, "mean vs exact", ex_mean, rx_mean)
+            else:
+                assert e_max <= r_max * 1.05 + 2 * ulp, (name, key, kern, "max", e_max, r_max)
+                assert e_mean <= r_mean * 1.05 + 1e-5, (name, key, kern, "mean", e_mean, r_mean)
     if case.get("actq"):
         for i, M in enumerate(case["Ms"]):
             x = refdual.x_for(case, M, i)

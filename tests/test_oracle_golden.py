@@ -155,6 +155,11 @@ def test_pack_and_forward_match_reference(name):
             else:
                 tol = TOL_REL_GEMV[out_t]
             assert err <= tol, (name, key, err, tol)
+            if name in EXACT_A8 and mt in ("GEMM", "GEMM_SPLITK", "GEMV_SPLITK"):
+                # 8-bit activations x 8-bit weights: the int32 (and, on these sizes, the fp32-of-fp8) accumulator is exact
+                # and the epilogue is one rounding -- the oracle must reproduce the reference's output BITS, so that a
+                # future oracle change inside the float tolerance cannot silently void "bit-exact" 
+                assert torch.equal(y, ref), (name, key, err)
             if p.input_dtype in O.MX_VALUES and not (p.scaled_activations and p.channel_scale_mode == 2 and mt == "GEMM_SPLITK"):
                 # MX paths: quantisers, scale indexing, NVFP4 norm and the output rounding are reproduced bit for bit
                 # (the post-scale split-K kernel scales in its fp32 buffer, one rounding fewer than the GEMM kernel
@@ -163,6 +168,9 @@ def test_pack_and_forward_match_reference(name):
             checked += 1
         i += 1
     assert checked > 0
+
+
+EXACT_A8 = ("a8w8_int8_dynamic", "a8w8_fp8_dynamic", "int8_w4_scalar_zero")
 
 
 def test_activation_quant_matches_reference():

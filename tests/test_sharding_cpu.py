@@ -101,6 +101,16 @@ def test_column_range_and_placeholders():
     s_mx = torch.arange(4 * 64, dtype=torch.uint8).view(4, 64).t()
     _, sl, _, _ = S.shard_tensors(W, s_mx, empty, None, 64, 1, 2)
     assert sl.shape == (32, 4) and sl.stride() == (1, 32) and torch.equal(sl, s_mx[32:])
+    # K/gs == N (N = 64, K = 2048, gs = 32): the shape alone cannot tell the group axis from the feature axis --
+    # the layer kind (mx flag) or, without it, the storage order does (sliced along K before)
+    s_sq = torch.arange(64 * 64, dtype=torch.int32).to(torch.uint8).view(64, 64).t()      # MX view: (N, K/gs), strides (1, N)
+    for flag in (True, None):
+        _, sl, _, _ = S.shard_tensors(W, s_sq, empty, None, 64, 1, 2, mx=flag)
+        assert sl.shape == (32, 64) and sl.stride() == (1, 32) and torch.equal(sl, s_sq[32:]), flag
+    s_grp = torch.arange(64 * 64, dtype=torch.float32).view(64, 64)                       # ordinary (K/gs, N), contiguous
+    for flag in (False, None):
+        _, sl, _, _ = S.shard_tensors(W, s_grp, empty, None, 64, 1, 2, mx=flag)
+        assert sl.shape == (64, 32) and sl.is_contiguous() and torch.equal(sl, s_grp[:, 32:]), flag
 
 
 def test_column_sharded_linear_builds_a_consistent_local_layer():
