@@ -4,27 +4,31 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 Workload at N=1 (BASELINE.json configs[1]): A16W4 group-size-128 decode, M=1, K=N=4096, fp16.
-One *step* = one decode pass through LAYERS=64 distinct layers of that shape, chained
-(y of layer i is x of layer i+1), i.e. 572 MB of packed weights + metadata per step -- 4.5x the
-126 MB L2, so every layer streams from HBM (this is the "inputs larger than L2" timing rule).
-`value` is algorithmic bytes moved per second over the whole job, inputs resident in HBM; the step is
-replayed from a CUDA graph whose launches carry the programmatic-dependent-launch attribute.
-`e2e` is the same step end to end with HOST buffers: the step input is copied from pinned host memory, the
-64 `GemLiteLinear.__call__`s run (replayed from the CUDA graph a serving stack captures around its decode
-step -- torch.cuda.CUDAGraph, the public PyTorch facility) and the output is copied back to pinned host memory,
-all inside the timed region (host wall clock incl. the final synchronize).  The same loop with plain eager
-calls (one Python -> C-ABI call per layer) is reported next to it as `e2e.eager_value`.
-`prefill` reports the second half of the metric (M=4096 TFLOP/s) on configs[2].
-`independent_launches` (N=1, supplementary, never the headline): the same 64 layers with the same x for every call (no
-y -> x chain) on 4 streams inside one CUDA graph -- what the kernel streams once the dependent-launch hand-off is off
-the critical path.
+One *step* = one decode pass through LAYERS=64 distinct layers of that shape, chained (y of layer i is x of layer
+i+1), i.e. 572 MB of packed weights + metadata per step -- 4.5x the 126 MB L2, so every layer streams from HBM (the
+"inputs larger than L2" timing rule).  The layers are declared to the library in execution order
+(`gemlite_b200.link_layers`, what `helper.patch_model` does for a model), the step is replayed from a CUDA graph whose
+launches carry the programmatic-dependent-launch attribute.  `value` = algorithmic bytes per second over the whole job,
+inputs resident in HBM, device-timed.
+Other keys of the line:
+  e2e                  the same step with HOST buffers (pinned x -> device, graph replay, y -> pinned host, synchronize),
+                       host wall clock; next to it the eager variant (one Python -> C-ABI call per layer)
+  roofline             the decode kernel against the measured HBM peak (MEASURED_PEAKS.json)
+  isolated_call        one eager call, cold L2 (the reference's own timing protocol, examples/benchmark_triton.py:44-60)
+  prefill              second half of the metric: M=4096 TFLOP/s at K=N=4096 (the metric's shape) and 8192 (configs[2])
+  independent_launches supplementary: same 64 layers, same x for every call, 4 streams in one graph
+  reference_triton     the UNMODIFIED reference (baseline/_ref, Triton kernels) timed on this GPU on the same shapes by
+                       tools/ref_runner.py (child process): decode chained / flush, prefill -- the comparison
+                       `north_star` asks for.  {"unavailable": ...} when baseline/_ref is absent.
+  cpu_baseline         oracle/cpu_a16w4.c (gcc + OpenMP restatement, all host threads) on a bounded sample
 
-With --gpus N > 1 (torchrun): weak scaling -- every rank owns its own column shard (4096 columns)
-of LAYERS wide layers (global N = 4096*world), x replicated, and the step ends with ONE NCCL
-all-gather of the step's outputs; value = bytes of all ranks / max-over-ranks time.
+With --gpus N > 1 (torchrun): every layer is ONE wide layer (N_global = 4096 * world columns, K = 4096) sharded by
+output column with `ColumnShardedLinear`; a step = the 64 shard calls (same x) + ONE NCCL all-gather of the step's
+outputs, captured in the same CUDA graph when NCCL allows it; weak scaling (per-GPU work fixed), value = bytes of all
+ranks / max-over-ranks device time.  `mxfp4_sharded` adds BASELINE configs[4] (MXFP4 16384^2 split over the ranks).
 
---impl reference: times the CPU restatement of the reference path (oracle port: torch dequant +
-matmul, all host threads) on a bounded sample of the same workload, rank 0 only.
+--impl reference: the CPU arm (rank 0 only): oracle/cpu_a16w4.c on all host threads; a step = a bounded sample of the
+workload (SAMPLE_LAYERS distinct layers), K steps timed as asked.
 """
 import argparse
 import json
@@ -148,84 +152,120 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(self.rows), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
-def make_weights(dev, layers, seed=0):
+SAMPLE_LAYERS = 16            # CPU arm: distinct layers per step (143 MB of packed weights)
+
+
+def workload_config(world):
+    return {"workload": f"A16W4 gs={GROUP} decode M=1 K=N={K} fp16 (BASELINE configs[1]); step = {LAYERS} "
+                        f"{'chained layers' if world == 1 else 'column shards of wide layers (N_global=%d) + one NCCL all-gather' % (N * world)}",
+            "l2": f"{LAYERS} distinct layers = {LAYERS * ALGO_BYTES / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)",
+            "launch": "CUDA graph replay, programmatic dependent launch, layers linked in execution order",
+            "chain": ("independent layers (diagnostic)" if INDEPENDENT else "y_i feeds x_{i+1}") if world == 1 else "same x for every shard call",
+            "parallelism": f"column-shard x{world}",
+            "prefetch_hint_distance": int(os.environ.get("GEMLITE_B200_PREFETCH_DISTANCE", "2"))}
+
+
+def make_weights(dev, layers, seed=0, n_out=N):
     """Synthetic A16W4 layers (seeded, generated on the device). Scales are chosen so that a chained
     pass keeps |x| roughly constant: std(W) * sqrt(K) ~= 1."""
     g = torch.Generator(device=dev).manual_seed(seed)
-    out = []
     for _ in range(layers):
-        W_q = torch.randint(0, 16, (N, K), generator=g, device=dev, dtype=torch.int32).to(torch.uint8)
-        ng = N * K // GROUP
+        W_q = torch.randint(0, 16, (n_out, K), generator=g, device=dev, dtype=torch.int32).to(torch.uint8)
+        ng = n_out * K // GROUP
         scales = (torch.rand(ng, 1, generator=g, device=dev) * 0.002 + 0.0024).half()
         zeros = (torch.rand(ng, 1, generator=g, device=dev) * 3 + 6).half()
-        out.append((W_q, scales, zeros))
-    return out
+        yield W_q, scales, zeros
 
 
-def cpu_reference_sample(threads, seconds=10.0, max_calls=200):
-    """Oracle port (torch dequant + matmul, fp32) of one 4096^2 A16W4 layer on the host cores."""
-    from oracle import gemlite_oracle as O
-    torch.set_num_threads(threads)
-    g = torch.Generator().manual_seed(0)
-    W_q = torch.randint(0, 16, (N, K), generator=g, dtype=torch.int32).to(torch.uint8)
-    scales = (torch.rand(N * K // GROUP, 1, generator=g) * 0.002 + 0.0024).half()
-    zeros = (torch.rand(N * K // GROUP, 1, generator=g) * 3 + 6).half()
-    p = O.prepare(W_q, scales, zeros, W_nbits=4, group_size=GROUP, in_features=K, out_features=N)
-    Wp = p.W_q.contiguous()
-    x = (torch.randn(1, K, generator=g) / 10).half()
-    O.cpu_dequant_matmul(Wp, p.scales, p.zeros, x, GROUP)
-    t0 = time.perf_counter()
-    calls = 0
-    while calls < max_calls and (time.perf_counter() - t0) < seconds:
-        O.cpu_dequant_matmul(Wp, p.scales, p.zeros, x, GROUP)
-        calls += 1
-    dt = time.perf_counter() - t0
-    return ALGO_BYTES * calls / dt / 1e9, calls, dt
+# ------------------------------------------------------------------------------------------------------------------
+# CPU arm: oracle/cpu_a16w4.c (gcc + OpenMP), the only place outside tests/ and smoke() that executes oracle/ code
+# ------------------------------------------------------------------------------------------------------------------
+class CpuSample:
+    """SAMPLE_LAYERS distinct packed A16W4 layers in host memory + the C baseline bound to them."""
+
+    def __init__(self):
+        import numpy as np
+        from oracle import build_cpu
+        self.np, self.C = np, build_cpu
+        build_cpu.load()
+        rng = np.random.default_rng(0)
+        G = K // GROUP
+        self.layers = []
+        for _ in range(SAMPLE_LAYERS):
+            Wp = rng.integers(-2 ** 31, 2 ** 31 - 1, size=(K // 8, N), dtype=np.int64).astype(np.int32)   # 8 random codes per word
+            s = (rng.random((G, N), dtype=np.float32) * 0.002 + 0.0024).astype(np.float16).astype(np.float32)
+            z = (-(rng.random((G, N), dtype=np.float32) * 3 + 6) * s).astype(np.float16).astype(np.float32)    # z' = -z * s
+            self.layers.append((Wp, s, z))
+        self.x = (rng.standard_normal((1, K), dtype=np.float32) / 10).astype(np.float16).astype(np.float32)
+        self.threads = build_cpu.threads()
+
+    def step(self):
+        x = self.x
+        for (Wp, s, z) in self.layers:
+            y = self.C.forward(Wp, s, z, x)
+            x = (y / max(1e-6, float(self.np.abs(y).max())) / 10).astype(self.np.float32)   # keep the chain in range
+        return x
+
+    def timed(self, steps, warmup):
+        for _ in range(max(warmup, 1)):
+            self.step()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            self.step()
+        return (time.perf_counter() - t0) / steps
+
+
+def cpu_baseline_obj(steps=20, warmup=2):
+    try:
+        cs = CpuSample()
+        sec = cs.timed(steps, warmup)
+        v = SAMPLE_LAYERS * ALGO_BYTES / sec / 1e9
+        return {"value": v, "unit": "GB/s", "cores": cs.threads, "kind": "port",
+                "sample": f"{steps} steps x {SAMPLE_LAYERS} distinct 4096x4096 A16W4 layers (chained, M=1) through oracle/cpu_a16w4.c "
+                          f"(gcc -O3 + OpenMP, fp32, group-wise factorised dequant), {sec * 1e3 / SAMPLE_LAYERS:.3f} ms/layer",
+                "ms_per_layer": sec * 1e3 / SAMPLE_LAYERS}, sec
+    except Exception as e:
+        return {"value": 0.0, "unit": "GB/s", "cores": os.cpu_count() or 1, "kind": "port", "sample": f"failed: {e!r}"[:200]}, float("nan")
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    # a "step" = LAYERS layer calls; the CPU arm runs a bounded sample of it (calls are identical work)
-    per_step_calls = 4
-    vals = []
-    for _ in range(args.warmup):
-        cpu_reference_sample(threads, seconds=1.0, max_calls=per_step_calls)
-    t_all = time.perf_counter()
-    for _ in range(args.steps):
-        v, calls, dt = cpu_reference_sample(threads, seconds=30.0, max_calls=per_step_calls)
-        vals.append((v, dt / calls))
-    v = sum(a for a, _ in vals) / len(vals)
-    ms_call = 1e3 * sum(b for _, b in vals) / len(vals)
+    cs = CpuSample()
+    sec = cs.timed(args.steps, args.warmup)
+    v = SAMPLE_LAYERS * ALGO_BYTES / sec / 1e9
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_call * LAYERS, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"A16W4 gs={GROUP} decode M=1 K=N={K}, {LAYERS} layers/step "
-                               f"(CPU arm: {per_step_calls} layer calls sampled per step, extrapolated)"},
-        "cpu_baseline": {"value": v, "unit": "GB/s", "cores": threads, "kind": "port",
-                         "sample": f"{per_step_calls} calls/step x {args.steps} steps of torch unpack+dequant+matmul (fp32) "
-                                   f"on one 4096x4096 A16W4 layer, {ms_call:.1f} ms/call"},
+        "config": workload_config(world),
+        "cpu_baseline": {"value": v, "unit": "GB/s", "cores": cs.threads, "kind": "port",
+                         "sample": f"each step = {SAMPLE_LAYERS} of the {LAYERS} layers of the workload ({SAMPLE_LAYERS * ALGO_BYTES / 1e6:.0f} MB of "
+                                   f"distinct packed weights, chained, M=1) through oracle/cpu_a16w4.c (gcc -O3 + OpenMP, all host "
+                                   f"threads); {sec * 1e3 / SAMPLE_LAYERS:.3f} ms per 4096x4096 layer; value is a rate, so the sample size "
+                                   f"does not scale it"},
         "e2e": {"value": v, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
-def time_prefill(dev):
-    """Second half of the metric: M=4096 on K=N=8192 (configs[2]); returns dict or None if not available."""
+# ------------------------------------------------------------------------------------------------------------------
+# secondary legs (N = 1)
+# ------------------------------------------------------------------------------------------------------------------
+def time_prefill(dev, pk, pn, pm=4096):
+    """Second half of the metric: M=4096 TFLOP/s; flush protocol (256 MB between iterations), median of 10."""
     try:
         from gemlite_b200 import _cabi
         from gemlite_b200.helper import A16W4_HQQ_INT
         g = torch.Generator(device=dev).manual_seed(1)
-        W_q = torch.randint(0, 16, (PF_N, PF_K), generator=g, device=dev, dtype=torch.int32).to(torch.uint8)
-        ng = PF_N * PF_K // GROUP
+        W_q = torch.randint(0, 16, (pn, pk), generator=g, device=dev, dtype=torch.int32).to(torch.uint8)
+        ng = pn * pk // GROUP
         scales = (torch.rand(ng, 1, generator=g, device=dev) * 0.01 + 0.001).half()
         zeros = (torch.rand(ng, 1, generator=g, device=dev) * 15).half()
         layer = A16W4_HQQ_INT(device=dev, dtype=torch.float16).from_weights(W_q, scales, zeros)
         del W_q
-        x = (torch.randn(PF_M, PF_K, generator=g, device=dev) / 10).half()
-        y = layer(x)
+        x = (torch.randn(pm, pk, generator=g, device=dev) / 10).half()
+        layer(x)
         kern = _cabi.last_kernel()
         if kern == "generic_cuda_core":
             return {"available": False, "kernel": kern}
@@ -241,14 +281,73 @@ def time_prefill(dev):
             ts.append(a.elapsed_time(b))
         ts.sort()
         ms = ts[len(ts) // 2]
-        flops = 2.0 * PF_M * PF_K * PF_N
+        flops = 2.0 * pm * pk * pn
         peaks = measured_peaks()
         peak = peaks.get("bf16_tflops", 1590.0)
-        return {"available": True, "kernel": kern, "workload": f"A16W4 gs={GROUP} prefill M={PF_M} K=N={PF_K} fp16",
-                "ms": ms, "tflops": flops / ms / 1e9, "peak_tflops": peak,
-                "frac": flops / ms / 1e9 / peak, "l2": "256 MB flush between iterations"}
+        return {"available": True, "kernel": kern, "workload": f"A16W4 gs={GROUP} prefill M={pm} K=N={pk} fp16",
+                "ms": ms, "tflops": flops / ms / 1e9, "peak_tflops": peak, "frac": flops / ms / 1e9 / peak,
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops (cuBLAS burst)" if "bf16_tflops" in peaks else "fallback 1590",
+                "l2": "256 MB flush between iterations"}
     except Exception as e:  # keep the decode line alive, but say why
         return {"available": False, "error": repr(e)[:200]}
+
+
+def isolated_call(layer, x, dev, rep=100):
+    """What a caller outside a CUDA graph sees: one eager GemLiteLinear.__call__, cold L2, one event pair per call."""
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    ts = []
+    for _ in range(rep):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); layer(x); b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b) * 1e3)
+    ts.sort()
+    return {"us_min": ts[0], "us_median": ts[len(ts) // 2], "protocol": "256 MB L2 flush, event pair around one eager call "
+            "(examples/benchmark_triton.py:44-60); includes the host launch path"}
+
+
+def reference_triton_leg(budget_s=150.0):
+    """The unmodified reference's Triton kernels on this GPU (child process; baseline/_ref)."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref", "gemlite")
+    if not os.path.isdir(ref_dir):
+        return {"unavailable": "baseline/_ref/gemlite is absent (pip install --target baseline/_ref, DESIGN.md section 4)"}
+    import tempfile
+    I4 = dict(kind="pack_int", nbits=4, gs=GROUP, dtype="float16", seed=100)
+    timing = [
+        dict(name="decode_M1_4096", build=dict(I4, N=N, K=K), M=1, n_layers=LAYERS, chained=True, rep=100),
+        dict(name="prefill_M4096_4096", build=dict(I4, N=4096, K=4096), M=4096, n_layers=8, rep=20),
+        dict(name="prefill_M4096_8192", build=dict(I4, N=8192, K=8192), M=4096, n_layers=4, rep=20),
+    ]
+    tmp = tempfile.mkdtemp(prefix="bench_ref_")
+    job, out = os.path.join(tmp, "job.pt"), os.path.join(tmp, "out.pt")
+    torch.save({"cases": [], "timing": timing, "autotune": "fast", "budget_s": budget_s}, job)
+    env = dict(os.environ)
+    env.pop("PYTHONPATH", None)
+    t0 = time.time()
+    try:
+        subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ref_runner.py"), job, out], env=env, cwd=tmp,
+                       timeout=budget_s + 120, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    except subprocess.TimeoutExpired:
+        pass
+    if not os.path.exists(out):
+        return {"unavailable": "reference child produced no result (see tools/ref_runner.py)"}
+    r = torch.load(out, weights_only=False)
+    t = r["timing"]
+    res = {"version": r.get("version"), "triton": r.get("triton"), "autotune": "fast (the reference's default mode; no b200.json ships)",
+           "seconds": time.time() - t0, "protocols": "graph: distinct layers > L2 in one CUDA graph, ms per call; flush: eager call after a "
+           "256 MB L2 flush (the reference's own protocol)", "raw": t}
+    d = t.get("decode_M1_4096", {})
+    if "graph_chained_ms_per_layer" in d:
+        us = d["graph_chained_ms_per_layer"] * 1e3
+        res["decode"] = {"us_per_layer_chained_graph": us, "value": ALGO_BYTES / us / 1e3, "unit": "GB/s",
+                         "us_flush_median": d.get("flush_median_ms", 0) * 1e3}
+    for key, (pk, pn) in (("prefill_M4096_4096", (4096, 4096)), ("prefill_M4096_8192", (8192, 8192))):
+        d = t.get(key, {})
+        if "graph_ms_per_layer" in d:
+            res[key] = {"ms_graph": d["graph_ms_per_layer"], "ms_flush_median": d.get("flush_median_ms"),
+                        "tflops": 2.0 * 4096 * pk * pn / d["graph_ms_per_layer"] / 1e9}
+    return res
 
 
 def capture_independent(layers, x, n_streams, dev):
@@ -295,8 +394,7 @@ def time_graph_us_per_layer(graph, steps, n_layers):
 
 
 def independent_leg(layers, x, dev, peak, n_streams=4, steps=30):
-    """Supplementary number (never the headline): the same layers without the y -> x chain, on n_streams streams.
-    Shows what the decode kernel streams once the dependent-launch hand-off is off the critical path."""
+    """Supplementary number (never the headline): the same layers without the y -> x chain, on n_streams streams."""
     try:
         graph, keep = capture_independent(layers, x, n_streams, dev)
         us = time_graph_us_per_layer(graph, steps, len(layers))
@@ -308,34 +406,96 @@ def independent_leg(layers, x, dev, peak, n_streams=4, steps=30):
         return {"error": f"{type(e).__name__}: {str(e).splitlines()[0][:160] if str(e) else ''}"}
 
 
+def mxfp4_sharded_leg(dev, rank, world, steps=10):
+    """BASELINE configs[4]: MXFP4 gs=32 K=N=16384 column-sharded over the ranks (strong scaling: total work fixed),
+    kernel time and kernel + all-gather time at M=1 and M=4096, device-timed, max over ranks."""
+    import torch.distributed as dist
+    from gemlite_b200.helper import A16W4_MXFP
+    from gemlite_b200.sharding import ColumnShardedLinear
+    NK = 16384
+    out = {"workload": f"A16W4 MXFP4 gs=32 K=N={NK} bf16, {world} column shards", "per_M": {}}
+    try:
+        g = torch.Generator(device=dev).manual_seed(123)
+        n_loc = NK // world
+        # the shard of a layer whose codes / scales are random: generated shard-locally with a rank-dependent seed
+        W_q = torch.randint(0, 16, (n_loc, NK), generator=torch.Generator(device=dev).manual_seed(1000 + rank), device=dev, dtype=torch.uint8)
+        sc = torch.randint(118, 126, (n_loc, NK // 32), generator=g, device=dev, dtype=torch.uint8).view(torch.float8_e8m0fnu)
+        local = A16W4_MXFP(device=dev, dtype=torch.bfloat16).from_weights(W_q, sc)
+        del W_q
+        for M in (1, 4096):
+            x = (torch.randn(M, NK, device=dev, generator=g) / 10).bfloat16()
+            y = local(x)
+            gathered = torch.empty(world, M, n_loc, dtype=torch.bfloat16, device=dev)
+
+            def timed(with_gather):
+                for _ in range(3):
+                    yy = local(x)
+                    if with_gather:
+                        dist.all_gather_into_tensor(gathered.view(-1), yy.view(-1))
+                torch.cuda.synchronize(); dist.barrier()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(steps):
+                    yy = local(x)
+                    if with_gather:
+                        dist.all_gather_into_tensor(gathered.view(-1), yy.view(-1))
+                b.record(); torch.cuda.synchronize()
+                t = torch.tensor([a.elapsed_time(b) / steps], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                return t.item()
+
+            k_ms, kg_ms = timed(False), timed(True)
+            byts = (NK * NK // 2 + NK * NK // 32) / world
+            out["per_M"][str(M)] = {"kernel_ms": k_ms, "kernel_plus_gather_ms": kg_ms,
+                                    "per_gpu_weight_GBps": byts / k_ms / 1e6,
+                                    "aggregate_tflops": 2.0 * M * NK * NK / kg_ms / 1e9, "gather_bytes_per_rank": M * n_loc * 2}
+            del x, y, gathered
+    except Exception as e:
+        out["error"] = f"{type(e).__name__}: {str(e).splitlines()[0][:200] if str(e) else ''}"
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
-    from gemlite_b200 import _cabi
+    from gemlite_b200 import _cabi, link_layers
     from gemlite_b200.helper import A16W4_HQQ_INT
+    from gemlite_b200.sharding import ColumnShardedLinear
 
     dev = torch.device(f"cuda:{local_rank}")
     torch.cuda.set_device(dev)
     layers = []
-    for (W_q, scales, zeros) in make_weights(dev, 1 if ALIAS else LAYERS, seed=rank):
-        layers.append(A16W4_HQQ_INT(device=dev, dtype=torch.float16).from_weights(W_q, scales, zeros))
-        del W_q
-    if ALIAS:
-        layers = layers * LAYERS
+    if world == 1:
+        for (W_q, scales, zeros) in make_weights(dev, 1 if ALIAS else LAYERS, seed=0):
+            layers.append(A16W4_HQQ_INT(device=dev, dtype=torch.float16).from_weights(W_q, scales, zeros))
+            del W_q
+        if ALIAS:
+            layers = layers * LAYERS
+    else:
+        # ONE wide layer per step position (same seed on every rank => the same global weights), sharded by output column
+        for (W_q, scales, zeros) in make_weights(dev, LAYERS, seed=0, n_out=N * world):
+            full = A16W4_HQQ_INT(device=dev, dtype=torch.float16).from_weights(W_q, scales, zeros)
+            del W_q, scales, zeros
+            layers.append(ColumnShardedLinear(full, rank, world).local)
+            del full
+        torch.cuda.empty_cache()
+    link_distance = int(os.environ.get("GEMLITE_B200_PREFETCH_DISTANCE", "2"))
+    if not ALIAS:
+        link_layers(layers, link_distance)
     torch.cuda.synchronize()
     x0 = (torch.randn(1, K, device=dev, generator=torch.Generator(device=dev).manual_seed(7)) / 10).half()
     x_in = x0.clone()          # static input buffer of the captured step (the e2e leg copies host data into it)
 
-    # device-resident step: chained decode pass (N=1) or independent shards of wide layers + one all-gather
     outs = torch.empty(LAYERS, 1, N, dtype=torch.float16, device=dev)
     gathered = torch.empty(world * LAYERS, 1, N, dtype=torch.float16, device=dev) if world > 1 else None
 
-    def step_body():
+    def step_body(with_gather):
         x = x_in
         if world > 1:
-            # shard outputs are collected for the single gather with ONE concatenation at the end of the step (a copy
-            # per layer would put a non-PDL kernel between every two decode launches)
             ys = [layer(x) for layer in layers]
-            torch.stack(ys, out=outs)
+            torch.stack(ys, out=outs)            # one concatenation at the end: no foreign kernel between decode launches
+            if with_gather:
+                dist.all_gather_into_tensor(gathered.view(-1), outs.view(-1))
             return outs
         for layer in layers:
             y = layer(x)
@@ -343,21 +503,35 @@ def run_ours(args, rank, world, local_rank):
                 x = y
         return x
 
-    # warm up eagerly (module load, smem opt-in), then capture the step in a CUDA graph
+    # warm up eagerly (module load, smem opt-in, NCCL communicator), then capture the step in a CUDA graph
     for _ in range(2):
-        step_body()
+        step_body(True)
     torch.cuda.synchronize()
-    graph = torch.cuda.CUDAGraph()
     stream = torch.cuda.Stream(device=dev)
-    with torch.cuda.stream(stream):
-        step_body()
-        torch.cuda.synchronize()
-        with torch.cuda.graph(graph, stream=stream):
-            result = step_body()
+    gather_in_graph = False
+
+    def capture(with_gather):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(stream):
+            step_body(with_gather)
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g, stream=stream):
+                r = step_body(with_gather)
+        return g, r
+
+    if world > 1:
+        try:
+            graph, result = capture(True)
+            gather_in_graph = True
+        except Exception:
+            torch.cuda.synchronize()
+            graph, result = capture(False)
+    else:
+        graph, result = capture(False)
 
     def one_step():
         graph.replay()
-        if world > 1:
+        if world > 1 and not gather_in_graph:
             dist.all_gather_into_tensor(gathered.view(-1), outs.view(-1))
 
     for _ in range(max(args.warmup, 3)):
@@ -383,11 +557,18 @@ def run_ours(args, rank, world, local_rank):
     ms_step = ms_total / args.steps
     value = world * LAYERS * ALGO_BYTES / (ms_step * 1e-3) / 1e9
 
-    # kernel-only time inside the step (graph replay without the gather), for the roofline object
+    # kernel-only time inside the step (the decode launches without the gather), for the roofline object
+    if world > 1 and gather_in_graph:
+        kgraph, _ = capture(False)
+    else:
+        kgraph = graph
+    for _ in range(3):
+        kgraph.replay()
+    torch.cuda.synchronize()
     evk0, evk1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     evk0.record()
     for _ in range(args.steps):
-        graph.replay()
+        kgraph.replay()
     evk1.record()
     torch.cuda.synchronize()
     us_per_launch = evk0.elapsed_time(evk1) * 1e3 / (args.steps * LAYERS)
@@ -399,9 +580,8 @@ def run_ours(args, rank, world, local_rank):
 
     def e2e_graph_step():
         x_in.copy_(xh, non_blocking=True)
-        graph.replay()
+        one_step()
         if world > 1:
-            dist.all_gather_into_tensor(gathered.view(-1), outs.view(-1))
             yh.copy_(gathered[-1], non_blocking=True)
         else:
             yh.copy_(y_static, non_blocking=True)
@@ -433,47 +613,56 @@ def run_ours(args, rank, world, local_rank):
     eager_launches = _cabi.launch_count() - l0
     e2e_val = world * LAYERS * ALGO_BYTES / e2e_s / 1e9
     eager_val = LAYERS * ALGO_BYTES / eager_s / 1e9 if world == 1 else None
+    skip = os.environ.get("BENCH_SKIP_EXTRAS", "0") == "1"     # diagnostic sweeps only
+    mx_sharded = mxfp4_sharded_leg(dev, rank, world) if (world > 1 and not skip) else None
 
     if rank != 0:
         return
     peaks = measured_peaks()
     peak = peaks.get("hbm_gbs", 6650.0)
     achieved = ALGO_BYTES / (us_per_launch * 1e-6) / 1e9
-    traffic = None
+    traffic, traffic_src = None, None
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "decode_traffic.json")))
         traffic = prof.get("dram_bytes_per_launch")
+        traffic_src = prof.get("source", "profiles/decode_traffic.json (ncu --set full capture, not re-measured by this run)")
     except Exception:
         pass
-    skip = os.environ.get("BENCH_SKIP_EXTRAS", "0") == "1"     # diagnostic sweeps only
-    # the CPU baseline is reported at N = 1 only (rank 0); multi-GPU runs do not repeat it
-    cpu_v, cpu_calls, cpu_dt = (0.0, 0, 0.0) if (skip or world > 1) else cpu_reference_sample(os.cpu_count() or 1, seconds=12.0, max_calls=100)
-    prefill = time_prefill(dev) if (world == 1 and not skip) else None
+    cpu_obj = None
+    if world == 1 and not skip:
+        cpu_obj, _ = cpu_baseline_obj()
+    prefill = None
+    if world == 1 and not skip:
+        prefill = time_prefill(dev, PF_K, PF_N)
+        prefill["at_4096"] = time_prefill(dev, 4096, 4096)
     independent = independent_leg(layers, x0, dev, peak) if (world == 1 and not skip and not ALIAS) else None
+    isolated = isolated_call(layers[0], x0, dev) if (world == 1 and not skip) else None
+    ref_triton = reference_triton_leg() if (world == 1 and not skip and os.environ.get("BENCH_SKIP_REFERENCE_TRITON", "0") != "1") else None
+    cfg = workload_config(world)
+    handoff = {"handoff": "griddepcontrol.wait (programmatic dependent launch); a device-side arrival counter was measured slower (DESIGN.md 3.3)"}
+    if world > 1:
+        handoff["gather"] = "NCCL all-gather captured in the step's CUDA graph" if gather_in_graph else "NCCL all-gather issued eagerly after the graph replay"
     line = {
         "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
-        "data": "synthetic",
-        "config": {"workload": f"A16W4 gs={GROUP} decode M=1 K=N={K} fp16 (BASELINE configs[1]); step = {LAYERS} "
-                               f"{'chained layers' if world == 1 else 'column shards (N_global=%d) + one NCCL all-gather' % (N * world)}",
-                   "l2": f"{LAYERS} distinct layers = {LAYERS * ALGO_BYTES / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)",
-                   "launch": "CUDA graph replay, programmatic dependent launch", "chain": "independent layers (diagnostic)" if INDEPENDENT else "y_i feeds x_{i+1}", "parallelism": f"column-shard x{world}"},
+        "data": "synthetic", "config": cfg,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "gemv_w4_tma_kernel", "us_per_launch": us_per_launch,
-                     "algorithmic_bytes_per_launch": ALGO_BYTES,
+                     "traffic": traffic, "traffic_source": traffic_src, "kernel": _cabi.last_kernel() if world > 1 else "gemv_w4_m1_kernel",
+                     "us_per_launch": us_per_launch, "algorithmic_bytes_per_launch": ALGO_BYTES,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650"},
-        "cpu_baseline": ({"value": cpu_v, "unit": "GB/s", "cores": os.cpu_count() or 1, "kind": "port",
-                          "sample": f"{cpu_calls} calls of torch unpack+dequant+matmul (fp32) on one 4096x4096 A16W4 layer in {cpu_dt:.1f} s"}
-                         if world == 1 else None),
+        "cpu_baseline": cpu_obj,
         "e2e": {"value": e2e_val, "unit": "GB/s", "h2d_bytes_per_step": 2 * K, "d2h_bytes_per_step": 2 * N,
                 "ms_per_step": e2e_s * 1e3,
                 "path": "pinned host x -> device, CUDA-graph replay of the 64 GemLiteLinear.__call__s, y -> pinned host, synchronize",
                 "eager_value": eager_val, "eager_ms_per_step": (eager_s * 1e3 if world == 1 else None),
                 "eager_path": "same, one eager Python -> C-ABI call per layer"},
-        "gpu_launches": args.steps * LAYERS, "gpu_launches_e2e_eager": int(eager_launches),
+        "gpu_launches": args.steps * LAYERS, "gpu_launches_e2e_eager": int(eager_launches), "decode_handoff": handoff,
         "clocks": clocks.summary(),
         "prefill": prefill,
+        "isolated_call": isolated,
         "independent_launches": independent,
+        "reference_triton": ref_triton,
+        "mxfp4_sharded": mx_sharded,
     }
     print(json.dumps(line), flush=True)
 
@@ -489,9 +678,6 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        if args.steps > 5:
-            args.steps = 5      # bounded CPU sample
-        args.warmup = min(args.warmup, 1)
         run_reference(args, rank, world)
         return
     if world > 1:

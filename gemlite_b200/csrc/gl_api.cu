@@ -19,7 +19,6 @@ static thread_local char tl_error[512] = "";
 static thread_local const char* tl_kernel = "";
 static std::atomic<uint64_t> g_launches{0};
 std::atomic<int> g_pdl_enabled{1};
-std::atomic<uint64_t> g_chained_launches{0};
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -197,10 +196,14 @@ extern "C" int glb_version(void) { return GLB_ABI_VERSION; }
 extern "C" const char* glb_last_error(void) { return tl_error; }
 extern "C" const char* glb_last_kernel(void) { return tl_kernel; }
 extern "C" uint64_t glb_launch_count(void) { return g_launches.load(); }
-extern "C" uint64_t glb_chained_launch_count(void) { return g_chained_launches.load(); }
 extern "C" void glb_set_pdl(int enabled) { g_pdl_enabled.store(enabled ? 1 : 0); }
 extern "C" int glb_get_pdl(void) { return g_pdl_enabled.load(); }
 extern "C" int glb_debug_timeline(unsigned long long* out, int max_words) { return debug_read_timeline(out, max_words); }
+
+extern "C" int glb_prefetch_hint(const glb_linear* layer, const glb_linear* next) {
+  GLB_REQUIRE(layer != nullptr && layer->W_q != nullptr, GLB_ERR_INVALID, "glb_prefetch_hint: layer is NULL");
+  return set_prefetch_hint(*layer, next);
+}
 
 extern "C" unsigned long long glb_stream_capture_id(void* stream_) {
   cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
@@ -220,6 +223,7 @@ extern "C" size_t glb_workspace_bytes(const glb_linear* L, int64_t M, int matmul
   const bool gemv_name = (matmul_type <= GLB_MM_GEMV_SPLITK);
   const bool can_gemv = gemv_supported(*L, M), can_tc = gemm_tc_supported(*L, M);
   if (can_gemv && (gemv_name || (was_auto && M <= 16) || !can_tc)) return gemv_workspace(*L, M);
+  if ((was_auto || matmul_type != GLB_MM_GEMM) && gemm_mid_supported(*L, M)) return 0;
   if (can_tc) return gemm_tc_workspace(*L, M);
   return 0;
 }
@@ -252,6 +256,9 @@ extern "C" int glb_matmul(const glb_linear* L, const void* x, const void* scales
     return launch_gemv_a8(*L, x, sx, y, M, bias, stream);
   const bool prefer_gemv = can_gemv && (gemv_name || (was_auto && M <= 16) || !can_tc);
   if (prefer_gemv) return launch_gemv(*L, x, sx, y, M, bias, workspace, workspace_bytes, stream);
+  // 1b. batched decode, 16 < M <= 128 (the reference's GEMM_SPLITK range and the bottom of its GEMM range): streaming
+  //     mma.sync kernel (gl_gemm_mid.cu); an explicit "GEMM" request keeps the tcgen05 kernel
+  if ((was_auto || matmul_type != GLB_MM_GEMM) && gemm_mid_supported(*L, M)) return launch_gemm_mid(*L, x, y, M, bias, stream);
   if (can_tc) {
     const size_t need = gemm_tc_workspace(*L, M);
     GLB_REQUIRE(need == 0 || (workspace && workspace_bytes >= need), GLB_ERR_WORKSPACE,

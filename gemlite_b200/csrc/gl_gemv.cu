@@ -35,6 +35,36 @@
 namespace glb {
 namespace {
 
+// ---- L2 prefetch hints: layer (keyed by its W_q pointer) -> byte ranges of a layer that runs later ----
+struct PfHint { const void* ptr[3]; unsigned long long bytes[3]; };
+std::mutex g_pf_mu;
+std::unordered_map<const void*, PfHint> g_pf;
+
+// this CTA's contiguous 1/gridDim share of each hinted range -> cp.async.bulk.prefetch.L2, pieces of <= 4 KB per lane
+__device__ __forceinline__ void l2_prefetch_share(const unsigned char* const (&ptr)[3], const unsigned long long (&bytes)[3], int lane) {
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const unsigned long long total = bytes[a];
+    if (total == 0) continue;
+    unsigned long long share = ((total + gridDim.x - 1) / gridDim.x + 15ull) & ~15ull;
+    const unsigned long long beg = share * blockIdx.x;
+    if (beg >= total) continue;
+    if (beg + share > total) share = (total - beg) & ~15ull;
+    for (unsigned long long off = (unsigned long long)lane * 4096ull; off < share; off += 32ull * 4096ull) {
+      const unsigned long long n = (share - off < 4096ull) ? (share - off) : 4096ull;
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr[a] + beg + off), "r"((unsigned int)n) : "memory");
+    }
+  }
+}
+inline void fill_prefetch_hint(const void* wq, const unsigned char* (&ptr)[3], unsigned long long (&bytes)[3]) {
+  for (int a = 0; a < 3; ++a) { ptr[a] = nullptr; bytes[a] = 0; }
+  std::lock_guard<std::mutex> lk(g_pf_mu);
+  if (g_pf.empty()) return;
+  auto it = g_pf.find(wq);
+  if (it != g_pf.end())
+    for (int a = 0; a < 3; ++a) { ptr[a] = reinterpret_cast<const unsigned char*>(it->second.ptr[a]); bytes[a] = it->second.bytes[a]; }
+}
+
 constexpr int GV_THREADS = 256;
 constexpr int GV_WARPS = 8;
 constexpr int GV_COLS = 32;        // columns per cluster
@@ -460,6 +490,8 @@ struct GemvTmaParams {
   int chunk_shift;       // log2(rows per weight chunk)
   int debug;             // diagnostics only: bit 0 skip the main loop, bit 1 skip the weight copies
   int issue_mode;        // who issues the TMA copies (see the kernel)
+  const unsigned char* pf_ptr[3];      // L2 prefetch hint (glb_prefetch_hint), as in gemv_w4_m1_kernel
+  unsigned long long pf_bytes[3];
 };
 
 constexpr int GT_GPW = 4;    // META_REGS: groups a warp may own (their scale / zero vectors live in registers)
@@ -571,6 +603,7 @@ gemv_w4_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
       }
     }
   }
+  if (warp == 1) l2_prefetch_share(P.pf_ptr, P.pf_bytes, lane);
   if (P.late_trigger == 0) pdl_launch_dependents();  // everything this CTA can do ahead of its input has been issued
 #if GLB_GEMV_PREWAIT_ALL
   {
@@ -795,6 +828,7 @@ int launch_w4_tma(const glb_linear& L, const GemvParams& P0, int late_trigger, c
   P.bulk1d = late_trigger / 10;
   P.W = reinterpret_cast<const uint32_t*>(L.W_q);
   P.scales = P0.scales; P.zeros = P0.zeros;
+  fill_prefetch_hint(L.W_q, P.pf_ptr, P.pf_bytes);
   {
     int cr = rows_c / nch, sh = 0;
     while ((1 << sh) < cr) ++sh;
@@ -834,43 +868,37 @@ int launch_w4_tma(const glb_linear& L, const GemvParams& P0, int late_trigger, c
 
 
 // =================================================================================================
-// M == 1 decode kernel, round 2 ("v7"): same slab / TMA / swizzle scheme as gemv_w4_tma_kernel, rebuilt around the
-// two things the round-1 timeline showed on the critical path of a CHAIN of dependent layers
-// (profiles/decode_timeline_v52_r1.txt): the kernel-boundary hand-off (1.0-1.25 us) and a post-wait path of
-// ~2.3 us (block-wide x staging + barrier 0.85, main loop 1.45 at ~215 issued instructions per group and warp).
-//   * hand-off: when the library can PROVE during stream capture that this launch's x is the y of the decode launch
-//     captured right before it (cudaStreamGetCaptureInfo: the stream's only dependency is that kernel node), the
-//     consumer does not wait for kernel completion (griddepcontrol.wait) but for an arrival counter: every producer
-//     CTA stores its 32 outputs, fences, and adds 1 to a flag word; one thread per consumer CTA spins on
-//     ld.acquire.gpu until all producer CTAs have arrived.  griddepcontrol.wait is still executed before the kernel
-//     exits, so completion stays transitive along the stream.  Eager launches (and anything the library cannot prove
-//     adjacent) use griddepcontrol.wait as before.
-//   * x staging is per warp: a warp only ever touches the x words of its own groups, so it loads them itself
-//     (one 16-byte word per lane and group), permutes / pre-scales them in registers, reduces the group sums with
-//     shuffles and parks the words in its private rows of the x buffer -- no block barrier between the hand-off and
-//     the first HMMA.
-//   * main loop: two accumulator chains per group, the nibble shift on the FMA pipe (mul.hi), x fragments only in
-//     the 4 lanes of token 0, scale / zero vectors read once per group; all mbarrier waits are taken BEFORE the
-//     hand-off (in a chain the copies landed long ago), so the loop holds no polls.
+// M == 1 decode kernel, round 2 ("v7"): same slab / TMA / swizzle scheme as gemv_w4_tma_kernel with
+//   * per-warp x staging: a warp only ever touches the x words of its own groups, so it loads them itself (one
+//     16-byte word per lane and group), permutes / pre-scales them in registers, reduces the group sums with shuffles
+//     and parks the words in its private rows of the x buffer -- no block barrier between the hand-off and the first HMMA;
+//   * a leaner main loop (profiles/decode_v7_r2.txt): two accumulator chains per group, the nibble shift on the FMA pipe
+//     (mul.hi), x fragments only in the 4 lanes of token 0: ~148 issued instructions per group and warp instead of ~215;
+//   * an L2 prefetch hint: the CTAs also ask the L2 for their share of the tensors of the layer that will run a couple
+//     of launches later (glb_prefetch_hint), so that a just-launched CTA fills its shared memory from the L2 instead of
+//     waiting for HBM -- in a chain of dependent launches only ONE later layer can be resident per SM, and its
+//     launch -> first-byte latency otherwise bounds the chain's period.
+// Nothing spins before griddepcontrol.wait (the co-resident CTA of the previous layer is in its main loop then).
+// Tried on hardware in round 2 and removed (profiles/decode_experiments_r2.txt): a device-side arrival counter instead
+// of griddepcontrol.wait for provably adjacent launches (store y -> fence -> red / ld.acquire polling): 2.50 us per
+// EMPTY chained launch against 1.66 us with the kernel-boundary hand-off -- the hardware path is faster than two L2
+// round trips plus a gpu-scope fence.
 // =================================================================================================
 struct GemvM1Params {
   const void* x; void* y; const void* bias;
   int K, N, group_size, mode;
-  unsigned int* flag_in;     // producer's arrival counter (null: griddepcontrol.wait)
-  unsigned int expect;       // producer CTAs
-  unsigned int* flag_out;    // this launch's arrival counter (null: do not publish)
   int trigger;               // dependents are signalled 0: at kernel start, 2: right after the hand-off
-  int debug;                 // bit 0: skip main loop, bit 1: skip weight copies (timing experiments only)
+  int debug;                 // bit 0: skip main loop, bit 1: skip weight copies, bit 2: timeline stamps (diagnostics)
+  int chunk_shift;           // log2(packed rows per weight chunk)
+  // L2 prefetch hint (glb_prefetch_hint): tensors of the layer that will run `distance` launches after this one.
+  // Every CTA asks the L2 for its 1/gridDim share of each range (cp.async.bulk.prefetch.L2), before the hand-off.
+  const unsigned char* pf_ptr[3];
+  unsigned long long pf_bytes[3];
 };
 
 constexpr int M1_NW = 16;
 constexpr int M1_MAXGPW = 8;     // groups per warp (K / group_size / 16)
 
-__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 __device__ __forceinline__ uint4 ld_relaxed_gpu_v4(const void* p) {
   uint4 r;
   asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
@@ -897,18 +925,17 @@ gemv_w4_m1_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   unsigned char* zbuf = sbuf + meta_bytes;
   unsigned char* xs = zbuf + meta_bytes;                                 // rows x 16 B: permuted x words (warp-private rows)
   float* red = reinterpret_cast<float*>(xs + (size_t)rows * 16);         // [M1_NW][32]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(red + M1_NW * GV_COLS);   // [GT_NCH] weights, [1] metadata, [1] hand-off result
-  volatile unsigned int* okw = reinterpret_cast<volatile unsigned int*>(&bars[GT_NCH + 1]);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(red + M1_NW * GV_COLS);   // [GT_NCH] weights, [1] metadata
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g8 = lane >> 2, t4 = lane & 3;
 
+  // diagnostics (GLB_GEMV_DEBUG bit 2): %globaltimer phase stamps of thread 0 of the first / last CTA
+  const bool rec = (P.debug & 4) && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1);
+  unsigned long long ts[8];
+  if (rec) ts[0] = gtimer();
   // ---- 1. everything that does not depend on the previous layer ----
   if (threadIdx.x == 0) {
-    if (P.flag_out) {                      // fresh counter for this launch; visible before any dependent can start
-      *reinterpret_cast<volatile unsigned int*>(P.flag_out) = 0u;
-      __threadfence();
-    }
     ptx::prefetch_tmap(&tmap_w);
     ptx::prefetch_tmap(&tmap_s);
     for (int c = 0; c <= GT_NCH; ++c) ptx::mbar_init(&bars[c], 1);
@@ -922,28 +949,15 @@ gemv_w4_m1_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       ptx::tma_load_2d(wbuf + (size_t)c * chunk_rows * 128, &tmap_w, &bars[c], col0, c * chunk_rows);
     }
   }
+  if (warp == 1) l2_prefetch_share(P.pf_ptr, P.pf_bytes, lane);
+  if (rec) ts[1] = gtimer();                         // copies issued
   if (P.trigger == 0) pdl_launch_dependents();
   __syncthreads();                                   // barrier initialisation visible to every thread
-  ptx::mbar_wait(&bars[GT_NCH], 0);
-  if (!(P.debug & 2))
-    for (int c = 0; c < nch; ++c) ptx::mbar_wait(&bars[c], 0);
 
   // ---- 2. hand-off: the previous layer's y is this layer's x ----
-  bool flagged = false;
-  if (P.flag_in) {
-    if (threadIdx.x == 0) {
-      const unsigned long long t0 = gtimer();
-      unsigned int ok = 0, spins = 0;
-      while (true) {
-        if (ld_acquire_gpu(P.flag_in) >= P.expect) { ok = 1; break; }
-        if ((++spins & 63u) == 0u && gtimer() - t0 > 200000ull) break;   // 200 us: a lost arrival only costs the fallback below
-      }
-      *okw = ok;
-    }
-    __syncthreads();
-    flagged = (*okw != 0u);
-  }
-  if (!flagged) pdl_wait_prior_grids();
+  if (rec) ts[2] = gtimer();
+  pdl_wait_prior_grids();
+  if (rec) ts[3] = gtimer();                         // hand-off done
   if (P.trigger == 2) pdl_launch_dependents();
 
   // ---- 3. this warp's x words: load, permute, pre-scale, group sums ----
@@ -985,6 +999,7 @@ gemv_w4_m1_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     }
   }
   __syncwarp();
+  if (rec) ts[4] = gtimer();                         // x staged (warp 0)
 
   // ---- 4. main loop ----
   float out[4] = {0.f, 0.f, 0.f, 0.f};
@@ -992,10 +1007,12 @@ gemv_w4_m1_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   const unsigned char* xb = xs + (2 * t4) * 16;
   const unsigned char* wl = wbuf + (2 * t4) * 128;
   const int sw0 = (g8 ^ (2 * t4)) << 4, sw1 = (g8 ^ (2 * t4 + 1)) << 4;
+  ptx::mbar_wait(&bars[GT_NCH], 0);                  // scales / zeros landed (long ago, in a chain)
 #pragma unroll
   for (int gi = 0; gi < GPW; ++gi) {
     const int gl = warp + M1_NW * gi;
     if (gl >= ((P.debug & 1) ? 0 : G)) break;
+    if (!(P.debug & 2)) ptx::mbar_wait(&bars[(gl * rpg) >> P.chunk_shift], 0);   // this group's weight chunk landed
     float dacc[2][4];
 #pragma unroll
     for (int pr = 0; pr < 2; ++pr) dacc[pr][0] = dacc[pr][1] = dacc[pr][2] = dacc[pr][3] = 0.f;
@@ -1036,7 +1053,8 @@ gemv_w4_m1_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     }
   }
 
-  // ---- 5. cross-warp reduction, bias, store, publish ----
+  // ---- 5. cross-warp reduction, bias, store ----
+  if (rec) ts[5] = gtimer();                         // loop done (warp 0)
   if (t4 == 0) {
 #pragma unroll
     for (int c = 0; c < 4; ++c) red[warp * GV_COLS + 4 * g8 + c] = out[c];
@@ -1048,13 +1066,16 @@ gemv_w4_m1_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     for (int w = 0; w < M1_NW; ++w) v += red[w * GV_COLS + threadIdx.x];
     if (P.bias) v = rnd_out<BF16>(v) + cvt_meta<BF16>(reinterpret_cast<const uint16_t*>(P.bias)[col0 + threadIdx.x]);
     st_out<BF16>(P.y, (int64_t)col0 + threadIdx.x, v);
-    if (P.flag_out) {
-      __threadfence();                                // each lane's store is performed gpu-wide ...
-      __syncwarp();
-      if (threadIdx.x == 0) asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(P.flag_out) : "memory");   // ... before the arrival
+  }
+  if (rec) {
+    ts[6] = gtimer();
+    ts[7] = ts[0];
+    const unsigned int pos = atomicAdd(&g_timeline_pos, 1u);
+    if (pos < 8192 / 9) {
+      g_timeline[pos * 9] = blockIdx.x;
+      for (int k = 0; k < 8; ++k) g_timeline[pos * 9 + 1 + k] = ts[k];
     }
   }
-  if (flagged) pdl_wait_prior_grids();                // kernel completion stays transitive along the stream
 }
 
 template <int GPW> size_t gemv_m1_smem_bytes(int K, int group_size) {
@@ -1069,33 +1090,14 @@ bool gemv_m1_ok(const GemvParams& P) {
   if (rows * 128 > 64 * 1024 || rows < 32) return false;
   if (G > M1_NW * M1_MAXGPW || G > 256) return false;
   const int nch = (rows % (GT_NCH * rpg) == 0 && rows / GT_NCH >= 8) ? GT_NCH : 1;
-  if (rows / nch > 256 || (rows / nch) % 8 != 0) return false;
+  const int cr = rows / nch;
+  if (cr > 256 || cr % 8 != 0 || (cr & (cr - 1)) != 0 || cr % rpg != 0) return false;   // chunk index is a shift; whole groups per chunk
   if (rpg % 8 != 0 || rpg > 32) return false;           // swizzled 8-row blocks must not straddle groups
   return true;
 }
 
-// ---- per-stream chain tracking: which decode launch was captured last, and where it publishes ----
-constexpr int M1_SLOTS = 16;
-constexpr size_t M1_SLOT_BYTES = 128;
-constexpr size_t M1_FLAG_OFFSET = 64 * 1024 - M1_SLOTS * M1_SLOT_BYTES;   // tail of the workspace's counter region
-struct ChainState {
-  unsigned long long capture_id = 0;
-  cudaGraphNode_t node = nullptr;
-  const void* y = nullptr;
-  int N = 0, slot = -1;
-  unsigned int grid = 0;
-  const void* ws = nullptr;
-};
-std::mutex g_chain_mu;
-std::unordered_map<cudaStream_t, ChainState> g_chain;
-int chain_mode() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("GLB_GEMV_FLAGS"); v = e ? atoi(e) : 1; }
-  return v;
-}
-
 template <bool BF16, int RPG, bool FAST, int GPW>
-int launch_w4_m1(const glb_linear& L, const GemvParams& P0, void* workspace, size_t ws_bytes, cudaStream_t stream) {
+int launch_w4_m1(const glb_linear& L, const GemvParams& P0, cudaStream_t stream) {
   const int rows = P0.K / 8, G = P0.K / P0.group_size;
   constexpr int rpg = RPG * 4;
   const int nch = (rows % (GT_NCH * rpg) == 0 && rows / GT_NCH >= 8) ? GT_NCH : 1;
@@ -1108,50 +1110,27 @@ int launch_w4_m1(const glb_linear& L, const GemvParams& P0, void* workspace, siz
   if (rc != GLB_OK) return rc;
   GemvM1Params P;
   P.x = P0.x; P.y = P0.y; P.bias = P0.bias; P.K = P0.K; P.N = P0.N; P.group_size = P0.group_size; P.mode = P0.mode;
-  P.flag_in = nullptr; P.expect = 0; P.flag_out = nullptr;
+  fill_prefetch_hint(L.W_q, P.pf_ptr, P.pf_bytes);
   {
     static int dbg = -1, trig = -1;
     if (dbg < 0) { const char* e = getenv("GLB_GEMV_DEBUG"); dbg = e ? atoi(e) : 0; }
     if (trig < 0) { const char* e = getenv("GLB_GEMV_TRIGGER"); trig = e ? atoi(e) : 2; }
     P.debug = dbg; P.trigger = trig;
-  }
-  const unsigned int grid = (unsigned)(P0.N / GV_COLS);
-  // Flag hand-off only inside a stream capture, where adjacency can be proven from the capture's dependency set.
-  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
-  unsigned long long cap_id = 0;
-  const cudaGraphNode_t* deps = nullptr;
-  size_t ndeps = 0;
-  bool capturing = false;
-  const bool pdl = g_pdl_enabled.load() != 0;
-  if (chain_mode() && pdl && workspace && ws_bytes >= 64 * 1024 &&
-      cudaStreamGetCaptureInfo_v3(stream, &st, &cap_id, nullptr, &deps, nullptr, &ndeps) == cudaSuccess)
-    capturing = (st == cudaStreamCaptureStatusActive);
-  else
-    cudaGetLastError();
-  int slot = -1;
-  if (capturing) {
-    std::lock_guard<std::mutex> lk(g_chain_mu);
-    ChainState& cs = g_chain[stream];
-    unsigned int* flags = reinterpret_cast<unsigned int*>(reinterpret_cast<unsigned char*>(workspace) + M1_FLAG_OFFSET);
-    if (cs.capture_id == cap_id && cs.node != nullptr && ndeps == 1 && deps[0] == cs.node && cs.y == P0.x &&
-        cs.N == P0.K && cs.ws == workspace && cs.slot >= 0) {
-      P.flag_in = flags + (size_t)cs.slot * (M1_SLOT_BYTES / 4);
-      P.expect = cs.grid;
-    }
-    slot = (cs.capture_id == cap_id) ? (cs.slot + 1) % M1_SLOTS : 0;
-    P.flag_out = flags + (size_t)slot * (M1_SLOT_BYTES / 4);
+    int cr = rows / nch, sh = 0;
+    while ((1 << sh) < cr) ++sh;
+    P.chunk_shift = sh;
   }
   const size_t smem = gemv_m1_smem_bytes<GPW>(P0.K, P0.group_size);
   auto kern = gemv_w4_m1_kernel<BF16, RPG, FAST, GPW>;
   if (smem > 48 * 1024) GLB_ENSURE_SMEM(kern, smem);
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid);
+  cfg.gridDim = dim3((unsigned)(P0.N / GV_COLS));
   cfg.blockDim = dim3(M1_NW * 32);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   int na = 0;
-  if (pdl) {
+  if (g_pdl_enabled.load()) {
     attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[na].val.programmaticStreamSerializationAllowed = 1;
     ++na;
@@ -1160,19 +1139,6 @@ int launch_w4_m1(const glb_linear& L, const GemvParams& P0, void* workspace, siz
   cfg.numAttrs = na;
   GLB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tw, ts, tz, P));
   count_launch();
-  if (P.flag_in) g_chained_launches.fetch_add(1, std::memory_order_relaxed);
-  if (capturing) {
-    // the node this launch became = the stream's only dependency now
-    std::lock_guard<std::mutex> lk(g_chain_mu);
-    ChainState& cs = g_chain[stream];
-    cs = ChainState();
-    if (cudaStreamGetCaptureInfo_v3(stream, &st, &cap_id, nullptr, &deps, nullptr, &ndeps) == cudaSuccess &&
-        st == cudaStreamCaptureStatusActive && ndeps == 1) {
-      cs.capture_id = cap_id; cs.node = deps[0]; cs.y = P0.y; cs.N = P0.N; cs.slot = slot; cs.grid = grid; cs.ws = workspace;
-    } else {
-      cudaGetLastError();
-    }
-  }
   return GLB_OK;
 }
 
@@ -1219,10 +1185,10 @@ int dispatch_w4(const glb_linear& L, const GemvParams& P, void* workspace, size_
         (P.mode == 2 || (reinterpret_cast<uintptr_t>(L.zeros) & 15) == 0) && (P.N * 2) % 16 == 0) {   \
       constexpr int R2 = (RPG >= 2) ? RPG : 2;                                                        \
       const int gpw = (G + M1_NW - 1) / M1_NW;                                                        \
-      if (gpw <= 1) return launch_w4_m1<BF16, R2, F, 1>(L, P, workspace, ws_bytes, stream);           \
-      if (gpw <= 2) return launch_w4_m1<BF16, R2, F, 2>(L, P, workspace, ws_bytes, stream);           \
-      if (gpw <= 4) return launch_w4_m1<BF16, R2, F, 4>(L, P, workspace, ws_bytes, stream);           \
-      return launch_w4_m1<BF16, R2, F, 8>(L, P, workspace, ws_bytes, stream);                         \
+      if (gpw <= 1) return launch_w4_m1<BF16, R2, F, 1>(L, P, stream);           \
+      if (gpw <= 2) return launch_w4_m1<BF16, R2, F, 2>(L, P, stream);           \
+      if (gpw <= 4) return launch_w4_m1<BF16, R2, F, 4>(L, P, stream);           \
+      return launch_w4_m1<BF16, R2, F, 8>(L, P, stream);                         \
     }                                                                                                 \
     if (MT <= 8 && variant != 3 && (reinterpret_cast<uintptr_t>(L.scales) & 15) == 0 &&               \
         (P.mode == 2 || (reinterpret_cast<uintptr_t>(L.zeros) & 15) == 0) && (P.N * 2) % 16 == 0) {   \
@@ -1289,11 +1255,28 @@ bool gemv_supported(const glb_linear& L, int64_t M) {
   return true;
 }
 
-// The M == 1 kernel keeps the chained hand-off's arrival counters in the tail of the workspace's 64 KB counter region
-// (zero-initialised by the caller like the split-K counters; the kernels re-zero their own slot).
+// glb_prefetch_hint: when `layer` runs at M == 1, also pull `next`'s packed weights / scales / zeros towards the L2.
+// A hint, not a dependency: a stale or wrong hint costs bandwidth, never correctness (the ranges must stay mapped).
+int set_prefetch_hint(const glb_linear& layer, const glb_linear* next) {
+  std::lock_guard<std::mutex> lk(g_pf_mu);
+  if (!next) { g_pf.erase(layer.W_q); return GLB_OK; }
+  PfHint h;
+  h.ptr[0] = next->W_q;
+  h.bytes[0] = (unsigned long long)next->wq_rows * (unsigned long long)next->wq_cols * (unsigned long long)dtype_bytes(next->wq_dtype);
+  h.ptr[1] = next->scales; h.bytes[1] = next->scales ? (unsigned long long)next->scales_numel * dtype_bytes(next->scales_dtype) : 0;
+  h.ptr[2] = next->zeros;  h.bytes[2] = (next->zeros && next->zeros_numel > 1) ? (unsigned long long)next->zeros_numel * dtype_bytes(next->zeros_dtype) : 0;
+  for (int a = 0; a < 3; ++a)
+    if ((reinterpret_cast<uintptr_t>(h.ptr[a]) & 15) != 0 || h.bytes[a] < 16) { h.ptr[a] = nullptr; h.bytes[a] = 0; }
+  // only contiguous storage can be described by one range
+  if (!(next->wq_stride1 == 1 && next->wq_stride0 == next->wq_cols) && !(next->wq_stride0 == 1)) { h.ptr[0] = nullptr; h.bytes[0] = 0; }
+  if (g_pf.size() > 65536) g_pf.clear();
+  g_pf[layer.W_q] = h;
+  return GLB_OK;
+}
+
 size_t gemv_workspace(const glb_linear& L, int64_t M) {
-  (void)L;
-  return (M == 1 && chain_mode() && gemv_variant() == 7) ? (size_t)64 * 1024 : 0;
+  (void)L; (void)M;
+  return 0;                    // the decode kernels need no scratch
 }
 
 int launch_gemv(const glb_linear& L, const void* x, const float* scales_x, void* y, int64_t M, const void* bias,

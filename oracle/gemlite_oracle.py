@@ -550,6 +550,26 @@ def quantize_nvfp4(W: torch.Tensor):
 # ============================================================================================
 # CPU baseline used by bench.py: torch dequant + matmul on host cores
 # ============================================================================================
+def cpu_dequant_matmul_fast(Wp_i32: torch.Tensor, scales: torch.Tensor, zeros_fma: torch.Tensor,
+                            x: torch.Tensor, group_size: int) -> torch.Tensor:
+    """A16W4 (mode 4) on host cores without materialising the dequantised matrix: per group g
+        y[m, n] = sum_g s[g, n] * (sum_{k in g} x[m, k] q[k, n])  +  z'[g, n] * sum_{k in g} x[m, k]
+    with the codes taken straight from the packed bytes (a word (r, n) holds k = 8r .. 8r+7, byte b = nibbles 2b, 2b+1;
+    bitpack.py:42-54).  fp32 throughout; same result as cpu_dequant_matmul up to fp32 summation order.  This is the
+    timed CPU baseline of bench.py (the plain version below builds a (K/8, 8, N) int32 shift tensor per call)."""
+    Kp, N = Wp_i32.shape
+    G = scales.shape[0]
+    rpg = Kp // G                                                  # packed rows per group
+    M = x.shape[0]
+    by = Wp_i32.contiguous().view(torch.uint8).view(G, rpg, N, 4)  # little endian: byte b of the word
+    xf = x.to(torch.float32).view(M, G, rpg, 4, 2)                 # [m, g, r, b, h] = x[m, 8 (g rpg + r) + 2 b + h]
+    lo = (by & 15).to(torch.float32)
+    hi = (by >> 4).to(torch.float32)
+    P = torch.einsum("mgrb,grnb->mgn", xf[..., 0], lo) + torch.einsum("mgrb,grnb->mgn", xf[..., 1], hi)
+    sx = xf.sum(dim=(2, 3, 4))                                     # (M, G)
+    return (P * scales.to(torch.float32).unsqueeze(0)).sum(1) + sx @ zeros_fma.to(torch.float32)
+
+
 def cpu_dequant_matmul(Wp_i32: torch.Tensor, scales: torch.Tensor, zeros_fma: torch.Tensor,
                        x: torch.Tensor, group_size: int) -> torch.Tensor:
     """A16W4 (mode 4) dequant + matmul in fp32 with plain torch ops, vectorised (the timed baseline)."""

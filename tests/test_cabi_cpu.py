@@ -124,27 +124,30 @@ def _a16w4_desc(N, K, gs=128):
 
 
 def test_workspace_plan_without_gpu():
-    """glb_workspace_bytes is pure host logic: the 64 KB counter region for the M = 1 decode kernel (its chained
-    hand-off keeps arrival counters in the tail of that region), zero for full-size prefill, counters + fp32
+    """glb_workspace_bytes is pure host logic: zero for the decode kernels and for full-size prefill, counters + fp32
     partial tiles for the split-K range 16 < M <= 128 of a narrow layer (tiles * splits <= SM pairs)."""
     lib = _cabi.load()
     d = _a16w4_desc(4096, 4096)
-    assert lib.glb_workspace_bytes(ctypes.byref(d), 1, -1) == 65536      # decode kernel: hand-off counters only
+    assert lib.glb_workspace_bytes(ctypes.byref(d), 1, -1) == 0          # decode kernel
     assert lib.glb_workspace_bytes(ctypes.byref(d), 16, -1) == 0
     assert lib.glb_workspace_bytes(ctypes.byref(d), 4096, -1) == 0       # 256 tiles: no split
     assert lib.glb_workspace_bytes(ctypes.byref(d), 256, -1) == 0        # split-K is not used above M = 128
-    w32 = lib.glb_workspace_bytes(ctypes.byref(d), 32, -1)
+    # 16 < M <= 128 goes to the batched-decode kernel (gl_gemm_mid.cu, no scratch) unless "GEMM" is requested by name,
+    # which keeps the CTA-pair tcgen05 kernel and its split-K plan
+    assert lib.glb_workspace_bytes(ctypes.byref(d), 32, -1) == 0 and lib.glb_workspace_bytes(ctypes.byref(d), 128, -1) == 0
+    GEMM = 4
+    w32 = lib.glb_workspace_bytes(ctypes.byref(d), 32, GEMM)
     # fixed 64 KB counter region (the same for every layer: one workspace serves all layers of a stream, so the
     # partial tiles of one layer must never overlap the words another layer reads as counters)
     # + 16 tiles x 4 splits x 2 CTAs x 128 rows x 64 columns fp32
     assert w32 == 65536 + 16 * 4 * 2 * 128 * 64 * 4, w32
-    w128 = lib.glb_workspace_bytes(ctypes.byref(d), 128, -1)
+    w128 = lib.glb_workspace_bytes(ctypes.byref(d), 128, GEMM)
     assert w128 == 65536 + 16 * 4 * 2 * 128 * 128 * 4, w128
     # a layer with another tile count gets the same counter region
     other = _a16w4_desc(2048, 4096)
-    assert lib.glb_workspace_bytes(ctypes.byref(other), 32, -1) == 65536 + 8 * 8 * 2 * 128 * 64 * 4
+    assert lib.glb_workspace_bytes(ctypes.byref(other), 32, GEMM) == 65536 + 8 * 8 * 2 * 128 * 64 * 4
     wide = _a16w4_desc(16384, 4096)
-    assert lib.glb_workspace_bytes(ctypes.byref(wide), 64, -1) == 0      # 64 tiles already fill the 74 SM pairs
+    assert lib.glb_workspace_bytes(ctypes.byref(wide), 64, GEMM) == 0    # 64 tiles already fill the 74 SM pairs
 
 
 def _mx_desc(N, K, input_dtype, nbits, gs, csm, scales_dtype):

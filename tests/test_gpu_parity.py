@@ -308,11 +308,11 @@ def test_pair_kernel_split_k_small_batches(dtype):
     for M in (17, 64, 65, 128, 200, 256):
         x = xgen(M, K, dtype, 500 + M)
         xd = x.to(DEV)
-        y = layer(xd)
+        y = layer.forward_manual(xd, "GEMM")     # by name: the automatic choice for M <= 128 is the batched-decode kernel
         assert _cabi.last_kernel() == "gemm_a16w4_tcgen05_2cta", (M, _cabi.last_kernel())
         assert relerr(y, O.forward(p, x)) <= REL[dtype], (dtype, M)
         for _ in range(3):                       # same workspace, counters must have returned to zero; bitwise repeatable
-            assert torch.equal(layer(xd), y)
+            assert torch.equal(layer.forward_manual(xd, "GEMM"), y)
 
 
 def test_split_k_layers_of_different_width_share_one_workspace():
@@ -332,7 +332,7 @@ def test_split_k_layers_of_different_width_share_one_workspace():
         xd = x.to(DEV)
         first = None
         for rep in range(3):
-            got = [layer(xd) for layer, _ in layers]
+            got = [layer.forward_manual(xd, "GEMM") for layer, _ in layers]
             assert _cabi.last_kernel() == "gemm_a16w4_tcgen05_2cta"
             for (layer, p), y, w in zip(layers, got, want):
                 assert relerr(y, w) <= REL[dtype], (M, rep, p.out_features, relerr(y, w))
@@ -631,14 +631,14 @@ def test_split_k_under_graph_capture_without_warmup_on_the_capture_stream():
     xs = [xgen(M, K, dtype, 880 + M).to(DEV) for M in (32, 100)]
     side = torch.cuda.Stream(device=DEV)
     with torch.cuda.stream(side):                 # warm-up and eager reference on ANOTHER stream
-        want = [layer(x) for x in xs]
+        want = [layer.forward_manual(x, "GEMM") for x in xs]
         assert _cabi.last_kernel() == "gemm_a16w4_tcgen05_2cta"
     torch.cuda.synchronize()
     graphs, outs = [], []
     for x in xs:
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):                 # torch's default capture stream: no eager workspace exists for it
-            outs.append(layer(x))
+            outs.append(layer.forward_manual(x, "GEMM"))
         graphs.append(g)
     for i in (1, 0, 1, 0):
         graphs[i].replay()
@@ -647,11 +647,12 @@ def test_split_k_under_graph_capture_without_warmup_on_the_capture_stream():
 
 
 # ------------------------------------------------------------------------------------------------
-def test_chained_decode_graph_uses_flag_handoff_and_matches_eager():
-    """A chain of M = 1 layers captured in one CUDA graph: every launch after the first proves (from the capture's
-    dependency set) that its x is the y of the launch before it and waits on that launch's arrival counter instead of
-    kernel completion.  The result must equal the eager chain bit for bit, on every replay; a foreign kernel between two
-    layers (in-place activation on y) must switch that link back to the kernel-boundary wait."""
+def test_chained_decode_graph_matches_eager_with_and_without_prefetch_hints():
+    """A chain of M = 1 layers (y of layer i is x of layer i + 1) captured in one CUDA graph with programmatic dependent
+    launch, with the layers linked in execution order (L2 prefetch hints, `link_layers`) and without: the result must
+    equal the eager chain bit for bit on every replay -- the hint is advisory -- also with a foreign in-place kernel
+    between two layers, and after the hints are cleared."""
+    from gemlite_b200 import link_layers
     K = N = 4096
     dt = torch.float16
     layers = []
@@ -671,21 +672,101 @@ def test_chained_decode_graph_uses_flag_handoff_and_matches_eager():
     y_ref, y_ref_act = chain(x).clone(), chain(x, 2).clone()
     torch.cuda.synchronize()
     assert _cabi.last_kernel() == "gemv_w4_mma"
-    for act_after, want in ((None, y_ref), (2, y_ref_act)):
-        st = torch.cuda.Stream()
-        st.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(st):
-            chain(x, act_after)
-            torch.cuda.synchronize()
-            c0 = _cabi.chained_launch_count()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=st):
-                y = chain(x, act_after)
-            n_flag = _cabi.chained_launch_count() - c0
-            for _ in range(25):
-                g.replay()
+    n_params = sum(1 for _ in layers[0].parameters())
+    for distance in (2, 1, 0):
+        link_layers(layers, distance)
+        assert sum(1 for _ in layers[0].parameters()) == n_params and len(list(layers[0].children())) == 0   # the hint is not a submodule
+        for act_after, want in ((None, y_ref), (2, y_ref_act)):
+            st = torch.cuda.Stream()
+            st.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(st):
+                chain(x, act_after)
                 torch.cuda.synchronize()
-                assert torch.equal(y, want), (act_after, (y != want).sum().item())
-        if os.environ.get("GLB_GEMV_FLAGS", "1") != "0" and os.environ.get("GLB_GEMV_VARIANT", "7") == "7":
-            assert n_flag == (5 if act_after is None else 4), (act_after, n_flag)
-    torch.cuda.current_stream().wait_stream(st)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=st):
+                    y = chain(x, act_after)
+                for _ in range(10):
+                    g.replay()
+                    torch.cuda.synchronize()
+                    assert torch.equal(y, want), (distance, act_after, (y != want).sum().item())
+            torch.cuda.current_stream().wait_stream(st)
+
+
+# ------------------------------------------------------------------------------------------------
+def test_column_shards_reproduce_the_unsharded_layer_on_the_gpu():
+    """SURVEY 8e on the real CUDA path: every column shard of a packed layer (ColumnShardedLinear.local), run on its own
+    and concatenated in rank order -- what the all-gather produces -- equals the unsharded layer's output BIT FOR BIT
+    (a column of y depends only on that column of W / scales / zeros).  A16W4 at decode and prefill batch sizes, A8W8
+    int8, MXFP4 including the K/32 == N shape whose scales are square (sliced along the wrong axis)."""
+    from gemlite_b200.sharding import ColumnShardedLinear
+    cases = []
+    W_q, s, z = gen_int(1024, 2048, 4, 128, torch.float16, seed=321)
+    cases.append(("a16w4", GemLiteLinear(4, 128, 2048, 1024, DType.FP16, DType.FP16).pack(W_q.to(DEV), s.to(DEV), z.to(DEV)),
+                  torch.float16, (1, 5, 16, 200)))
+    Wf = (torch.randn(512, 1024, generator=torch.Generator().manual_seed(5)) / 10).half()
+    cases.append(("a8w8_int8", A8W8_INT8_dynamic(device=DEV, dtype=torch.float16).from_weights(Wf.to(DEV)), torch.float16, (1, 16, 150)))
+    for (n, k) in ((512, 1024), (256, 8192)):                      # 8192 / 32 == 256: square MX scale matrix
+        lin = torch.nn.Linear(k, n, bias=False, dtype=torch.bfloat16, device=DEV)
+        lin.weight.data = (torch.randn(n, k, generator=torch.Generator().manual_seed(n)) / 10).to(device=DEV, dtype=torch.bfloat16)
+        cases.append((f"mxfp4_{n}x{k}", A16W4_MXFP(device=DEV, dtype=torch.bfloat16).from_linear(lin, del_orig=False), torch.bfloat16, (1, 4, 200)))
+    for name, layer, dt, Ms in cases:
+        for world in (2, 4):
+            shards = [ColumnShardedLinear(layer, r, world).local for r in range(world)]
+            for M in Ms:
+                x = xgen(M, layer.in_features, dt, 40 + M).to(DEV)
+                full = layer(x)
+                k_full = _cabi.last_kernel()
+                parts = torch.cat([sh(x) for sh in shards], dim=-1)
+                k_shard = _cabi.last_kernel()
+                if k_shard == k_full:          # same kernel, same per-column summation order: bit-equal
+                    assert torch.equal(parts, full), (name, world, M, k_full, (parts != full).sum().item())
+                else:                          # a narrow shard can fall to another kernel (tile-width rules): fp tolerance
+                    assert relerr(parts, full) <= REL[dt], (name, world, M, k_full, k_shard)
+
+
+# ------------------------------------------------------------------------------------------------
+# Batched decode, 16 < M <= 128: gl_gemm_mid.cu (cluster of K/1024 CTAs per 128-column slab, mma.sync, exact dequant)
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(256, 1024), (512, 2048), (384, 4096), (128, 8192)])
+def test_a16w4_batched_decode_kernel_vs_oracle(dtype, shape):
+    N, K = shape
+    gd = gemlite_b200.dtypes.TORCH_TO_DTYPE[dtype]
+    for gs, mode in ((128, "fma"), (64, "nofma"), (256, "sym"), (64, "fma")):
+        W_q, scales, zeros = gen_int(N, K, 4, gs, dtype, seed=gs + K // 64 + (3 if mode == "fma" else 5))
+        bias = (torch.randn(N, generator=torch.Generator().manual_seed(6)) / 10).to(dtype) if mode != "sym" else None
+        z_in = None if mode == "sym" else zeros
+        layer = GemLiteLinear(4, gs, K, N, gd, gd)
+        layer.pack(W_q.to(DEV), scales.to(DEV), None if z_in is None else z_in.to(DEV), None if bias is None else bias.to(DEV),
+                   fma_mode=(mode == "fma"))
+        p = O.prepare(W_q, scales, z_in, W_nbits=4, group_size=gs, in_features=K, out_features=N,
+                      input_dtype=O.DTYPE_OF[dtype], output_dtype=O.DTYPE_OF[dtype], bias=bias, fma_mode=(mode == "fma"))
+        for M in (17, 32, 63, 64, 65, 100, 128):          # one and two token passes, ragged tails
+            x = xgen(M, K, dtype, 300 + M)
+            y = layer(x.to(DEV))
+            assert _cabi.last_kernel() == "gemm_a16w4_mma_mid", (M, _cabi.last_kernel())
+            e = relerr(y, O.forward(p, x))
+            assert e <= REL[dtype], (dtype, shape, gs, mode, M, e)
+            assert torch.equal(layer(x.to(DEV)), y)       # deterministic: fixed-order reductions, no atomics
+        # the explicitly named kernels of the reference still resolve: GEMM -> tcgen05 pair kernel, GEMM_SPLITK -> this one
+        x = xgen(40, K, dtype, 9).to(DEV)
+        layer.forward_manual(x, "GEMM_SPLITK")
+        assert _cabi.last_kernel() == "gemm_a16w4_mma_mid"
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_batched_decode_kernel_dequant_is_bit_exact(dtype):
+    """One-hot activations (row m of x = e_{k0 + m}) => y[m, n] is the dequantised weight W[n, k0 + m] itself: the MMA
+    operand must hold exactly the reference's dequantize() values (utils.py:57-89), for every k position of a word and
+    both halves of the CTA's k range."""
+    N, K, gs = 256, 2048, 64
+    W_q, scales, zeros = gen_int(N, K, 4, gs, dtype, seed=15)
+    gd = gemlite_b200.dtypes.TORCH_TO_DTYPE[dtype]
+    layer = GemLiteLinear(4, gs, K, N, gd, gd).pack(W_q.to(DEV), scales.to(DEV), zeros.to(DEV))
+    p = O.prepare(W_q, scales, zeros, W_nbits=4, group_size=gs, in_features=K, out_features=N,
+                  input_dtype=O.DTYPE_OF[dtype], output_dtype=O.DTYPE_OF[dtype])
+    for k0 in (0, 960, 1024 + 37, K - 128):
+        x = torch.zeros(128, K, dtype=dtype)
+        x[torch.arange(128), k0 + torch.arange(128)] = 1
+        y = layer(x.to(DEV))
+        assert _cabi.last_kernel() == "gemm_a16w4_mma_mid"
+        assert torch.equal(y.cpu(), O.forward(p, x)), k0

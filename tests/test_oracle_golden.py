@@ -210,3 +210,24 @@ def test_mx_activation_quantisers_match_reference():
                 assert np.array_equal(s.view(torch.uint8).numpy(), sr), key
                 seen += 1
     assert seen == 18
+
+
+def test_c_cpu_baseline_matches_the_oracle():
+    """oracle/cpu_a16w4.c (gcc + OpenMP; bench.py's cpu_baseline and --impl reference legs) against the torch port and the
+    rounding-exact oracle on a seeded A16W4 layer: fp32 summation-order noise only."""
+    import numpy as np
+    from oracle import build_cpu as C
+    N, K, gs = 256, 1024, 128
+    g = torch.Generator().manual_seed(5)
+    W_q = torch.randint(0, 16, (N, K), generator=g, dtype=torch.int32).to(torch.uint8)
+    scales = (torch.rand(N * K // gs, 1, generator=g) * 0.01 + 0.001).half()
+    zeros = (torch.rand(N * K // gs, 1, generator=g) * 15).half()
+    p = O.prepare(W_q, scales, zeros, W_nbits=4, group_size=gs, in_features=K, out_features=N)
+    assert p.W_group_mode == 4
+    x = (torch.randn(3, K, generator=g) / 10).half()
+    y_c = C.forward(p.W_q.contiguous().numpy(), p.scales.float().numpy(), p.zeros.float().numpy(), x.float().numpy())
+    y_t = O.cpu_dequant_matmul_fast(p.W_q.contiguous(), p.scales, p.zeros, x, gs).numpy()
+    y_o = O.forward(p, x).float().numpy()
+    scale = np.abs(y_o).max()
+    assert np.abs(y_c - y_t).max() <= 1e-5 * scale
+    assert np.abs(y_c - y_o).max() <= 2e-3 * scale       # the oracle rounds every dequantised weight and the output to fp16

@@ -1,11 +1,12 @@
 """Diagnostic: pipelined timeline of the decode kernel (GLB_GEMV_DEBUG=4) inside a CUDA-graph replay."""
 import ctypes, os, sys
 os.environ["GLB_GEMV_DEBUG"] = "4"
+LINK = int(os.environ.get("TL_LINK", "0"))
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from gemlite_b200 import _cabi
 from gemlite_b200.helper import A16W4_HQQ_INT
-dev = "cuda:0"; K = N = 4096; L = 16
+dev = "cuda:0"; K = N = 4096; L = 24
 g = torch.Generator(device=dev).manual_seed(0)
 layers = []
 for _ in range(L):
@@ -13,6 +14,9 @@ for _ in range(L):
     s = (torch.rand(N * K // 128, 1, generator=g, device=dev) * 0.002 + 0.0024).half()
     z = (torch.rand(N * K // 128, 1, generator=g, device=dev) * 3 + 6).half()
     layers.append(A16W4_HQQ_INT(device=dev, dtype=torch.float16).from_weights(W_q, s, z))
+if LINK:
+    from gemlite_b200 import link_layers
+    link_layers(layers, LINK)
 x0 = (torch.randn(1, K, device=dev) / 10).half()
 def step():
     x = x0
@@ -34,6 +38,9 @@ rec = np.array(buf[:n], dtype=np.uint64).reshape(-1, 9).astype(np.int64)
 rec = rec[np.argsort(rec[:, 1])]
 t0 = rec[0, 1]
 names = ["start", "tma_issued", "wait_done", "staged", "meta", "w0_ready", "loop_done", "reduced"]
+if os.environ.get("GLB_GEMV_VARIANT", "7") == "7":
+    names = ["start", "issued", "meta_ok", "handoff", "x_staged", "loop_done", "published", "(flagged)"]
+    rec[:, 8] = rec[:, 8] + rec[:, 1] - (rec[:, 8] * 0)      # last column is a flag, shown as start + flag
 print("cta   " + " ".join(f"{n:>11s}" for n in names) + "   (ns since first start; deltas in brackets)")
 for r in rec:
     t = r[1:] - t0
