@@ -6,9 +6,8 @@
 Workload at N=1 (BASELINE.json configs[1]): A16W4 group-size-128 decode, M=1, K=N=4096, fp16.
 One *step* = one decode pass through LAYERS=64 distinct layers of that shape, chained (y of layer i is x of layer
 i+1), i.e. 572 MB of packed weights + metadata per step -- 4.5x the 126 MB L2, so every layer streams from HBM (the
-"inputs larger than L2" timing rule).  The layers are declared to the library in execution order
-(`gemlite_b200.link_layers`, what `helper.patch_model` does for a model), the step is replayed from a CUDA graph whose
-launches carry the programmatic-dependent-launch attribute.  `value` = algorithmic bytes per second over the whole job,
+"inputs larger than L2" timing rule).  The step is replayed from a CUDA graph whose launches carry
+the programmatic-dependent-launch attribute.  `value` = algorithmic bytes per second over the whole job,
 inputs resident in HBM, device-timed.
 Other keys of the line:
   e2e                  the same step with HOST buffers (pinned x -> device, graph replay, y -> pinned host, synchronize),
@@ -159,10 +158,9 @@ def workload_config(world):
     return {"workload": f"A16W4 gs={GROUP} decode M=1 K=N={K} fp16 (BASELINE configs[1]); step = {LAYERS} "
                         f"{'chained layers' if world == 1 else 'column shards of wide layers (N_global=%d) + one NCCL all-gather' % (N * world)}",
             "l2": f"{LAYERS} distinct layers = {LAYERS * ALGO_BYTES / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)",
-            "launch": "CUDA graph replay, programmatic dependent launch, layers linked in execution order",
+            "launch": "CUDA graph replay, programmatic dependent launch",
             "chain": ("independent layers (diagnostic)" if INDEPENDENT else "y_i feeds x_{i+1}") if world == 1 else "same x for every shard call",
-            "parallelism": f"column-shard x{world}",
-            "prefetch_hint_distance": int(os.environ.get("GEMLITE_B200_PREFETCH_DISTANCE", "2"))}
+            "parallelism": f"column-shard x{world}"}
 
 
 def make_weights(dev, layers, seed=0, n_out=N):
@@ -458,7 +456,7 @@ def mxfp4_sharded_leg(dev, rank, world, steps=10):
 # ------------------------------------------------------------------------------------------------------------------
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
-    from gemlite_b200 import _cabi, link_layers
+    from gemlite_b200 import _cabi
     from gemlite_b200.helper import A16W4_HQQ_INT
     from gemlite_b200.sharding import ColumnShardedLinear
 
@@ -479,9 +477,6 @@ def run_ours(args, rank, world, local_rank):
             layers.append(ColumnShardedLinear(full, rank, world).local)
             del full
         torch.cuda.empty_cache()
-    link_distance = int(os.environ.get("GEMLITE_B200_PREFETCH_DISTANCE", "2"))
-    if not ALIAS:
-        link_layers(layers, link_distance)
     torch.cuda.synchronize()
     x0 = (torch.randn(1, K, device=dev, generator=torch.Generator(device=dev).manual_seed(7)) / 10).half()
     x_in = x0.clone()          # static input buffer of the captured step (the e2e leg copies host data into it)

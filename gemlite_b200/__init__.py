@@ -13,7 +13,7 @@ from .dtypes import DType  # noqa: F401
 from .core import (  # noqa: F401
     GemLiteLinear, GemLiteLinearTriton, GEMLITE_ACC_DTYPE, GEMLITE_MATMUL_TYPES, GEMLITE_MATMUL_TYPES_MAPPING,
     forward_functional, get_matmul_type, get_default_gemv,
-    set_autotune, set_autotune_setting, set_packing_bitwidth, set_acc_dtype, set_kernel_caching, link_layers,
+    set_autotune, set_autotune_setting, set_packing_bitwidth, set_acc_dtype, set_kernel_caching,
 )
 from . import helper  # noqa: F401
 

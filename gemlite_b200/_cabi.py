@@ -39,7 +39,7 @@ class GlbLinear(ctypes.Structure):
 
 EXPORTS = [
     "glb_version", "glb_last_error", "glb_last_kernel", "glb_launch_count", "glb_pack_cols", "glb_unpack_cols",
-    "glb_quant_act_per_token", "glb_quant_act_mx", "glb_stream_capture_id", "glb_workspace_bytes", "glb_matmul", "glb_set_pdl", "glb_get_pdl", "glb_debug_timeline", "glb_prefetch_hint",
+    "glb_quant_act_per_token", "glb_quant_act_mx", "glb_stream_capture_id", "glb_workspace_bytes", "glb_matmul", "glb_set_pdl", "glb_get_pdl", "glb_debug_timeline", 
 ]
 
 
@@ -84,8 +84,6 @@ def load():
         lib.glb_get_pdl.restype = i32
         lib.glb_debug_timeline.argtypes = [vp, i32]
         lib.glb_debug_timeline.restype = i32
-        lib.glb_prefetch_hint.argtypes = [ctypes.POINTER(GlbLinear), ctypes.POINTER(GlbLinear)]
-        lib.glb_prefetch_hint.restype = i32
         if os.environ.get("GLB_PDL", "1") == "0":
             lib.glb_set_pdl(0)
         _lib = lib

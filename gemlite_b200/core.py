@@ -217,29 +217,6 @@ def _matmul(x2d: Tensor, bias: Optional[Tensor], tensor_args: List[Tensor], meta
     return out
 
 
-def link_layers(layers, distance: int = None):
-    """Tell the library the static execution order of `layers` (B200 extension, no reference equivalent): when layer i
-    runs in the decode regime its kernel also asks the L2 for the packed tensors of layer i + distance, so that a chain
-    of small dependent launches is not bound by launch -> first-byte latency.  Purely advisory -- results
-    never depend on it.  Each layer keeps a reference to its target so the hinted ranges stay allocated; call with
-    distance=0 to clear.  `helper.patch_model` links the layers it creates."""
-    if distance is None:
-        distance = int(os.environ.get("GEMLITE_B200_PREFETCH_DISTANCE", "2"))
-    lib = _cabi.load()
-    layers = [l for l in layers if isinstance(l, GemLiteLinear) and getattr(l, "W_q", None) is not None and l.W_q.is_cuda]
-    for i, layer in enumerate(layers):
-        target = layers[i + distance] if (distance > 0 and i + distance < len(layers)) else None
-        src = _make_desc(layer.W_q, layer.scales, layer.zeros, layer.get_meta_args())
-        if target is None or target.W_q.device != layer.W_q.device:
-            lib.glb_prefetch_hint(ctypes.byref(src), None)
-            object.__setattr__(layer, "_prefetch_target", None)      # plain attribute: NOT a registered submodule
-            continue
-        dst = _make_desc(target.W_q, target.scales, target.zeros, target.get_meta_args())
-        _cabi.check(lib.glb_prefetch_hint(ctypes.byref(src), ctypes.byref(dst)), "glb_prefetch_hint")
-        object.__setattr__(layer, "_prefetch_target", target)
-    return layers
-
-
 # ---------------------------------------------------------------------------------------------------
 # functional forward (custom op so that torch.compile / vLLM can trace through it)
 # ---------------------------------------------------------------------------------------------------

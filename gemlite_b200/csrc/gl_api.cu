@@ -200,11 +200,6 @@ extern "C" void glb_set_pdl(int enabled) { g_pdl_enabled.store(enabled ? 1 : 0);
 extern "C" int glb_get_pdl(void) { return g_pdl_enabled.load(); }
 extern "C" int glb_debug_timeline(unsigned long long* out, int max_words) { return debug_read_timeline(out, max_words); }
 
-extern "C" int glb_prefetch_hint(const glb_linear* layer, const glb_linear* next) {
-  GLB_REQUIRE(layer != nullptr && layer->W_q != nullptr, GLB_ERR_INVALID, "glb_prefetch_hint: layer is NULL");
-  return set_prefetch_hint(*layer, next);
-}
-
 extern "C" unsigned long long glb_stream_capture_id(void* stream_) {
   cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
   unsigned long long id = 0;
@@ -251,6 +246,9 @@ extern "C" int glb_matmul(const glb_linear* L, const void* x, const void* scales
   // 0. MXFP4 weight-only layers at M <= 4: streaming CUDA-core kernel (the reference sends every MX dtype at M == 1 to
   //    GEMM_SPLITK, core.py:100-114); an explicit "GEMM" request keeps the tensor-core kernel
   if (matmul_type != GLB_MM_GEMM && gemv_mx_supported(*L, M)) return launch_gemv_mx(*L, x, y, M, bias, stream);
+  // 0a. A8W8 at 16 < M <= 128: clustered streaming kernel (gl_gemm_a8_mid.cu); "GEMM" by name keeps the tcgen05 tile
+  if ((was_auto || matmul_type != GLB_MM_GEMM) && gemm_a8_mid_supported(*L, M))
+    return launch_gemm_a8_mid(*L, x, sx, y, M, bias, stream);
   // 0b. A8W8 at M <= 16: 16-feature-row streaming kernel (gl_gemv_a8.cu) (validated in round 2)
   if (matmul_type != GLB_MM_GEMM && gemv_a8_enabled() && gemv_a8_supported(*L, M))
     return launch_gemv_a8(*L, x, sx, y, M, bias, stream);

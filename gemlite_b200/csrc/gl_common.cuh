@@ -74,7 +74,6 @@ bool gemv_supported(const glb_linear& L, int64_t M);
 int launch_gemv(const glb_linear& L, const void* x, const float* scales_x, void* y, int64_t M,
                 const void* bias, void* workspace, size_t ws_bytes, cudaStream_t stream);
 size_t gemv_workspace(const glb_linear& L, int64_t M);
-int set_prefetch_hint(const glb_linear& layer, const glb_linear* next);
 int debug_read_timeline(unsigned long long* out, int max_words);
 bool gemm_tc_supported(const glb_linear& L, int64_t M);
 size_t gemm_tc_workspace(const glb_linear& L, int64_t M);
@@ -93,6 +92,9 @@ int launch_gemv_a8(const glb_linear& L, const void* x, const float* scales_x, vo
                    cudaStream_t stream);
 size_t gemm_tc2_workspace(const glb_linear& L, int64_t M);
 bool gemm_mid_supported(const glb_linear& L, int64_t M);
+bool gemm_a8_mid_supported(const glb_linear& L, int64_t M);
+int launch_gemm_a8_mid(const glb_linear& L, const void* x, const float* scales_x, void* y, int64_t M, const void* bias,
+                       cudaStream_t stream);
 int launch_gemm_mid(const glb_linear& L, const void* x, void* y, int64_t M, const void* bias, cudaStream_t stream);
 int launch_gemm_tc2(const glb_linear& L, const void* x, void* y, int64_t M, void* workspace, size_t ws_bytes, const void* bias,
                     cudaStream_t stream);

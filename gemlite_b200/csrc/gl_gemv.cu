@@ -35,36 +35,6 @@
 namespace glb {
 namespace {
 
-// ---- L2 prefetch hints: layer (keyed by its W_q pointer) -> byte ranges of a layer that runs later ----
-struct PfHint { const void* ptr[3]; unsigned long long bytes[3]; };
-std::mutex g_pf_mu;
-std::unordered_map<const void*, PfHint> g_pf;
-
-// this CTA's contiguous 1/gridDim share of each hinted range -> cp.async.bulk.prefetch.L2, pieces of <= 4 KB per lane
-__device__ __forceinline__ void l2_prefetch_share(const unsigned char* const (&ptr)[3], const unsigned long long (&bytes)[3], int lane) {
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    const unsigned long long total = bytes[a];
-    if (total == 0) continue;
-    unsigned long long share = ((total + gridDim.x - 1) / gridDim.x + 15ull) & ~15ull;
-    const unsigned long long beg = share * blockIdx.x;
-    if (beg >= total) continue;
-    if (beg + share > total) share = (total - beg) & ~15ull;
-    for (unsigned long long off = (unsigned long long)lane * 4096ull; off < share; off += 32ull * 4096ull) {
-      const unsigned long long n = (share - off < 4096ull) ? (share - off) : 4096ull;
-      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr[a] + beg + off), "r"((unsigned int)n) : "memory");
-    }
-  }
-}
-inline void fill_prefetch_hint(const void* wq, const unsigned char* (&ptr)[3], unsigned long long (&bytes)[3]) {
-  for (int a = 0; a < 3; ++a) { ptr[a] = nullptr; bytes[a] = 0; }
-  std::lock_guard<std::mutex> lk(g_pf_mu);
-  if (g_pf.empty()) return;
-  auto it = g_pf.find(wq);
-  if (it != g_pf.end())
-    for (int a = 0; a < 3; ++a) { ptr[a] = reinterpret_cast<const unsigned char*>(it->second.ptr[a]); bytes[a] = it->second.bytes[a]; }
-}
-
 constexpr int GV_THREADS = 256;
 constexpr int GV_WARPS = 8;
 constexpr int GV_COLS = 32;        // columns per cluster
@@ -490,8 +460,6 @@ struct GemvTmaParams {
   int chunk_shift;       // log2(rows per weight chunk)
   int debug;             // diagnostics only: bit 0 skip the main loop, bit 1 skip the weight copies
   int issue_mode;        // who issues the TMA copies (see the kernel)
-  const unsigned char* pf_ptr[3];      // L2 prefetch hint (glb_prefetch_hint), as in gemv_w4_m1_kernel
-  unsigned long long pf_bytes[3];
 };
 
 constexpr int GT_GPW = 4;    // META_REGS: groups a warp may own (their scale / zero vectors live in registers)
@@ -603,7 +571,6 @@ gemv_w4_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
       }
     }
   }
-  if (warp == 1) l2_prefetch_share(P.pf_ptr, P.pf_bytes, lane);
   if (P.late_trigger == 0) pdl_launch_dependents();  // everything this CTA can do ahead of its input has been issued
 #if GLB_GEMV_PREWAIT_ALL
   {
@@ -828,7 +795,6 @@ int launch_w4_tma(const glb_linear& L, const GemvParams& P0, int late_trigger, c
   P.bulk1d = late_trigger / 10;
   P.W = reinterpret_cast<const uint32_t*>(L.W_q);
   P.scales = P0.scales; P.zeros = P0.zeros;
-  fill_prefetch_hint(L.W_q, P.pf_ptr, P.pf_bytes);
   {
     int cr = rows_c / nch, sh = 0;
     while ((1 << sh) < cr) ++sh;
@@ -874,15 +840,16 @@ int launch_w4_tma(const glb_linear& L, const GemvParams& P0, int late_trigger, c
 //     and parks the words in its private rows of the x buffer -- no block barrier between the hand-off and the first HMMA;
 //   * a leaner main loop (profiles/decode_v7_r2.txt): two accumulator chains per group, the nibble shift on the FMA pipe
 //     (mul.hi), x fragments only in the 4 lanes of token 0: ~148 issued instructions per group and warp instead of ~215;
-//   * an L2 prefetch hint: the CTAs also ask the L2 for their share of the tensors of the layer that will run a couple
-//     of launches later (glb_prefetch_hint), so that a just-launched CTA fills its shared memory from the L2 instead of
-//     waiting for HBM -- in a chain of dependent launches only ONE later layer can be resident per SM, and its
-//     launch -> first-byte latency otherwise bounds the chain's period.
 // Nothing spins before griddepcontrol.wait (the co-resident CTA of the previous layer is in its main loop then).
-// Tried on hardware in round 2 and removed (profiles/decode_experiments_r2.txt): a device-side arrival counter instead
-// of griddepcontrol.wait for provably adjacent launches (store y -> fence -> red / ld.acquire polling): 2.50 us per
-// EMPTY chained launch against 1.66 us with the kernel-boundary hand-off -- the hardware path is faster than two L2
-// round trips plus a gpu-scope fence.
+// Tried on hardware in round 2 and removed (profiles/decode_experiments_r2.txt):
+//   * a device-side arrival counter instead of griddepcontrol.wait for provably adjacent launches (store y -> fence ->
+//     red / ld.acquire polling): 2.50 us per EMPTY chained launch against 1.66 us with the kernel-boundary hand-off --
+//     the hardware path is faster than two L2 round trips plus a gpu-scope fence;
+//   * an L2 prefetch hint (every CTA asks the L2 for its share of the tensors of the layer 1 / 2 / 3 launches ahead,
+//     cp.async.bulk.prefetch.L2): 3.97 us per layer against 3.59 without -- the prefetch competes with the fill the
+//     next launch is waiting for;
+//   * one polling lane per warp (+ __syncwarp) on the copy barriers: ptxas then wraps every later shuffle in
+//     WARPSYNC.COLLECTIVE sequences, 2x slower end to end; all weight waits ahead of the hand-off: +0.4 us.
 // =================================================================================================
 struct GemvM1Params {
   const void* x; void* y; const void* bias;
@@ -890,10 +857,6 @@ struct GemvM1Params {
   int trigger;               // dependents are signalled 0: at kernel start, 2: right after the hand-off
   int debug;                 // bit 0: skip main loop, bit 1: skip weight copies, bit 2: timeline stamps (diagnostics)
   int chunk_shift;           // log2(packed rows per weight chunk)
-  // L2 prefetch hint (glb_prefetch_hint): tensors of the layer that will run `distance` launches after this one.
-  // Every CTA asks the L2 for its 1/gridDim share of each range (cp.async.bulk.prefetch.L2), before the hand-off.
-  const unsigned char* pf_ptr[3];
-  unsigned long long pf_bytes[3];
 };
 
 constexpr int M1_NW = 16;
@@ -949,7 +912,6 @@ gemv_w4_m1_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       ptx::tma_load_2d(wbuf + (size_t)c * chunk_rows * 128, &tmap_w, &bars[c], col0, c * chunk_rows);
     }
   }
-  if (warp == 1) l2_prefetch_share(P.pf_ptr, P.pf_bytes, lane);
   if (rec) ts[1] = gtimer();                         // copies issued
   if (P.trigger == 0) pdl_launch_dependents();
   __syncthreads();                                   // barrier initialisation visible to every thread
@@ -1110,7 +1072,6 @@ int launch_w4_m1(const glb_linear& L, const GemvParams& P0, cudaStream_t stream)
   if (rc != GLB_OK) return rc;
   GemvM1Params P;
   P.x = P0.x; P.y = P0.y; P.bias = P0.bias; P.K = P0.K; P.N = P0.N; P.group_size = P0.group_size; P.mode = P0.mode;
-  fill_prefetch_hint(L.W_q, P.pf_ptr, P.pf_bytes);
   {
     static int dbg = -1, trig = -1;
     if (dbg < 0) { const char* e = getenv("GLB_GEMV_DEBUG"); dbg = e ? atoi(e) : 0; }
@@ -1253,25 +1214,6 @@ bool gemv_supported(const glb_linear& L, int64_t M) {
   const size_t smem = (size_t)mt * L.K * 2 + (size_t)mt * (L.K / gs) * 4 + (size_t)(GV_WARPS + 1) * mt * GV_COLS * 4 + 16;
   if (smem > 200 * 1024) return false;
   return true;
-}
-
-// glb_prefetch_hint: when `layer` runs at M == 1, also pull `next`'s packed weights / scales / zeros towards the L2.
-// A hint, not a dependency: a stale or wrong hint costs bandwidth, never correctness (the ranges must stay mapped).
-int set_prefetch_hint(const glb_linear& layer, const glb_linear* next) {
-  std::lock_guard<std::mutex> lk(g_pf_mu);
-  if (!next) { g_pf.erase(layer.W_q); return GLB_OK; }
-  PfHint h;
-  h.ptr[0] = next->W_q;
-  h.bytes[0] = (unsigned long long)next->wq_rows * (unsigned long long)next->wq_cols * (unsigned long long)dtype_bytes(next->wq_dtype);
-  h.ptr[1] = next->scales; h.bytes[1] = next->scales ? (unsigned long long)next->scales_numel * dtype_bytes(next->scales_dtype) : 0;
-  h.ptr[2] = next->zeros;  h.bytes[2] = (next->zeros && next->zeros_numel > 1) ? (unsigned long long)next->zeros_numel * dtype_bytes(next->zeros_dtype) : 0;
-  for (int a = 0; a < 3; ++a)
-    if ((reinterpret_cast<uintptr_t>(h.ptr[a]) & 15) != 0 || h.bytes[a] < 16) { h.ptr[a] = nullptr; h.bytes[a] = 0; }
-  // only contiguous storage can be described by one range
-  if (!(next->wq_stride1 == 1 && next->wq_stride0 == next->wq_cols) && !(next->wq_stride0 == 1)) { h.ptr[0] = nullptr; h.bytes[0] = 0; }
-  if (g_pf.size() > 65536) g_pf.clear();
-  g_pf[layer.W_q] = h;
-  return GLB_OK;
 }
 
 size_t gemv_workspace(const glb_linear& L, int64_t M) {

@@ -106,11 +106,6 @@ def patch_model(model, device, processor, skip_modules=["lm_head", "vision", "vi
 
     walk(model)
     model = model.to(device=device)
-    # static execution order hint for the decode kernels (module order approximates it; advisory, see core.link_layers)
-    packed = [m for m in model.modules() if isinstance(m, GemLiteLinear)]
-    if packed and packed[0].W_q.is_cuda:
-        from .core import link_layers
-        link_layers(packed)
     if torch.cuda.is_available():
         torch.cuda.empty_cache()
     gc.collect()

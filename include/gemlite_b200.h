@@ -167,13 +167,6 @@ GLB_API int glb_matmul(const glb_linear* layer, const void* x, const void* scale
 
 /* Global knobs (host side, cheap): enable programmatic dependent launch on the decode kernels so that
  * a layer's weight prefetch overlaps the tail of the previous layer's kernel. Default: on. */
-/* Static execution order as a hint (no reference equivalent: the reference's Triton kernels cannot see past one layer).
- * When `layer` runs in the decode regime (M == 1) its CTAs also ask the L2 for the packed weights / scales / zeros of
- * `next` -- the layer the caller will run a couple of launches later (patch_model() links every layer to the one two
- * positions after it).  next == NULL clears the hint.  Purely advisory: results never depend on it; the ranges of
- * `next` must stay allocated while the hint is set. */
-GLB_API int glb_prefetch_hint(const glb_linear* layer, const glb_linear* next);
-
 GLB_API void glb_set_pdl(int enabled);
 GLB_API int glb_get_pdl(void);
 

@@ -24,7 +24,6 @@ def main():
     ap.add_argument("--iters", type=int, default=50)
     ap.add_argument("--dtype", default="fp16")
     ap.add_argument("--tag", default="")
-    ap.add_argument("--link", type=int, default=0, help="link_layers distance (0: no L2 prefetch hint)")
     a = ap.parse_args()
     dev = "cuda:0"
     dt = torch.float16 if a.dtype == "fp16" else torch.bfloat16
@@ -38,9 +37,6 @@ def main():
         s = (torch.rand(N * K // a.gs, 1, generator=g, device=dev) * 0.002 + 0.0024).to(dt)   # std(W) * sqrt(K) ~ 1 (bench.py)
         z = (torch.rand(N * K // a.gs, 1, generator=g, device=dev) * 3 + 6).to(dt)
         layers.append(GemLiteLinear(4, a.gs, K, N, gd, gd).pack(W_q, s, z))
-    if a.link:
-        from gemlite_b200 import link_layers
-        link_layers(layers, a.link)
     x = (torch.randn(1, K, generator=g, device=dev) / 10).to(dt)
     # eager reference chain
     h = x
@@ -86,7 +82,7 @@ def main():
     gbs = nbytes / best / 1e3
     env = {k: os.environ[k] for k in os.environ if k.startswith("GLB_")}
     print(f"{a.tag:14s} us/layer={best:6.3f} GB/s={gbs:7.0f} frac={gbs / peak:5.3f} "
-          f"link={a.link} equal_eager={same}/{same_after} finite={finite} kernel={kern} absmax={float(h.float().abs().max()):.3g} env={env}", flush=True)
+          f"equal_eager={same}/{same_after} finite={finite} kernel={kern} absmax={float(h.float().abs().max()):.3g} env={env}", flush=True)
 
 
 if __name__ == "__main__":

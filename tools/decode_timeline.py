@@ -1,7 +1,6 @@
 """Diagnostic: pipelined timeline of the decode kernel (GLB_GEMV_DEBUG=4) inside a CUDA-graph replay."""
 import ctypes, os, sys
 os.environ["GLB_GEMV_DEBUG"] = "4"
-LINK = int(os.environ.get("TL_LINK", "0"))
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from gemlite_b200 import _cabi
@@ -14,9 +13,6 @@ for _ in range(L):
     s = (torch.rand(N * K // 128, 1, generator=g, device=dev) * 0.002 + 0.0024).half()
     z = (torch.rand(N * K // 128, 1, generator=g, device=dev) * 3 + 6).half()
     layers.append(A16W4_HQQ_INT(device=dev, dtype=torch.float16).from_weights(W_q, s, z))
-if LINK:
-    from gemlite_b200 import link_layers
-    link_layers(layers, LINK)
 x0 = (torch.randn(1, K, device=dev) / 10).half()
 def step():
     x = x0
