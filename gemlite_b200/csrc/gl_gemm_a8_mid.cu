@@ -27,7 +27,6 @@ constexpr int AM_KC = 1024;                      // k bytes per CTA
 constexpr int AM_PITCH = AM_KC + 64;             // row pitch: 68 x 16 B => the 8 lanes of a quarter-warp hit 8 bank groups
 constexpr int AM_NW = 16;
 constexpr int AM_TOK = 64;
-constexpr int AM_NT = AM_TOK / 8;
 constexpr int AM_WBYTES = AM_ROWS * AM_PITCH;    // 136 KB
 constexpr int AM_XBYTES = AM_TOK * AM_PITCH;     // 68 KB; reused as the [2][64][128] 32-bit reduction buffer
 constexpr int AM_SMEM = AM_WBYTES + AM_XBYTES + 128;
@@ -52,19 +51,21 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
                "l"(gsrc), "r"(bytes), "r"(ptx::smem_u32(bar))
                : "memory");
 }
-__device__ __forceinline__ uint32_t ld_dsmem_u32(uint32_t cluster_addr) {
-  uint32_t v;
-  asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(cluster_addr) : "memory");
+__device__ __forceinline__ uint4 ld_dsmem_u32x4(uint32_t cluster_addr) {
+  uint4 v;
+  asm volatile("ld.shared::cluster.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(cluster_addr) : "memory");
   return v;
 }
 
-template <bool IS_INT>
+// NT = 8-token tiles per pass (8: 64 tokens, 4: 32 tokens for M <= 32)
+template <bool IS_INT, int NT>
 __global__ void __launch_bounds__(AM_NW * 32, 1)
 gemm_a8w8_mid_kernel(const A8MidParams P) {
+  constexpr int TOK = NT * 8, NREG = 4 * NT, PLANE = 8 * NREG * 32;    // 32-bit words per k-half plane (fragment order)
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* wbuf = smem;                                           // [128][AM_PITCH]
   unsigned char* xbuf = wbuf + AM_WBYTES;                               // [64][AM_PITCH]
-  uint32_t* red = reinterpret_cast<uint32_t*>(xbuf);                    // [2 k halves][64][128] after the main loop
+  uint32_t* red = reinterpret_cast<uint32_t*>(xbuf);                    // [2 k halves][8 feature blocks][4 NT regs][32 lanes] after the main loop
   uint64_t* bars = reinterpret_cast<uint64_t*>(xbuf + AM_XBYTES);       // [4] weights (32 rows each), [1] x
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -92,8 +93,8 @@ gemm_a8w8_mid_kernel(const A8MidParams P) {
   const unsigned char* xa = xbuf + (size_t)g * AM_PITCH + (size_t)kh * 512 + 16 * t;
 
   int pass = 0;
-  for (int tok0 = 0; tok0 < P.M; tok0 += AM_TOK, ++pass) {
-    const int ntok = (P.M - tok0 < AM_TOK) ? (P.M - tok0) : AM_TOK;
+  for (int tok0 = 0; tok0 < P.M; tok0 += TOK, ++pass) {
+    const int ntok = (P.M - tok0 < TOK) ? (P.M - tok0) : TOK;
     // ---- x tile: one bulk copy per token row (rows >= M keep whatever the buffer holds; their outputs are never stored) ----
     if (threadIdx.x == 0) ptx::mbar_arrive_expect_tx(&bars[4], (uint32_t)ntok * AM_KC);
     if (pass > 0) ptx::fence_proxy_async_smem();                         // generic accesses of the reduction buffer before async-proxy writes
@@ -103,10 +104,10 @@ gemm_a8w8_mid_kernel(const A8MidParams P) {
     if (pass == 0) ptx::mbar_wait(&bars[fb >> 1], 0);
     ptx::mbar_wait(&bars[4], (uint32_t)(pass & 1));
 
-    int32_t acci[AM_NT][4];
-    float accf[AM_NT][4];
+    int32_t acci[NT][4];
+    float accf[NT][4];
 #pragma unroll
-    for (int n = 0; n < AM_NT; ++n)
+    for (int n = 0; n < NT; ++n)
 #pragma unroll
       for (int i = 0; i < 4; ++i) { acci[n][i] = 0; accf[n][i] = 0.f; }
 #pragma unroll 2
@@ -114,7 +115,7 @@ gemm_a8w8_mid_kernel(const A8MidParams P) {
       const uint4 p = *reinterpret_cast<const uint4*>(wa + o);
       const uint4 q = *reinterpret_cast<const uint4*>(wb + o);
 #pragma unroll
-      for (int n = 0; n < AM_NT; ++n) {
+      for (int n = 0; n < NT; ++n) {
         const uint4 xv = *reinterpret_cast<const uint4*>(xa + (size_t)n * 8 * AM_PITCH + o);
         if (IS_INT) {
           mma_s8(acci[n], p.x, q.x, p.y, q.y, xv.x, xv.y);
@@ -126,67 +127,81 @@ gemm_a8w8_mid_kernel(const A8MidParams P) {
       }
     }
 
-    // ---- reduction: k halves through shared memory, ranks through DSMEM ----
+    // ---- reduction: k halves through shared memory, ranks through DSMEM; partial tiles stay in FRAGMENT order
+    //      ([feature block][register][lane]: conflict-free stores, 128-bit loads) until the store decodes them ----
     __syncthreads();                                                    // every warp is done reading the x tile
+    {
+      uint32_t* plane = red + (size_t)kh * PLANE + (size_t)fb * NREG * 32 + lane;
 #pragma unroll
-    for (int n = 0; n < AM_NT; ++n)
+      for (int n = 0; n < NT; ++n)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        // d0 / d1: (feature g, tokens 2t, 2t+1); d2 / d3: (feature g + 8, same tokens)
-        const int f = fb * 16 + g + ((i & 2) ? 8 : 0), tok = n * 8 + 2 * t + (i & 1);
-        red[((size_t)kh * AM_TOK + tok) * AM_ROWS + f] = IS_INT ? (uint32_t)acci[n][i] : __float_as_uint(accf[n][i]);
-      }
+        for (int i = 0; i < 4; ++i) plane[(n * 4 + i) * 32] = IS_INT ? (uint32_t)acci[n][i] : __float_as_uint(accf[n][i]);
+    }
     __syncthreads();
-    for (int i = threadIdx.x; i < AM_TOK * AM_ROWS; i += AM_NW * 32) {
-      const uint32_t a = red[i], b = red[AM_TOK * AM_ROWS + i];
-      red[i] = IS_INT ? (uint32_t)((int32_t)a + (int32_t)b) : __float_as_uint(__uint_as_float(a) + __uint_as_float(b));
+    for (int i = threadIdx.x; i < PLANE / 4; i += AM_NW * 32) {
+      uint4* p0 = reinterpret_cast<uint4*>(red) + i;
+      const uint4 a = p0[0], b = p0[PLANE / 4];
+      if (IS_INT) p0[0] = make_uint4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);          // two's complement: exact
+      else p0[0] = make_uint4(__float_as_uint(__uint_as_float(a.x) + __uint_as_float(b.x)), __float_as_uint(__uint_as_float(a.y) + __uint_as_float(b.y)),
+                              __float_as_uint(__uint_as_float(a.z) + __uint_as_float(b.z)), __float_as_uint(__uint_as_float(a.w) + __uint_as_float(b.w)));
     }
     if (ks > 1) ptx::cluster_sync(); else __syncthreads();
     {
-      const int per = AM_TOK * AM_ROWS / ks;
+      const int per = (PLANE / 4) / ks;
       const uint32_t red_addr = ptx::smem_u32(red);
       for (int j = threadIdx.x; j < per; j += AM_NW * 32) {
-        const int i = (int)rank * per + j;
-        const int tok = i >> 7, fl = i & (AM_ROWS - 1);
-        const int m = tok0 + tok;
-        int32_t si = 0;
-        float sf = 0.f;
+        const int q4 = (int)rank * per + j;                             // 4 consecutive lanes of one register
+        uint4 v;
         if (ks > 1) {
-          for (int r = 0; r < ks; ++r) {
-            const uint32_t v = ld_dsmem_u32(ptx::mapa(red_addr + (uint32_t)i * 4u, (uint32_t)r));
-            if (IS_INT) si += (int32_t)v; else sf += __uint_as_float(v);
+          v = ld_dsmem_u32x4(ptx::mapa(red_addr + (uint32_t)q4 * 16u, 0u));
+          for (int r = 1; r < ks; ++r) {
+            const uint4 u = ld_dsmem_u32x4(ptx::mapa(red_addr + (uint32_t)q4 * 16u, (uint32_t)r));
+            if (IS_INT) { v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w; }
+            else {
+              v.x = __float_as_uint(__uint_as_float(v.x) + __uint_as_float(u.x)); v.y = __float_as_uint(__uint_as_float(v.y) + __uint_as_float(u.y));
+              v.z = __float_as_uint(__uint_as_float(v.z) + __uint_as_float(u.z)); v.w = __float_as_uint(__uint_as_float(v.w) + __uint_as_float(u.w));
+            }
           }
         } else {
-          if (IS_INT) si = (int32_t)red[i]; else sf = __uint_as_float(red[i]);
+          v = reinterpret_cast<const uint4*>(red)[q4];
         }
-        if (m >= P.M) continue;
-        const int f = feat0 + fl;
-        const int64_t oi = (int64_t)m * P.N + f;
-        if (IS_INT && P.out_dtype == GLB_INT32 && P.csm == 0 && !P.bias) {
-          reinterpret_cast<int32_t*>(P.y)[oi] = si;
-          continue;
-        }
-        float v = IS_INT ? (float)si : sf;                               // cvt.rn.f32.s32
+        // decode: element e = q4 * 4 + t -> (feature block, register = n * 4 + i, lane = 4 g + t)
+        const int e = q4 * 4;
+        const int blk = e / (NREG * 32), reg = (e >> 5) % NREG, gq = (e & 31) >> 2;
+        const int i = reg & 3, n = reg >> 2;
+        const int f = feat0 + blk * 16 + gq + ((i & 2) ? 8 : 0);
+        const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
         const float sb = (P.csm == 1 || P.csm == 3) ? P.scales_w[f] : 1.f;
-        if (P.csm == 1) v = __fmul_rn(v, sb);
-        else if (P.csm == 2) v = __fmul_rn(v, P.scales_x[m]);
-        else if (P.csm == 3) v = __fmul_rn(v, __fmul_rn(P.scales_x[m], sb));
         float bv = 0.f;
         if (P.bias) {
           if (P.out_dtype == GLB_FP16) bv = __half2float(reinterpret_cast<const __half*>(P.bias)[f]);
           else if (P.out_dtype == GLB_BF16) bv = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(P.bias)[f]);
           else bv = reinterpret_cast<const float*>(P.bias)[f];
         }
-        if (P.out_dtype == GLB_FP16) {
-          if (P.bias) v = __half2float(__float2half_rn(v)) + bv;
-          reinterpret_cast<__half*>(P.y)[oi] = __float2half_rn(v);
-        } else if (P.out_dtype == GLB_BF16) {
-          if (P.bias) v = __bfloat162float(__float2bfloat16_rn(v)) + bv;
-          reinterpret_cast<__nv_bfloat16*>(P.y)[oi] = __float2bfloat16_rn(v);
-        } else if (P.out_dtype == GLB_FP32) {
-          reinterpret_cast<float*>(P.y)[oi] = v + bv;
-        } else {
-          reinterpret_cast<int32_t*>(P.y)[oi] = (int32_t)(v + bv);
+#pragma unroll
+        for (int tq = 0; tq < 4; ++tq) {                                // the four lanes of the group: tokens 2 t + (i & 1)
+          const int m = tok0 + n * 8 + 2 * tq + (i & 1);
+          if (m >= P.M) continue;
+          const int64_t oi = (int64_t)m * P.N + f;
+          if (IS_INT && P.out_dtype == GLB_INT32 && P.csm == 0 && !P.bias) {
+            reinterpret_cast<int32_t*>(P.y)[oi] = (int32_t)vv[tq];
+            continue;
+          }
+          float o = IS_INT ? (float)(int32_t)vv[tq] : __uint_as_float(vv[tq]);        // cvt.rn.f32.s32
+          if (P.csm == 1) o = __fmul_rn(o, sb);
+          else if (P.csm == 2) o = __fmul_rn(o, P.scales_x[m]);
+          else if (P.csm == 3) o = __fmul_rn(o, __fmul_rn(P.scales_x[m], sb));
+          if (P.out_dtype == GLB_FP16) {
+            if (P.bias) o = __half2float(__float2half_rn(o)) + bv;
+            reinterpret_cast<__half*>(P.y)[oi] = __float2half_rn(o);
+          } else if (P.out_dtype == GLB_BF16) {
+            if (P.bias) o = __bfloat162float(__float2bfloat16_rn(o)) + bv;
+            reinterpret_cast<__nv_bfloat16*>(P.y)[oi] = __float2bfloat16_rn(o);
+          } else if (P.out_dtype == GLB_FP32) {
+            reinterpret_cast<float*>(P.y)[oi] = o + bv;
+          } else {
+            reinterpret_cast<int32_t*>(P.y)[oi] = (int32_t)(o + bv);
+          }
         }
       }
     }
@@ -233,7 +248,8 @@ int launch_gemm_a8_mid(const glb_linear& L, const void* x, const float* scales_x
   P.M = (int)M; P.N = (int)L.N; P.K = (int)L.K; P.csm = L.channel_scale_mode; P.out_dtype = L.output_dtype;
   P.ks = (int)(L.K / AM_KC);
   const bool is_int = (act_storage_dtype(L.input_dtype) == GLB_INT8);
-  auto kern = is_int ? gemm_a8w8_mid_kernel<true> : gemm_a8w8_mid_kernel<false>;
+  auto kern = (M <= 32) ? (is_int ? gemm_a8w8_mid_kernel<true, 4> : gemm_a8w8_mid_kernel<false, 4>)
+                        : (is_int ? gemm_a8w8_mid_kernel<true, 8> : gemm_a8w8_mid_kernel<false, 8>);
   GLB_ENSURE_SMEM(kern, AM_SMEM);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(L.N / AM_ROWS) * (unsigned)P.ks);

@@ -33,11 +33,10 @@ constexpr int MID_SUB = 32;                       // columns per sub-slab (one 1
 constexpr int MID_NW = 16;
 constexpr int MID_KC = 1024;                      // k per CTA
 constexpr int MID_ROWS = MID_KC / 8;              // packed rows per CTA (128)
-constexpr int MID_TOK = 64;                       // tokens per pass
-constexpr int MID_NT = MID_TOK / 8;
+constexpr int MID_TOK = 64;                       // tokens per pass (the NT = 4 instantiation uses 32)
 constexpr int MID_XSTRIDE = MID_ROWS * 16 + 16;   // bytes per token of the x tile: odd number of 16-byte units
 constexpr int MID_WBYTES = MID_ROWS * MID_COLS * 4;          // 64 KB
-constexpr int MID_XBYTES = MID_TOK * MID_XSTRIDE;            // 129 KB; reused as the [4][64][128] fp32 reduction buffer
+constexpr int MID_XBYTES = MID_TOK * MID_XSTRIDE;            // 129 KB; reused as the [4 k quarters] x 32 KB reduction planes
 constexpr int MID_SMEM = MID_WBYTES + MID_XBYTES + 64 + 1024;
 static_assert(4 * MID_TOK * MID_COLS * 4 <= MID_XBYTES, "reduction buffer must fit in the x tile");
 
@@ -98,20 +97,22 @@ template <bool BF16> __device__ __forceinline__ void dequant_word(uint32_t q, ui
   }
 }
 
-__device__ __forceinline__ float ld_dsmem_f32(uint32_t cluster_addr) {
-  float v;
-  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(cluster_addr) : "memory");
+__device__ __forceinline__ float4 ld_dsmem_f32x4(uint32_t cluster_addr) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(cluster_addr) : "memory");
   return v;
 }
 
-template <bool BF16>
+// NT = 8-token tiles per pass (8: 64 tokens, 4: 32 tokens for M <= 32)
+template <bool BF16, int NT>
 __global__ void __launch_bounds__(MID_NW * 32, 1)
 gemm_a16w4_mid_kernel(const __grid_constant__ CUtensorMap tmap_w, const MidParams P) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* wbuf = smem_raw;                                   // 4 sub-slabs x [128 rows][128 B], TMA 128B swizzle
   if ((ptx::smem_u32(smem_raw) & 1023u) != 0u) __trap();
   unsigned char* xs = wbuf + MID_WBYTES;                            // [64 tokens][MID_XSTRIDE]
-  float* red = reinterpret_cast<float*>(xs);                        // [4 k quarters][64][128] after the main loop
+  float* red = reinterpret_cast<float*>(xs);                        // [4 k quarters][4 sub-slabs][16 NT regs][32 lanes] after the main loop
+  constexpr int TOK = NT * 8, NREG = 8 * NT, PLANE = 4 * NREG * 32;   // floats per k-quarter plane
   uint64_t* bars = reinterpret_cast<uint64_t*>(xs + MID_XBYTES);    // [4] one per sub-slab
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -144,22 +145,31 @@ gemm_a16w4_mid_kernel(const __grid_constant__ CUtensorMap tmap_w, const MidParam
   const int ncol = col0 + sl * MID_SUB + 4 * g8;                    // first of this lane's 4 columns
   auto dup = [](uint32_t v) { return v | (v << 16); };
 
-  for (int tok0 = 0; tok0 < P.M; tok0 += MID_TOK) {
-    // ---- stage the x tile: tokens tok0 .. tok0+63, k in [kbeg, kbeg + 1024), one permuted 16-byte word per packed row ----
+  for (int tok0 = 0; tok0 < P.M; tok0 += TOK) {
+    // ---- stage the x tile: tokens tok0 .. tok0+TOK-1, k in [kbeg, kbeg + 1024), one permuted 16-byte word per packed row;
+    //      eight loads in flight per thread (one L2 round trip per batch instead of one per word) ----
     {
       const uint16_t* xg = reinterpret_cast<const uint16_t*>(P.x) + kbeg;
-      for (int i = threadIdx.x; i < MID_TOK * MID_ROWS; i += MID_NW * 32) {
-        const int tok = i >> 7, r = i & (MID_ROWS - 1);
-        const int m = tok0 + tok;
-        uint4 o = make_uint4(0u, 0u, 0u, 0u);
-        if (m < P.M) {
-          const uint4 v = *reinterpret_cast<const uint4*>(xg + (size_t)m * P.K + (size_t)r * 8);
-          o.x = __byte_perm(v.x, v.z, 0x5410);   // (k0,k4)
-          o.y = __byte_perm(v.x, v.z, 0x7632);   // (k1,k5)
-          o.z = __byte_perm(v.y, v.w, 0x5410);   // (k2,k6)
-          o.w = __byte_perm(v.y, v.w, 0x7632);   // (k3,k7)
+      for (int i0 = threadIdx.x; i0 < TOK * MID_ROWS; i0 += 8 * MID_NW * 32) {
+        uint4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int i = i0 + j * MID_NW * 32;
+          const int m = tok0 + (i >> 7);
+          v[j] = make_uint4(0u, 0u, 0u, 0u);
+          if (i < TOK * MID_ROWS && m < P.M) v[j] = *reinterpret_cast<const uint4*>(xg + (size_t)m * P.K + (size_t)(i & (MID_ROWS - 1)) * 8);
         }
-        *reinterpret_cast<uint4*>(xs + (size_t)tok * MID_XSTRIDE + (size_t)r * 16) = o;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int i = i0 + j * MID_NW * 32;
+          if (i >= TOK * MID_ROWS) continue;
+          uint4 o;
+          o.x = __byte_perm(v[j].x, v[j].z, 0x5410);   // (k0,k4)
+          o.y = __byte_perm(v[j].x, v[j].z, 0x7632);   // (k1,k5)
+          o.z = __byte_perm(v[j].y, v[j].w, 0x5410);   // (k2,k6)
+          o.w = __byte_perm(v[j].y, v[j].w, 0x7632);   // (k3,k7)
+          *reinterpret_cast<uint4*>(xs + (size_t)(i >> 7) * MID_XSTRIDE + (size_t)(i & (MID_ROWS - 1)) * 16) = o;
+        }
       }
     }
     __syncthreads();
@@ -168,11 +178,11 @@ gemm_a16w4_mid_kernel(const __grid_constant__ CUtensorMap tmap_w, const MidParam
       __syncwarp();
     }
 
-    float acc[2][MID_NT][4];
+    float acc[2][NT][4];
 #pragma unroll
     for (int pr = 0; pr < 2; ++pr)
 #pragma unroll
-      for (int nt = 0; nt < MID_NT; ++nt) acc[pr][nt][0] = acc[pr][nt][1] = acc[pr][nt][2] = acc[pr][nt][3] = 0.f;
+      for (int nt = 0; nt < NT; ++nt) acc[pr][nt][0] = acc[pr][nt][1] = acc[pr][nt][2] = acc[pr][nt][3] = 0.f;
 
     for (int rg = 0; rg < 32; rg += rpg) {                            // groups of this warp's k quarter
       const int g = (kbeg >> 3) / rpg + (row_beg + rg) / rpg;         // global group index
@@ -193,7 +203,7 @@ gemm_a16w4_mid_kernel(const __grid_constant__ CUtensorMap tmap_w, const MidParam
           dequant_word<BF16>(q.w, s2[3], z2[3], P.mode, w[3]);
           const unsigned char* xr = xs + (size_t)g8 * MID_XSTRIDE + (size_t)row * 16;
 #pragma unroll
-          for (int nt = 0; nt < MID_NT; ++nt) {
+          for (int nt = 0; nt < NT; ++nt) {
             const uint4 xv = *reinterpret_cast<const uint4*>(xr + (size_t)nt * 8 * MID_XSTRIDE);
             mma16816<BF16>(acc[0][nt], w[0][0], w[1][0], w[0][1], w[1][1], xv.x, xv.y);
             mma16816<BF16>(acc[0][nt], w[0][2], w[1][2], w[0][3], w[1][3], xv.z, xv.w);
@@ -204,44 +214,61 @@ gemm_a16w4_mid_kernel(const __grid_constant__ CUtensorMap tmap_w, const MidParam
       }
     }
 
-    // ---- reduction: k-quarter warps through shared memory, cluster ranks through DSMEM, both in fixed order ----
+    // ---- reduction: k-quarter warps through shared memory, cluster ranks through DSMEM, both in fixed order.  The
+    //      partial tiles stay in FRAGMENT order ([sub-slab][register][lane]: conflict-free 32-bit stores, 128-bit loads)
+    //      until the very last step decodes (register, lane) -> (token, column) for the store ----
     __syncthreads();                                                  // every warp is done reading the x tile
+    {
+      float* plane = red + (size_t)kq * PLANE + (size_t)sl * NREG * 32 + lane;
 #pragma unroll
-    for (int pr = 0; pr < 2; ++pr)
+      for (int pr = 0; pr < 2; ++pr)
 #pragma unroll
-      for (int nt = 0; nt < MID_NT; ++nt) {
-        // d0: (col 4 g8 + 2 pr, token 2 t4)  d1: (same col, token + 1)  d2 / d3: col + 1
-        float* base = red + ((size_t)kq * MID_TOK + (nt * 8 + 2 * t4)) * MID_COLS + sl * MID_SUB + 4 * g8 + 2 * pr;
-        base[0] = acc[pr][nt][0];
-        base[MID_COLS] = acc[pr][nt][1];
-        base[1] = acc[pr][nt][2];
-        base[MID_COLS + 1] = acc[pr][nt][3];
-      }
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) plane[((pr * NT + nt) * 4 + i) * 32] = acc[pr][nt][i];
+    }
     __syncthreads();
-    for (int i = threadIdx.x; i < MID_TOK * MID_COLS; i += MID_NW * 32)
-      red[i] = (red[i] + red[MID_TOK * MID_COLS + i]) + (red[2 * MID_TOK * MID_COLS + i] + red[3 * MID_TOK * MID_COLS + i]);
+    for (int i = threadIdx.x; i < PLANE / 4; i += MID_NW * 32) {
+      float4* p0 = reinterpret_cast<float4*>(red) + i;
+      const float4 a = p0[0], b = p0[PLANE / 4], c = p0[2 * (PLANE / 4)], d = p0[3 * (PLANE / 4)];
+      p0[0] = make_float4((a.x + b.x) + (c.x + d.x), (a.y + b.y) + (c.y + d.y), (a.z + b.z) + (c.z + d.z), (a.w + b.w) + (c.w + d.w));
+    }
     if (ks > 1) ptx::cluster_sync(); else __syncthreads();
     {
-      const int per = MID_TOK * MID_COLS / ks;                        // elements this rank finishes
+      const int per = (PLANE / 4) / ks;                               // float4 groups this rank finishes
       const uint32_t red_addr = ptx::smem_u32(red);
       for (int j = threadIdx.x; j < per; j += MID_NW * 32) {
-        const int i = (int)rank * per + j;
-        const int tok = i >> 7, col = i & (MID_COLS - 1);
-        const int m = tok0 + tok;
-        float v = 0.f;
+        const int q4 = (int)rank * per + j;                           // float4 index: 4 consecutive lanes of one register
+        float4 v;
         if (ks > 1) {
-          for (int r = 0; r < ks; ++r) v += ld_dsmem_f32(ptx::mapa(red_addr + (uint32_t)i * 4u, (uint32_t)r));
+          v = ld_dsmem_f32x4(ptx::mapa(red_addr + (uint32_t)q4 * 16u, 0u));
+          for (int r = 1; r < ks; ++r) {
+            const float4 u = ld_dsmem_f32x4(ptx::mapa(red_addr + (uint32_t)q4 * 16u, (uint32_t)r));
+            v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+          }
         } else {
-          v = red[i];
+          v = reinterpret_cast<const float4*>(red)[q4];
         }
-        if (m < P.M) {
-          const int64_t oi = (int64_t)m * P.N + col0 + col;
+        // decode: element e = q4 * 4 + t4 -> (sub-slab, register = (pr * NT + nt) * 4 + i, lane = 4 g8 + t4)
+        const int e = q4 * 4;
+        const int slot = e / (NREG * 32), reg = (e >> 5) % NREG, gq = (e & 31) >> 2;
+        const int i = reg & 3, nt = (reg >> 2) % NT, pr = reg / (4 * NT);
+        const int col = col0 + slot * MID_SUB + 4 * gq + 2 * pr + (i >> 1);
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+        float bv = 0.f;
+        if (P.bias) bv = BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(P.bias)[col]) : __half2float(reinterpret_cast<const __half*>(P.bias)[col]);
+#pragma unroll
+        for (int tq = 0; tq < 4; ++tq) {                              // the four lanes of the group: tokens 2 t4 + (i & 1)
+          const int m = tok0 + nt * 8 + 2 * tq + (i & 1);
+          if (m >= P.M) continue;
+          float o = vv[tq];
+          const int64_t oi = (int64_t)m * P.N + col;
           if (BF16) {
-            if (P.bias) v = __bfloat162float(__float2bfloat16_rn(v)) + __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(P.bias)[col0 + col]);
-            reinterpret_cast<__nv_bfloat16*>(P.y)[oi] = __float2bfloat16_rn(v);
+            if (P.bias) o = __bfloat162float(__float2bfloat16_rn(o)) + bv;
+            reinterpret_cast<__nv_bfloat16*>(P.y)[oi] = __float2bfloat16_rn(o);
           } else {
-            if (P.bias) v = __half2float(__float2half_rn(v)) + __half2float(reinterpret_cast<const __half*>(P.bias)[col0 + col]);
-            reinterpret_cast<__half*>(P.y)[oi] = __float2half_rn(v);
+            if (P.bias) o = __half2float(__float2half_rn(o)) + bv;
+            reinterpret_cast<__half*>(P.y)[oi] = __float2half_rn(o);
           }
         }
       }
@@ -286,7 +313,8 @@ int launch_gemm_mid(const glb_linear& L, const void* x, void* y, int64_t M, cons
   P.M = (int)M; P.N = (int)L.N; P.K = (int)L.K; P.group_size = L.group_size; P.mode = L.W_group_mode;
   P.ks = (int)(L.K / MID_KC);
   const bool bf = (L.input_dtype == GLB_BF16);
-  auto kern = bf ? gemm_a16w4_mid_kernel<true> : gemm_a16w4_mid_kernel<false>;
+  auto kern = (M <= 32) ? (bf ? gemm_a16w4_mid_kernel<true, 4> : gemm_a16w4_mid_kernel<false, 4>)
+                        : (bf ? gemm_a16w4_mid_kernel<true, 8> : gemm_a16w4_mid_kernel<false, 8>);
   GLB_ENSURE_SMEM(kern, MID_SMEM);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(L.N / MID_COLS) * (unsigned)P.ks);

@@ -784,7 +784,7 @@ def test_a8w8_batched_decode_kernel(kind, shape):
         layer = cls(device=DEV, dtype=torch.float16).from_weights(W.clone().to(DEV), bias=None if b is None else b.to(DEV))
         Wc = layer.W_q.data.t().contiguous()                          # (N, K) codes
         sw = layer.scales.data.view(1, -1).float()
-        for M in (17, 40, 64, 65, 100, 128):
+        for M in (17, 32, 40, 64, 65, 100, 128):
             x = xgen(M, K, torch.float16, 70 + M).to(DEV)
             y = layer(x)
             assert _cabi.last_kernel() == f"gemm_a8w8_{kind}_mma_mid", (M, _cabi.last_kernel())
