@@ -277,7 +277,51 @@ int launch_aq_mx(const void* x, int64_t M, int64_t K, int mx_dtype, void* q, voi
   return GLB_OK;
 }
 
+// MX-quantised activations (e4m3 bytes or e2m1 nibbles + one e8m0 scale per 32) -> their exact values in bf16.
+// e4m3 has 4 significant bits, e2m1 2, the scale is a power of two >= 2^-30: every product is representable in bf16, so
+// a bf16 tensor-core GEMM over the expanded activations accumulates exactly the products tl.dot_scaled would
+// (gemm_kernels.py:508-524) -- used to run A8W4 / A4W4 MXFP dynamic layers on the MXFP4 tcgen05 kernels (gl_api.cu).
+template <bool FP4>
+__global__ void __launch_bounds__(256) expand_act_mx_kernel(const uint8_t* __restrict__ q, const uint8_t* __restrict__ scales,
+                                                            __nv_bfloat16* __restrict__ out, int64_t M, int64_t K) {
+  const int64_t per_row = K >> 3;                                  // 8 k per thread
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * per_row) return;
+  const int64_t r = i / per_row, t = i - r * per_row;
+  const float sc = e8m0_to_float(scales[r * (K >> 5) + (t >> 2)]);
+  float v[8];
+  if (FP4) {
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(q + r * (K >> 1) + t * 4);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fp4_e2m1_to_float((w >> (4 * j)) & 15u);
+  } else {
+    const uint2 w = *reinterpret_cast<const uint2*>(q + r * K + t * 8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fp8e4_to_float((uint8_t)(((j < 4) ? w.x : w.y) >> (8 * (j & 3))));
+  }
+  uint32_t o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j] * sc, v[2 * j + 1] * sc);      // exact
+    o[j] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  *reinterpret_cast<uint4*>(out + r * K + t * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 }  // namespace
+
+int launch_expand_act_mx(const void* q, const void* scales, void* out_bf16, int64_t M, int64_t K, int mx_dtype, cudaStream_t stream) {
+  const int64_t threads = M * (K >> 3);
+  const unsigned grid = (unsigned)((threads + 255) / 256);
+  if (mx_dtype == GLB_MXFP4)
+    expand_act_mx_kernel<true><<<grid, 256, 0, stream>>>((const uint8_t*)q, (const uint8_t*)scales, (__nv_bfloat16*)out_bf16, M, K);
+  else
+    expand_act_mx_kernel<false><<<grid, 256, 0, stream>>>((const uint8_t*)q, (const uint8_t*)scales, (__nv_bfloat16*)out_bf16, M, K);
+  count_launch();
+  GLB_CHECK_CUDA(cudaGetLastError());
+  return GLB_OK;
+}
+
 }  // namespace glb
 
 using namespace glb;

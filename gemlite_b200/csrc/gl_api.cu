@@ -180,6 +180,22 @@ static int validate(const glb_linear* L, int64_t M) {
   return GLB_OK;
 }
 
+// MXFP dynamic layers with MXFP4 weights and MX micro-scaled activations (A8W4_MXFP_dynamic post_scale=False,
+// A4W4_MXFP_dynamic; helper.py:732-893): the quantised activations are expanded to their exact bf16 values
+// (gl_actquant.cu) into the workspace and the layer then runs as the MXFP4 weight-only layer it also is -- on the
+// tcgen05 / streaming MXFP4 kernels instead of the CUDA-core general kernel.  Same products as tl.dot_scaled, fp32
+// accumulation.  (Native block-scaled tcgen05.mma would skip the expansion; not built yet.)
+static bool mx_expand_view(const glb_linear& L, glb_linear* as_weight_only) {
+  if (!(L.input_dtype == GLB_MXFP8 || L.input_dtype == GLB_MXFP4) || L.channel_scale_mode != 4) return false;
+  if (L.output_dtype != GLB_BF16) return false;
+  if (L.W_nbits != 4 || L.elements_per_sample != 2 || L.group_size != 32) return false;
+  glb_linear W = L;
+  W.input_dtype = GLB_MXBF16; W.output_dtype = GLB_MXBF16; W.scaled_activations = 0; W.channel_scale_mode = 0; W.W_group_mode = 2;
+  if (as_weight_only) *as_weight_only = W;
+  return true;
+}
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
 // reference dispatch: core.py:100-114
 static int pick_matmul_type(const glb_linear& L, int64_t M) {
   if (M > 64) return GLB_MM_GEMM;
@@ -212,6 +228,11 @@ extern "C" unsigned long long glb_stream_capture_id(void* stream_) {
 
 extern "C" size_t glb_workspace_bytes(const glb_linear* L, int64_t M, int matmul_type) {
   if (!L || M <= 0) return 0;
+  {
+    glb_linear W;
+    if (mx_expand_view(*L, &W) && (gemm_mx_tc2_supported(W, M) || gemv_mx_supported(W, M)))
+      return align256(gemm_tc_workspace(W, M)) + (size_t)M * (size_t)L->K * 2;
+  }
   const bool was_auto = (matmul_type == GLB_MM_AUTO);
   if (was_auto) matmul_type = pick_matmul_type(*L, M);
   // same routing as glb_matmul: the decode kernel first (its chained hand-off keeps arrival counters in the workspace)
@@ -232,6 +253,19 @@ extern "C" int glb_matmul(const glb_linear* L, const void* x, const void* scales
   GLB_REQUIRE(matmul_type >= GLB_MM_AUTO && matmul_type <= GLB_MM_GEMM, GLB_ERR_INVALID, "bad matmul_type %d", matmul_type);
   if (L->channel_scale_mode >= 2)
     GLB_REQUIRE(scales_x != nullptr, GLB_ERR_INVALID, "channel_scale_mode %d needs activation scales", L->channel_scale_mode);
+  {
+    glb_linear W;
+    if (mx_expand_view(*L, &W) && (gemm_mx_tc2_supported(W, M) || gemv_mx_supported(W, M))) {
+      const size_t inner = align256(gemm_tc_workspace(W, M)), need = inner + (size_t)M * (size_t)L->K * 2;
+      GLB_REQUIRE(workspace && workspace_bytes >= need, GLB_ERR_WORKSPACE, "MX dynamic layer: workspace too small: need %zu bytes, got %zu",
+                  need, workspace_bytes);
+      void* xb = reinterpret_cast<unsigned char*>(workspace) + inner;
+      rc = launch_expand_act_mx(x, scales_x, xb, M, L->K, L->input_dtype, stream);
+      if (rc != GLB_OK) return rc;
+      if (gemv_mx_supported(W, M)) return launch_gemv_mx(W, xb, y, M, bias, stream);
+      return launch_gemm_tc(W, xb, nullptr, y, M, workspace, inner, bias, stream);
+    }
+  }
   const bool was_auto = (matmul_type == GLB_MM_AUTO);
   if (was_auto) matmul_type = pick_matmul_type(*L, M);
   const bool gemv_name = (matmul_type <= GLB_MM_GEMV_SPLITK);

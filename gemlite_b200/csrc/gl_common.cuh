@@ -91,6 +91,7 @@ bool gemv_a8_supported(const glb_linear& L, int64_t M);
 int launch_gemv_a8(const glb_linear& L, const void* x, const float* scales_x, void* y, int64_t M, const void* bias,
                    cudaStream_t stream);
 size_t gemm_tc2_workspace(const glb_linear& L, int64_t M);
+int launch_expand_act_mx(const void* q, const void* scales, void* out_bf16, int64_t M, int64_t K, int mx_dtype, cudaStream_t stream);
 bool gemm_mid_supported(const glb_linear& L, int64_t M);
 bool gemm_a8_mid_supported(const glb_linear& L, int64_t M);
 int launch_gemm_a8_mid(const glb_linear& L, const void* x, const float* scales_x, void* y, int64_t M, const void* bias,

@@ -513,7 +513,12 @@ def test_mx_dynamic_layers_vs_oracle():
             for M in (1, 5, 40, 130):
                 x = xgen(M, K, dt, 700 + M)
                 y = layer(x.to(DEV))
-                assert _cabi.last_kernel() == "generic_cuda_core"
+                # MXFP4 weights + MX micro-scaled activations in bf16: exact bf16 expansion of the quantised activations, then
+                # the MXFP4 tensor-core / streaming kernels (gl_api.cu: mx_expand_view); everything else: general kernel
+                expanded = (dt == torch.bfloat16 and layer.channel_scale_mode == 4 and layer.W_nbits == 4
+                            and cls is not A4W4_NVFP_dynamic)
+                want = ("gemv_mxfp4" if M <= 4 else "gemm_a16w4_mxfp4_tcgen05_2cta") if expanded else "generic_cuda_core"
+                assert _cabi.last_kernel() == want, (cls.__name__, kw, dt, M, _cabi.last_kernel())
                 if layer.channel_scale_mode == 2:
                     # per-token fp8 activations: the GPU quantiser divides with div.full.f32 like the reference's Triton
                     # build (codes / scales bit-equal to it: test_gpu_vs_reference.py), the CPU oracle with the IEEE

@@ -245,7 +245,7 @@ def test_same_inputs_same_outputs_as_reference(both, name):
                 assert ex_mean <= rx_mean * 1.05 + 1e-5, (name, key, kern, "mean vs exact", ex_mean, rx_mean)
             else:
                 assert e_max <= r_max * 1.05 + 2 * ulp, (name, key, kern, "max", e_max, r_max)
-                assert e_mean <= r_mean * 1.05 + 1e-5, (name, key, kern, "mean", e_mean, r_mean)
+                assert e_mean <= r_mean * 1.05 + 5e-5, (name, key, kern, "mean", e_mean, r_mean)
     if case.get("actq"):
         for i, M in enumerate(case["Ms"]):
             x = refdual.x_for(case, M, i)
