@@ -156,7 +156,7 @@ SAMPLE_LAYERS = 16            # CPU arm: distinct layers per step (143 MB of pac
 
 def workload_config(world):
     return {"workload": f"A16W4 gs={GROUP} decode M=1 K=N={K} fp16 (BASELINE configs[1]); step = {LAYERS} "
-                        f"{'chained layers' if world == 1 else 'column shards of wide layers (N_global=%d) + one NCCL all-gather' % (N * world)}",
+                        f"{'chained layers' if world == 1 else 'column shards of wide layers (N_global=%d) + one output all-gather per step' % (N * world)}",
             "l2": f"{LAYERS} distinct layers = {LAYERS * ALGO_BYTES / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)",
             "launch": "CUDA graph replay, programmatic dependent launch",
             "chain": ("independent layers (diagnostic)" if INDEPENDENT else "y_i feeds x_{i+1}") if world == 1 else "same x for every shard call",
@@ -462,7 +462,7 @@ def run_ours(args, rank, world, local_rank):
 
     dev = torch.device(f"cuda:{local_rank}")
     torch.cuda.set_device(dev)
-    layers = []
+    layers, shards = [], []
     if world == 1:
         for (W_q, scales, zeros) in make_weights(dev, 1 if ALIAS else LAYERS, seed=0):
             layers.append(A16W4_HQQ_INT(device=dev, dtype=torch.float16).from_weights(W_q, scales, zeros))
@@ -474,7 +474,8 @@ def run_ours(args, rank, world, local_rank):
         for (W_q, scales, zeros) in make_weights(dev, LAYERS, seed=0, n_out=N * world):
             full = A16W4_HQQ_INT(device=dev, dtype=torch.float16).from_weights(W_q, scales, zeros)
             del W_q, scales, zeros
-            layers.append(ColumnShardedLinear(full, rank, world).local)
+            shards.append(ColumnShardedLinear(full, rank, world))
+            layers.append(shards[-1].local)
             del full
         torch.cuda.empty_cache()
     torch.cuda.synchronize()
@@ -524,10 +525,49 @@ def run_ours(args, rank, world, local_rank):
     else:
         graph, result = capture(False)
 
-    def one_step():
+    def nccl_step():
         graph.replay()
         if world > 1 and not gather_in_graph:
             dist.all_gather_into_tensor(gathered.view(-1), outs.view(-1))
+
+    # B200-native exchange for M = 1: the decode kernel's epilogue stores its 32 outputs into every rank's
+    # symmetric output buffer over NVLink; one barrier pair per step replaces stack + all-gather.  NCCL stays the baseline.
+    fused = {"available": False}
+    fgraph = None
+    if world > 1 and os.environ.get("BENCH_NO_FUSED_GATHER", "0") != "1":
+        try:
+            from gemlite_b200.sharding import SymmetricOutputs
+            sym = SymmetricOutputs(LAYERS, N * world, torch.float16, dev)
+
+            def fused_body():
+                sym.barrier()                       # every rank has finished reading the previous step's rows
+                for i, sh in enumerate(shards):
+                    sh.forward_scatter(x_in, sym, i)
+                sym.barrier()                       # every rank's columns have landed everywhere
+
+            fused_body()
+            torch.cuda.synchronize()
+            nccl_step()
+            torch.cuda.synchronize()
+            same = bool(torch.equal(sym.buf.view(LAYERS, world, N), gathered.view(world, LAYERS, N).transpose(0, 1)))
+            fgraph = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(stream):
+                fused_body()
+                torch.cuda.synchronize()
+                with torch.cuda.graph(fgraph, stream=stream):
+                    fused_body()
+            fused = {"available": True, "equals_nccl_gather": same,
+                     "how": "decode epilogue stores to every rank's symmetric buffer (glb_matmul_bcast) + 2 symmetric-memory barriers per step, in one CUDA graph"}
+        except Exception as e:      # keep the NCCL line alive, but say why
+            fused = {"available": False, "error": f"{type(e).__name__}: {str(e).splitlines()[0][:200] if str(e) else ''}"}
+            fgraph = None
+            torch.cuda.synchronize()
+
+    def one_step():
+        if fgraph is not None:
+            fgraph.replay()
+        else:
+            nccl_step()
 
     # NCCL connects channels lazily (also for graph-captured collectives): with N > 1 the first replays are milliseconds
     # slower than the steady state, so more untimed steps than asked are run (reported as `warmup`)
@@ -559,6 +599,20 @@ def run_ours(args, rank, world, local_rank):
     ms_step = ms_total / args.steps
     value = world * LAYERS * ALGO_BYTES / (ms_step * 1e-3) / 1e9
 
+    nccl_ms = None
+    if world > 1 and fgraph is not None:            # the NCCL variant of the same step, same timing rules (reported next to it)
+        for _ in range(n_warm):
+            nccl_step()
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(args.steps):
+            nccl_step()
+        b.record(); torch.cuda.synchronize(); dist.barrier()
+        tt = torch.tensor([a.elapsed_time(b) / args.steps], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        nccl_ms = tt.item()
+
     # kernel-only time inside the step (the decode launches without the gather), for the roofline object
     if world > 1 and gather_in_graph:
         kgraph, _ = capture(False)
@@ -584,7 +638,7 @@ def run_ours(args, rank, world, local_rank):
         x_in.copy_(xh, non_blocking=True)
         one_step()
         if world > 1:
-            yh.copy_(gathered[-1], non_blocking=True)
+            yh.copy_((sym.buf[-1, -N:] if fgraph is not None else gathered[-1]).view(1, N), non_blocking=True)
         else:
             yh.copy_(y_static, non_blocking=True)
         torch.cuda.synchronize()
@@ -643,7 +697,12 @@ def run_ours(args, rank, world, local_rank):
     cfg = workload_config(world)
     handoff = {"handoff": "griddepcontrol.wait (programmatic dependent launch); a device-side arrival counter was measured slower (DESIGN.md 3.3)"}
     if world > 1:
-        handoff["gather"] = "NCCL all-gather captured in the step's CUDA graph" if gather_in_graph else "NCCL all-gather issued eagerly after the graph replay"
+        handoff["gather"] = ("fused: " + fused["how"]) if fgraph is not None else \
+            ("NCCL all-gather captured in the step's CUDA graph" if gather_in_graph else "NCCL all-gather issued eagerly after the graph replay")
+        handoff["fused_gather"] = fused
+        handoff["nccl_baseline"] = None if nccl_ms is None else {
+            "ms_per_step": nccl_ms, "value": world * LAYERS * ALGO_BYTES / (nccl_ms * 1e-3) / 1e9, "unit": "GB/s",
+            "gather": "captured in the graph" if gather_in_graph else "eager"}
     line = {
         "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": n_warm,
         "ms_per_step": ms_step, "ms_per_step_rank0_min_median_max": [per_step[0], per_step[len(per_step) // 2], per_step[-1]], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",

@@ -39,7 +39,7 @@ class GlbLinear(ctypes.Structure):
 
 EXPORTS = [
     "glb_version", "glb_last_error", "glb_last_kernel", "glb_launch_count", "glb_pack_cols", "glb_unpack_cols",
-    "glb_quant_act_per_token", "glb_quant_act_mx", "glb_stream_capture_id", "glb_workspace_bytes", "glb_matmul", "glb_set_pdl", "glb_get_pdl", "glb_debug_timeline", 
+    "glb_quant_act_per_token", "glb_quant_act_mx", "glb_stream_capture_id", "glb_workspace_bytes", "glb_matmul", "glb_set_pdl", "glb_get_pdl", "glb_debug_timeline", "glb_matmul_bcast", 
 ]
 
 
@@ -79,6 +79,8 @@ def load():
         lib.glb_workspace_bytes.restype = sz
         lib.glb_matmul.argtypes = [ctypes.POINTER(GlbLinear), vp, vp, vp, i64, i32, vp, sz, vp, vp]
         lib.glb_matmul.restype = i32
+        lib.glb_matmul_bcast.argtypes = [ctypes.POINTER(GlbLinear), vp, vp, ctypes.POINTER(ctypes.c_void_p), i32, i64, i64, vp, vp]
+        lib.glb_matmul_bcast.restype = i32
         lib.glb_set_pdl.argtypes = [i32]
         lib.glb_set_pdl.restype = None
         lib.glb_get_pdl.restype = i32

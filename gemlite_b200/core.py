@@ -217,6 +217,26 @@ def _matmul(x2d: Tensor, bias: Optional[Tensor], tensor_args: List[Tensor], meta
     return out
 
 
+def matmul_bcast(x2d: Tensor, bias: Optional[Tensor], tensor_args: List[Tensor], meta_args: List[int], dst_ptrs, col0: int) -> None:
+    """Decode call (M == 1) whose result row is stored at column `col0` of every destination in `dst_ptrs` (a ctypes
+    array of device-accessible pointers: this rank's gathered-output row and the peers' symmetric buffers) -- the fused
+    output all-gather of `sharding.SymmetricOutputs`.  Raises NotImplementedError when the layer / batch size has no
+    multi-destination kernel (the caller then uses forward + a collective)."""
+    W_q, scales, zeros = tensor_args
+    _cabi.require_cuda(x2d, "matmul_bcast")
+    if x2d.shape[0] != 1 or not x2d.is_contiguous():
+        raise NotImplementedError("matmul_bcast: one contiguous activation row")
+    desc = _make_desc(W_q, scales, zeros, meta_args)
+    if x2d.shape[1] != desc.K:
+        raise RuntimeError(f"matmul_bcast: activations have {x2d.shape[1]} input features, the layer expects {desc.K}")
+    if bias is not None and (bias.dtype != x2d.dtype or not bias.is_contiguous()):
+        bias = bias.to(x2d.dtype).contiguous()
+    with torch.cuda.device(x2d.device):
+        rc = _cabi.load().glb_matmul_bcast(ctypes.byref(desc), x2d.data_ptr(), None, dst_ptrs, len(dst_ptrs), int(col0), 1,
+                                           bias.data_ptr() if bias is not None else None, _cabi.current_stream_ptr(x2d.device))
+    _cabi.check(rc, "glb_matmul_bcast")
+
+
 # ---------------------------------------------------------------------------------------------------
 # functional forward (custom op so that torch.compile / vLLM can trace through it)
 # ---------------------------------------------------------------------------------------------------

@@ -194,7 +194,9 @@ static bool mx_expand_view(const glb_linear& L, glb_linear* as_weight_only) {
   if (as_weight_only) *as_weight_only = W;
   return true;
 }
-static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+// the expanded activations live BEHIND whatever the inner launch uses of the (shared, per-stream) workspace, and never inside
+// its first 64 KB: those are the split-K arrival counters of every layer on the stream and must stay zero between launches
+static size_t expand_offset(size_t inner_ws) { const size_t a = (inner_ws + 255) & ~(size_t)255; return a < 65536 ? 65536 : a; }
 
 // reference dispatch: core.py:100-114
 static int pick_matmul_type(const glb_linear& L, int64_t M) {
@@ -216,6 +218,18 @@ extern "C" void glb_set_pdl(int enabled) { g_pdl_enabled.store(enabled ? 1 : 0);
 extern "C" int glb_get_pdl(void) { return g_pdl_enabled.load(); }
 extern "C" int glb_debug_timeline(unsigned long long* out, int max_words) { return debug_read_timeline(out, max_words); }
 
+extern "C" int glb_matmul_bcast(const glb_linear* L, const void* x, const void* scales_x, void* const* y_dst, int n_dst, int64_t col0,
+                                int64_t M, const void* bias, void* stream_) {
+  int rc = validate(L, M);
+  if (rc != GLB_OK) return rc;
+  GLB_REQUIRE(x && y_dst && n_dst >= 1 && n_dst <= 8, GLB_ERR_INVALID, "glb_matmul_bcast: bad arguments");
+  for (int d = 0; d < n_dst; ++d) GLB_REQUIRE(y_dst[d] != nullptr, GLB_ERR_INVALID, "glb_matmul_bcast: destination %d is NULL", d);
+  GLB_REQUIRE(gemv_bcast_supported(*L, M), GLB_ERR_UNSUPPORTED,
+              "glb_matmul_bcast: only A16W4 decode layers at M == 1 store to several destinations (use glb_matmul + a collective)");
+  return launch_gemv_bcast(*L, x, reinterpret_cast<const float*>(scales_x), y_dst[0], y_dst, n_dst, (long long)col0, M, bias, nullptr, 0,
+                           (cudaStream_t)stream_);
+}
+
 extern "C" unsigned long long glb_stream_capture_id(void* stream_) {
   cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
   unsigned long long id = 0;
@@ -231,7 +245,7 @@ extern "C" size_t glb_workspace_bytes(const glb_linear* L, int64_t M, int matmul
   {
     glb_linear W;
     if (mx_expand_view(*L, &W) && (gemm_mx_tc2_supported(W, M) || gemv_mx_supported(W, M)))
-      return align256(gemm_tc_workspace(W, M)) + (size_t)M * (size_t)L->K * 2;
+      return expand_offset(gemm_tc_workspace(W, M)) + (size_t)M * (size_t)L->K * 2;
   }
   const bool was_auto = (matmul_type == GLB_MM_AUTO);
   if (was_auto) matmul_type = pick_matmul_type(*L, M);
@@ -256,14 +270,14 @@ extern "C" int glb_matmul(const glb_linear* L, const void* x, const void* scales
   {
     glb_linear W;
     if (mx_expand_view(*L, &W) && (gemm_mx_tc2_supported(W, M) || gemv_mx_supported(W, M))) {
-      const size_t inner = align256(gemm_tc_workspace(W, M)), need = inner + (size_t)M * (size_t)L->K * 2;
+      const size_t inner_ws = gemm_tc_workspace(W, M), inner = expand_offset(inner_ws), need = inner + (size_t)M * (size_t)L->K * 2;
       GLB_REQUIRE(workspace && workspace_bytes >= need, GLB_ERR_WORKSPACE, "MX dynamic layer: workspace too small: need %zu bytes, got %zu",
                   need, workspace_bytes);
       void* xb = reinterpret_cast<unsigned char*>(workspace) + inner;
       rc = launch_expand_act_mx(x, scales_x, xb, M, L->K, L->input_dtype, stream);
       if (rc != GLB_OK) return rc;
       if (gemv_mx_supported(W, M)) return launch_gemv_mx(W, xb, y, M, bias, stream);
-      return launch_gemm_tc(W, xb, nullptr, y, M, workspace, inner, bias, stream);
+      return launch_gemm_tc(W, xb, nullptr, y, M, workspace, inner_ws, bias, stream);
     }
   }
   const bool was_auto = (matmul_type == GLB_MM_AUTO);
@@ -283,6 +297,8 @@ extern "C" int glb_matmul(const glb_linear* L, const void* x, const void* scales
   // 0a. A8W8 at 16 < M <= 128: clustered streaming kernel (gl_gemm_a8_mid.cu); "GEMM" by name keeps the tcgen05 tile
   if ((was_auto || matmul_type != GLB_MM_GEMM) && gemm_a8_mid_supported(*L, M))
     return launch_gemm_a8_mid(*L, x, sx, y, M, bias, stream);
+  // 0c. A16W8 weight-only (fp16 x int8 / e4m3) at M <= 16: streaming kernel with in-register widening (gl_gemv_a8.cu)
+  if (matmul_type != GLB_MM_GEMM && gemv_a16w8_supported(*L, M)) return launch_gemv_a16w8(*L, x, y, M, bias, stream);
   // 0b. A8W8 at M <= 16: 16-feature-row streaming kernel (gl_gemv_a8.cu) (validated in round 2)
   if (matmul_type != GLB_MM_GEMM && gemv_a8_enabled() && gemv_a8_supported(*L, M))
     return launch_gemv_a8(*L, x, sx, y, M, bias, stream);

@@ -74,6 +74,9 @@ bool gemv_supported(const glb_linear& L, int64_t M);
 int launch_gemv(const glb_linear& L, const void* x, const float* scales_x, void* y, int64_t M,
                 const void* bias, void* workspace, size_t ws_bytes, cudaStream_t stream);
 size_t gemv_workspace(const glb_linear& L, int64_t M);
+bool gemv_bcast_supported(const glb_linear& L, int64_t M);
+int launch_gemv_bcast(const glb_linear& L, const void* x, const float* scales_x, void* y, void* const* y_dst, int n_dst,
+                      long long y_col0, int64_t M, const void* bias, void* workspace, size_t ws_bytes, cudaStream_t stream);
 int debug_read_timeline(unsigned long long* out, int max_words);
 bool gemm_tc_supported(const glb_linear& L, int64_t M);
 size_t gemm_tc_workspace(const glb_linear& L, int64_t M);
@@ -87,6 +90,8 @@ bool gemm_a8_tc2_supported(const glb_linear& L, int64_t M);
 int launch_gemm_a8_tc2(const glb_linear& L, const void* x, const float* scales_x, void* y, int64_t M, const void* bias,
                        cudaStream_t stream);
 bool gemv_a8_enabled();
+bool gemv_a16w8_supported(const glb_linear& L, int64_t M);
+int launch_gemv_a16w8(const glb_linear& L, const void* x, void* y, int64_t M, const void* bias, cudaStream_t stream);
 bool gemv_a8_supported(const glb_linear& L, int64_t M);
 int launch_gemv_a8(const glb_linear& L, const void* x, const float* scales_x, void* y, int64_t M, const void* bias,
                    cudaStream_t stream);

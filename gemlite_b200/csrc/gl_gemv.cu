@@ -50,6 +50,9 @@ constexpr int GV_R = 8;            // uint4 loads a lane keeps in flight per bat
 #endif
 
 struct GemvParams {
+  void* const* y_dst = nullptr;   // glb_matmul_bcast: destinations (device-accessible pointers), else null
+  int n_dst = 0;
+  long long y_col0 = 0;
   const uint32_t* W;     // (K/8, N) int32
   const void* scales;    // (G, N)
   const void* zeros;     // (G, N) or null
@@ -853,6 +856,11 @@ int launch_w4_tma(const glb_linear& L, const GemvParams& P0, int late_trigger, c
 // =================================================================================================
 struct GemvM1Params {
   const void* x; void* y; const void* bias;
+  // fused output all-gather (glb_matmul_bcast): the 32 outputs of a CTA are stored to EVERY destination (this GPU's
+  // buffer and the peers' symmetric buffers mapped over NVLink), at column y_col0 of each; n_dst == 0: plain store to y
+  void* y_dst[8];
+  int n_dst;
+  long long y_col0;
   int K, N, group_size, mode;
   int trigger;               // dependents are signalled 0: at kernel start, 2: right after the hand-off
   int debug;                 // bit 0: skip main loop, bit 1: skip weight copies, bit 2: timeline stamps (diagnostics)
@@ -1027,7 +1035,12 @@ gemv_w4_m1_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
 #pragma unroll
     for (int w = 0; w < M1_NW; ++w) v += red[w * GV_COLS + threadIdx.x];
     if (P.bias) v = rnd_out<BF16>(v) + cvt_meta<BF16>(reinterpret_cast<const uint16_t*>(P.bias)[col0 + threadIdx.x]);
-    st_out<BF16>(P.y, (int64_t)col0 + threadIdx.x, v);
+    if (P.n_dst == 0) {
+      st_out<BF16>(P.y, (int64_t)col0 + threadIdx.x, v);
+    } else {
+#pragma unroll 1
+      for (int d = 0; d < P.n_dst; ++d) st_out<BF16>(P.y_dst[d], (int64_t)P.y_col0 + col0 + threadIdx.x, v);
+    }
   }
   if (rec) {
     ts[6] = gtimer();
@@ -1072,6 +1085,8 @@ int launch_w4_m1(const glb_linear& L, const GemvParams& P0, cudaStream_t stream)
   if (rc != GLB_OK) return rc;
   GemvM1Params P;
   P.x = P0.x; P.y = P0.y; P.bias = P0.bias; P.K = P0.K; P.N = P0.N; P.group_size = P0.group_size; P.mode = P0.mode;
+  P.n_dst = P0.n_dst; P.y_col0 = P0.y_col0;
+  for (int d = 0; d < 8; ++d) P.y_dst[d] = (d < P0.n_dst) ? P0.y_dst[d] : nullptr;
   {
     static int dbg = -1, trig = -1;
     if (dbg < 0) { const char* e = getenv("GLB_GEMV_DEBUG"); dbg = e ? atoi(e) : 0; }
@@ -1223,13 +1238,29 @@ size_t gemv_workspace(const glb_linear& L, int64_t M) {
 
 int launch_gemv(const glb_linear& L, const void* x, const float* scales_x, void* y, int64_t M, const void* bias,
                 void* workspace, size_t ws_bytes, cudaStream_t stream) {
+  return launch_gemv_bcast(L, x, scales_x, y, nullptr, 0, 0, M, bias, workspace, ws_bytes, stream);
+}
+
+// fused output all-gather: only the M == 1 kernel stores to several destinations
+bool gemv_bcast_supported(const glb_linear& L, int64_t M) {
+  if (M != 1 || !gemv_supported(L, M) || gemv_variant() != 7) return false;
+  GemvParams P;
+  P.K = (int)L.K; P.N = (int)L.N; P.M = 1; P.group_size = L.group_size; P.mode = L.W_group_mode;
+  return gemv_m1_ok(P) && L.group_size >= 64 && (reinterpret_cast<uintptr_t>(L.scales) & 15) == 0 &&
+         (L.W_group_mode == 2 || (reinterpret_cast<uintptr_t>(L.zeros) & 15) == 0) && (L.N * 2) % 16 == 0;
+}
+
+int launch_gemv_bcast(const glb_linear& L, const void* x, const float* scales_x, void* y, void* const* y_dst, int n_dst,
+                      long long y_col0, int64_t M, const void* bias, void* workspace, size_t ws_bytes, cudaStream_t stream) {
   (void)scales_x;
+  if (n_dst > 0) GLB_REQUIRE(n_dst <= 8 && gemv_bcast_supported(L, M), GLB_ERR_UNSUPPORTED, "fused output gather: M == 1 A16W4 decode layers only");
   GLB_REQUIRE(gemv_supported(L, M), GLB_ERR_UNSUPPORTED, "decode kernel: unsupported layer configuration");
   GLB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, GLB_ERR_INVALID, "decode kernel: x must be 16-byte aligned");
   GemvParams P;
   P.W = reinterpret_cast<const uint32_t*>(L.W_q);
   P.scales = L.scales; P.zeros = (L.W_group_mode == 2) ? nullptr : L.zeros;
   P.x = x; P.y = y; P.bias = bias;
+  P.y_dst = y_dst; P.n_dst = n_dst; P.y_col0 = y_col0;
   P.K = (int)L.K; P.N = (int)L.N; P.M = (int)M;
   P.group_size = L.group_size; P.mode = L.W_group_mode;
   const bool bf = (L.input_dtype == GLB_BF16);

@@ -210,6 +210,166 @@ gemv_a8w8_kernel(const A8vParams P) {
   }
 }
 
+// =================================================================================================
+// A16W8 weight-only decode (fp16 activations x int8 / e4m3 weights, M <= 16): helper.A16W8_INT8 / A16W8_FP8
+// (gemlite/helper.py:88-170; the reference sends these to GEMV_SPLITK at M == 1, core.py:100-114).  Same streaming
+// skeleton as gemv_a8w8_kernel (16 feature rows per CTA over the full K, rows bulk-copied ahead of griddepcontrol.wait);
+// the weights are widened to fp16 in registers -- int8: byte ^ 0x80 -> prmt with 0x64 -> (1024 + u) -> hsub2 1152 = the
+// exact signed value (one LOP3 per 4, one PRMT + one HSUB2 per 2 weights); e4m3: cvt.rn.f16x2.e4m3x2, exact -- and fed
+// to mma.sync.m16n8k16 with fp32 accumulation.  The per-channel scale is applied to the accumulator (W_group_mode 2:
+// the reference rounds every q * s to fp16 first, so this path differs from the oracle by weight-rounding noise like the
+// 4-bit decode kernel; channel_scale_mode 1 is identical to the reference's post-scale).
+// =================================================================================================
+struct A16vParams {
+  const uint8_t* W;        // (N, K) bytes
+  const void* x;           // (M, K) fp16
+  const float* scales_w;   // (N)
+  void* y;
+  const void* bias;
+  int M, N, K;
+};
+
+__device__ __forceinline__ void mma_f16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// 4 weight bytes (k .. k+3 of one row) -> two fp16x2 registers (k, k+1) and (k+2, k+3)
+template <int WF> __device__ __forceinline__ void widen4(uint32_t w, uint32_t& lo, uint32_t& hi) {
+  if (WF == 0) {
+    const uint32_t u = w ^ 0x80808080u;                                   // signed -> offset-128
+    uint32_t m0, m1;
+    asm("prmt.b32 %0, %1, %2, 0x5140;" : "=r"(m0) : "r"(u), "r"(0x64646464u));     // (1024 + u0, 1024 + u1)
+    asm("prmt.b32 %0, %1, %2, 0x7362;" : "=r"(m1) : "r"(u), "r"(0x64646464u));     // (1024 + u2, 1024 + u3)
+    const __half2 k1152 = __half2half2(__ushort_as_half((unsigned short)0x6480));  // 1152
+    __half2 r0 = __hsub2(*reinterpret_cast<const __half2*>(&m0), k1152), r1 = __hsub2(*reinterpret_cast<const __half2*>(&m1), k1152);
+    lo = *reinterpret_cast<uint32_t*>(&r0); hi = *reinterpret_cast<uint32_t*>(&r1);
+  } else {
+    asm("{\n\t.reg .b16 t;\n\tcvt.u16.u32 t, %1;\n\tcvt.rn.f16x2.e4m3x2 %0, t;\n\t}" : "=r"(lo) : "r"(w & 0xffffu));
+    asm("{\n\t.reg .b16 t;\n\tcvt.u16.u32 t, %1;\n\tcvt.rn.f16x2.e4m3x2 %0, t;\n\t}" : "=r"(hi) : "r"(w >> 16));
+  }
+}
+
+template <int WF, int NT>
+__global__ void __launch_bounds__(A8V_WARPS * 32, 1)
+gemv_a16w8_kernel(const A16vParams P) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int K = P.K, pitch = K + A8V_PAD, xpitch = 2 * K + 16;          // (2K + 16) / 16 odd => conflict-free token rows
+  const int xrows = (P.M < 8 * NT) ? P.M : 8 * NT;
+  unsigned char* wbuf = smem;                                            // [16][pitch]
+  unsigned char* xbuf = wbuf + (size_t)A8V_ROWS * pitch;                 // [xrows][xpitch]
+  float* red = reinterpret_cast<float*>(xbuf + (((size_t)xrows * xpitch + 127) & ~(size_t)127));   // [8 warps][NT][16][8]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(red + A8V_WARPS * NT * 128);                       // [4] weights, [1] x
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int feat0 = blockIdx.x * A8V_ROWS;
+  const int kq = K / A8V_NCH;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int c = 0; c <= A8V_NCH; ++c) ptx::mbar_init(&bars[c], 1);
+      ptx::fence_mbar_init();
+      for (int c = 0; c < A8V_NCH; ++c) ptx::mbar_arrive_expect_tx(&bars[c], (uint32_t)(A8V_ROWS * kq));
+    }
+    __syncwarp();
+    if (lane < A8V_ROWS) {
+      const uint8_t* src = P.W + (size_t)(feat0 + lane) * K;
+#pragma unroll
+      for (int c = 0; c < A8V_NCH; ++c) bulk_copy_g2s(wbuf + (size_t)lane * pitch + c * kq, src + c * kq, (uint32_t)kq, &bars[c]);
+    }
+  }
+  __syncthreads();
+  pdl_wait_prior_grids();
+  pdl_launch_dependents();
+  if (threadIdx.x == 0) {
+    ptx::mbar_arrive_expect_tx(&bars[A8V_NCH], (uint32_t)xrows * (uint32_t)K * 2u);
+    for (int m = 0; m < xrows; ++m)
+      bulk_copy_g2s(xbuf + (size_t)m * xpitch, reinterpret_cast<const unsigned char*>(P.x) + (size_t)m * K * 2, (uint32_t)K * 2u, &bars[A8V_NCH]);
+  }
+
+  float acc[NT][4];
+#pragma unroll
+  for (int n = 0; n < NT; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+  const int kw = K / A8V_WARPS;                                         // k (= bytes) of every row this warp owns
+  const unsigned char* wa = wbuf + (size_t)g * pitch + (size_t)warp * kw + 16 * t;
+  const unsigned char* wb = wa + (size_t)8 * pitch;
+  const unsigned char* xa[NT];
+#pragma unroll
+  for (int n = 0; n < NT; ++n) {
+    const int tok = n * 8 + g;
+    xa[n] = xbuf + (size_t)(tok < xrows ? tok : 0) * xpitch + ((size_t)warp * kw + 16 * t) * 2;    // rows >= M: any valid row (discarded)
+  }
+  ptx::mbar_wait(&bars[warp >> 1], 0);
+  ptx::mbar_wait(&bars[A8V_NCH], 0);
+#pragma unroll 2
+  for (int o = 0; o < kw; o += 64) {
+    const uint4 p = *reinterpret_cast<const uint4*>(wa + o);             // 16 weights of row g:     k = o + 16 t .. + 15
+    const uint4 q = *reinterpret_cast<const uint4*>(wb + o);             // 16 weights of row g + 8
+    uint32_t pl[4], ph[4], ql[4], qh[4];
+    widen4<WF>(p.x, pl[0], ph[0]); widen4<WF>(p.y, pl[1], ph[1]); widen4<WF>(p.z, pl[2], ph[2]); widen4<WF>(p.w, pl[3], ph[3]);
+    widen4<WF>(q.x, ql[0], qh[0]); widen4<WF>(q.y, ql[1], qh[1]); widen4<WF>(q.z, ql[2], qh[2]); widen4<WF>(q.w, ql[3], qh[3]);
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      const uint4 x0 = *reinterpret_cast<const uint4*>(xa[n] + 2 * o);        // x of the same 16 k: (k, k+1) (k+2, k+3) ...
+      const uint4 x1 = *reinterpret_cast<const uint4*>(xa[n] + 2 * o + 16);
+      mma_f16(acc[n], pl[0], ql[0], ph[0], qh[0], x0.x, x0.y);
+      mma_f16(acc[n], pl[1], ql[1], ph[1], qh[1], x0.z, x0.w);
+      mma_f16(acc[n], pl[2], ql[2], ph[2], qh[2], x1.x, x1.y);
+      mma_f16(acc[n], pl[3], ql[3], ph[3], qh[3], x1.z, x1.w);
+    }
+  }
+
+#pragma unroll
+  for (int n = 0; n < NT; ++n) {
+    float* r = red + ((size_t)warp * NT + n) * 128;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r[(g + ((i & 2) ? 8 : 0)) * 8 + 2 * t + (i & 1)] = acc[n][i];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NT * 128; i += A8V_WARPS * 32) {
+    const int n = i >> 7, col = (i >> 4) & 7, row = i & 15;
+    const int m = n * 8 + col;
+    if (m >= P.M) continue;
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < A8V_WARPS; ++w) v += red[((size_t)w * NT + n) * 128 + row * 8 + col];
+    const int f = feat0 + row;
+    v = __fmul_rn(v, P.scales_w[f]);
+    if (P.bias) v = __half2float(__float2half_rn(v)) + __half2float(reinterpret_cast<const __half*>(P.bias)[f]);
+    reinterpret_cast<__half*>(P.y)[(int64_t)m * P.N + f] = __float2half_rn(v);
+  }
+}
+
+size_t a16v_smem_bytes(int K, int M, int nt) {
+  const int xrows = (M < 8 * nt) ? M : 8 * nt;
+  return (size_t)A8V_ROWS * (K + A8V_PAD) + ((((size_t)xrows * (2 * K + 16)) + 127) & ~(size_t)127) + (size_t)A8V_WARPS * nt * 128 * 4 +
+         (A8V_NCH + 1) * 8 + 16;
+}
+
+template <int WF, int NT>
+int launch_a16v(const A16vParams& P, cudaStream_t stream) {
+  const size_t smem = a16v_smem_bytes(P.K, P.M, NT);
+  auto kern = gemv_a16w8_kernel<WF, NT>;
+  if (smem > 48 * 1024) GLB_ENSURE_SMEM(kern, smem);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(P.N / A8V_ROWS));
+  cfg.blockDim = dim3(A8V_WARPS * 32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  int na = 0;
+  if (g_pdl_enabled.load()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  GLB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, P));
+  count_launch();
+  return GLB_OK;
+}
+
 size_t a8v_smem_bytes(int K, int nt) {
   return (size_t)(A8V_ROWS + 8 * nt) * (K + A8V_PAD) + (size_t)A8V_WARPS * nt * 128 * 4 + (A8V_NCH + 1) * 8 + 16;
 }
@@ -264,6 +424,35 @@ bool gemv_a8_supported(const glb_linear& L, int64_t M) {
   if (reinterpret_cast<uintptr_t>(L.W_q) & 15) return false;
   if (a8v_smem_bytes((int)L.K, M <= 8 ? 1 : 2) > 220 * 1024) return false;
   return true;
+}
+
+// A16W8 weight-only (fp16 activations; int8 or e4m3 weights; per-channel fp32 scales applied before (W_group_mode 2) or
+// after (channel_scale_mode 1) the product -- helper.py:156-163)
+bool gemv_a16w8_supported(const glb_linear& L, int64_t M) {
+  if (M < 1 || M > 16) return false;
+  if (L.input_dtype != GLB_FP16 || L.output_dtype != GLB_FP16) return false;
+  if (L.W_nbits != 8 || L.elements_per_sample != 1) return false;
+  if (!(L.wq_dtype == GLB_INT8 || L.wq_dtype == GLB_FP8E4)) return false;
+  if (L.wq_stride0 != 1 || L.wq_stride1 != L.K) return false;
+  if (!((L.W_group_mode == 2 && L.channel_scale_mode == 0) || (L.W_group_mode == 0 && L.channel_scale_mode == 1))) return false;
+  if (L.scales_dtype != GLB_FP32 || L.scales_numel != L.N || L.group_size != L.K) return false;
+  if (L.zeros_numel > 0 && L.W_group_mode != 0 && L.W_group_mode != 2) return false;
+  if (L.N % A8V_ROWS != 0 || L.K % (A8V_WARPS * 64) != 0) return false;
+  if (reinterpret_cast<uintptr_t>(L.W_q) & 15) return false;
+  if (a16v_smem_bytes((int)L.K, (int)M, M <= 8 ? 1 : 2) > 220 * 1024) return false;
+  return true;
+}
+
+int launch_gemv_a16w8(const glb_linear& L, const void* x, void* y, int64_t M, const void* bias, cudaStream_t stream) {
+  GLB_REQUIRE(gemv_a16w8_supported(L, M), GLB_ERR_UNSUPPORTED, "A16W8 decode kernel: unsupported layer configuration");
+  GLB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, GLB_ERR_INVALID, "A16W8 decode kernel: x must be 16-byte aligned");
+  A16vParams P;
+  P.W = reinterpret_cast<const uint8_t*>(L.W_q); P.x = x; P.scales_w = reinterpret_cast<const float*>(L.scales);
+  P.y = y; P.bias = bias; P.M = (int)M; P.N = (int)L.N; P.K = (int)L.K;
+  const bool f8 = (L.wq_dtype == GLB_FP8E4);
+  set_kernel_name(f8 ? "gemv_a16w8_fp8" : "gemv_a16w8_int8");
+  if (f8) return (M <= 8) ? launch_a16v<1, 1>(P, stream) : launch_a16v<1, 2>(P, stream);
+  return (M <= 8) ? launch_a16v<0, 1>(P, stream) : launch_a16v<0, 2>(P, stream);
 }
 
 int launch_gemv_a8(const glb_linear& L, const void* x, const float* scales_x, void* y, int64_t M, const void* bias,

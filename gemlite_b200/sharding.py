@@ -84,6 +84,41 @@ def gather_columns(y_local: Tensor, group=None) -> Tensor:
     return out.movedim(0, -2).reshape(*y_local.shape[:-1], world * y_local.shape[-1])
 
 
+class SymmetricOutputs:
+    """Gathered outputs in NVLink-mapped symmetric memory: `rows` output rows of `n_global` columns, the same buffer on
+    every rank (torch.distributed._symmetric_memory: cudaMalloc'd, exchanged over IPC, peer pointers valid in kernels).
+    `ColumnShardedLinear.forward_scatter` makes the decode kernel store its columns into every rank's copy (the
+    transfer is the kernel's own epilogue, 64 bytes per CTA and peer); `barrier()` is the only synchronisation of a step.
+    B200-native replacement of the NCCL all-gather for M == 1; NCCL stays the fallback and the reported
+    baseline."""
+
+    def __init__(self, rows: int, n_global: int, dtype, device, group=None):
+        import ctypes
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        group = group if group is not None else dist.group.WORLD
+        self.rows, self.n_global, self.dtype = rows, n_global, dtype
+        self.buf = symm_mem.empty(rows, n_global, dtype=dtype, device=device)
+        self.handle = symm_mem.rendezvous(self.buf, group)
+        self.world, self.rank = self.handle.world_size, self.handle.rank
+        self._ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        self._ctypes = ctypes
+        self._row_arrays = {}
+
+    def row_ptrs(self, row: int):
+        """ctypes array of the address of `row` in every rank's buffer (own rank first: it is also the plain output)."""
+        a = self._row_arrays.get(row)
+        if a is None:
+            off = row * self.n_global * self.buf.element_size()
+            order = [self.rank] + [r for r in range(self.world) if r != self.rank]
+            a = (self._ctypes.c_void_p * self.world)(*[self._ptrs[r] + off for r in order])
+            self._row_arrays[row] = a
+        return a
+
+    def barrier(self):
+        self.handle.barrier(channel=0)
+
+
 class ColumnShardedLinear(torch.nn.Module):
     """One rank's shard of a packed `GemLiteLinear` + the all-gather of the outputs.
 
@@ -116,3 +151,12 @@ class ColumnShardedLinear(torch.nn.Module):
 
     def forward(self, x: Tensor) -> Tensor:
         return gather_columns(self.local(x), self.group)
+
+    def forward_scatter(self, x: Tensor, out: "SymmetricOutputs", row: int = 0) -> None:
+        """Decode call whose shard of the output is stored straight into row `row` of every rank's `out` buffer (fused
+        output all-gather).  The caller brackets a step with `out.barrier()`.  NotImplementedError when the shard has no
+        multi-destination kernel (anything but A16W4 at M == 1): use forward()."""
+        from .core import matmul_bcast
+        x2d = x.view(-1, x.shape[-1])
+        matmul_bcast(x2d, self.local.bias, self.local.get_tensor_args(), self.local.get_meta_args(), out.row_ptrs(row),
+                     self.rank * (self.out_features // self.world))

@@ -167,6 +167,14 @@ GLB_API int glb_matmul(const glb_linear* layer, const void* x, const void* scale
 
 /* Global knobs (host side, cheap): enable programmatic dependent launch on the decode kernels so that
  * a layer's weight prefetch overlaps the tail of the previous layer's kernel. Default: on. */
+/* Fused output all-gather for column-sharded decode (no reference equivalent -- the reference is single-GPU).
+ * Like glb_matmul at M == 1, but the result row is stored at column `col0` of EVERY destination in `y_dst`
+ * (device-accessible pointers to row 0 / column 0 of each rank's gathered output: this GPU's buffer and the peers'
+ * symmetric buffers mapped over NVLink).  The caller synchronises the ranks (one barrier per step).  Returns
+ * GLB_ERR_UNSUPPORTED for anything but an A16W4 decode layer at M == 1: use glb_matmul + a collective there. */
+GLB_API int glb_matmul_bcast(const glb_linear* layer, const void* x, const void* scales_x, void* const* y_dst, int n_dst,
+                             int64_t col0, int64_t M, const void* bias, void* stream);
+
 GLB_API void glb_set_pdl(int enabled);
 GLB_API int glb_get_pdl(void);
 

@@ -806,3 +806,25 @@ def test_a8w8_batched_decode_kernel(kind, shape):
                     ref = ref + b.to(DEV).double()
                 assert relerr(y, ref) <= 2e-3, (shape, M, relerr(y, ref))
             assert torch.equal(layer(x), y)
+
+
+@pytest.mark.parametrize("kind", ["int8", "fp8"])
+@pytest.mark.parametrize("post_scale", [False, True])
+def test_a16w8_weight_only_decode_kernel(kind, post_scale):
+    """helper.A16W8_INT8 / A16W8_FP8 at M <= 16 on the streaming kernel of gl_gemv_a8.cu (fp16 activations, weights
+    widened to fp16 in registers, per-channel scale on the fp32 accumulator) against the oracle; larger batches stay on
+    the general kernel.  Pre-scale mode differs from the oracle by the fp16 rounding of every q * s (decode tolerance)."""
+    N, K = 512, 2048
+    W = (torch.randn(N, K, generator=torch.Generator().manual_seed(77)) / 10).half()
+    bias = (torch.randn(N, generator=torch.Generator().manual_seed(3)) / 10).half()
+    cls = A16W8_INT8 if kind == "int8" else A16W8_FP8
+    for b in (None, bias):
+        layer = cls(device=DEV, dtype=torch.float16, post_scale=post_scale).from_weights(W.clone().to(DEV), bias=None if b is None else b.to(DEV))
+        p = oracle_from_layer(layer)
+        for M in (1, 3, 8, 16, 40):
+            x = xgen(M, K, torch.float16, 60 + M)
+            y = layer(x.to(DEV))
+            want = f"gemv_a16w8_{kind}" if M <= 16 else "generic_cuda_core"
+            assert _cabi.last_kernel() == want, (M, _cabi.last_kernel())
+            e = relerr(y, O.forward(p, x))
+            assert e <= REL_DECODE[torch.float16], (kind, post_scale, b is not None, M, e)
