@@ -64,10 +64,12 @@ class ClockSampler:
     query takes well under a millisecond; polled every 4 ms so that the launching thread is not disturbed); nvidia-smi
     -lms is the fallback when the NVML binding is missing."""
 
-    def __init__(self, index=0):
+    def __init__(self, index=0, threaded=True):
         self.rows, self.proc, self.index = [], None, index
         self.nvml, self.handle, self.stop = None, None, False
         self.max_mhz = None
+        self.threaded = threaded      # False: no polling thread; the caller samples explicitly (sample()) while the GPU
+                                      # executes already-enqueued work, so NVML never contends with a launch
 
     def __enter__(self):
         try:
@@ -87,8 +89,9 @@ class ClockSampler:
             pynvml.nvmlDeviceGetClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
             (getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons)(self.handle)
             self.nvml = pynvml
-            self.thr = threading.Thread(target=self._poll, daemon=True)
-            self.thr.start()
+            if self.threaded:
+                self.thr = threading.Thread(target=self._poll, daemon=True)
+                self.thr.start()
             return self
         except Exception:
             self.nvml = None
@@ -123,13 +126,28 @@ class ClockSampler:
                 break
             time.sleep(0.004)      # a few hundred Hz would contend with the launching thread for driver locks
 
+    def sample(self):
+        """One NVML sample from the calling thread (threaded=False mode)."""
+        n = self.nvml
+        if n is None:
+            return
+        try:
+            get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+            R = (getattr(n, "nvmlClocksEventReasonHwSlowdown", 0x8), getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20), getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4))
+            mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+            mask = int(get_reasons(self.handle))
+            self.rows.append([str(mhz), str(self.max_mhz), ""] + ["Active" if (mask & r) else "Not Active" for r in R])
+        except Exception:
+            pass
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def __exit__(self, *a):
         self.stop = True
-        if self.nvml is not None:
+        if self.nvml is not None and self.threaded:
             try:
                 self.thr.join(timeout=1)
             except Exception:
@@ -580,14 +598,19 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    with ClockSampler(local_rank) as clocks:
+    with ClockSampler(local_rank, threaded=False) as clocks:
         ev0.record()
         marks[0].record()
         for i in range(args.steps):
             one_step()
             marks[i + 1].record()
         ev1.record()
+        # the K steps are enqueued (graph launches are asynchronous) and executing: sample the clocks now, from this
+        # thread, instead of from a polling thread that can hold driver locks a launch needs
+        for _ in range(3):
+            clocks.sample()
         torch.cuda.synchronize()
+        clocks.sample()
     per_step = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps))
     if world > 1:
         dist.barrier()
