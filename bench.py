@@ -555,7 +555,16 @@ def run_ours(args, rank, world, local_rank):
     if world > 1 and os.environ.get("BENCH_NO_FUSED_GATHER", "0") != "1":
         try:
             from gemlite_b200.sharding import SymmetricOutputs
-            sym = SymmetricOutputs(LAYERS, N * world, torch.float16, dev)
+            sym, sym_err = None, None
+            try:
+                sym = SymmetricOutputs(LAYERS, N * world, torch.float16, dev)
+            except Exception as e:
+                sym_err = e
+            # all ranks take the fused path or none does: a rank that failed alone would leave the others in a barrier
+            ok = torch.tensor([0 if sym is None else 1], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if ok.item() == 0:
+                raise sym_err if sym_err is not None else RuntimeError("symmetric buffers unavailable on another rank")
 
             def fused_body():
                 sym.barrier()                       # every rank has finished reading the previous step's rows

@@ -84,6 +84,7 @@ int launch_gemm_tc(const glb_linear& L, const void* x, const float* scales_x, vo
                    void* workspace, size_t ws_bytes, const void* bias, cudaStream_t stream);
 bool gemm_tc2_supported(const glb_linear& L, int64_t M);
 bool gemm_mx_tc2_supported(const glb_linear& L, int64_t M);
+bool gemm_w8_tc2_supported(const glb_linear& L, int64_t M);
 bool gemv_mx_supported(const glb_linear& L, int64_t M);
 int launch_gemv_mx(const glb_linear& L, const void* x, void* y, int64_t M, const void* bias, cudaStream_t stream);
 bool gemm_a8_tc2_supported(const glb_linear& L, int64_t M);

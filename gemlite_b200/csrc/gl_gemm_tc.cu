@@ -679,10 +679,14 @@ bool a8w8_tc_supported(const glb_linear& L, int64_t M) {
 bool gemm_tc_supported(const glb_linear& L, int64_t M) {
   if (a8w8_tc_supported(L, M)) return true;
   if (gemm_mx_tc2_supported(L, M)) return true;
+  if (gemm_w8_tc2_supported(L, M)) return true;
   if (M < 1 || M > (1 << 24)) return false;
   if (!(L.input_dtype == GLB_FP16 || L.input_dtype == GLB_BF16)) return false;
   if (L.output_dtype != L.input_dtype || L.meta_dtype != L.input_dtype) return false;
-  if (L.W_nbits != 4 || L.elements_per_sample != 8 || L.wq_dtype != GLB_INT32) return false;
+  // packed int32 words: 4-bit on both tcgen05 kernels; 8 / 2 / 1-bit (HQQ layers, packing_bitwidth 32) on the pair kernel only
+  if (!(L.W_nbits == 4 || L.W_nbits == 8 || L.W_nbits == 2 || L.W_nbits == 1)) return false;
+  if (L.elements_per_sample != 32 / L.W_nbits || L.wq_dtype != GLB_INT32) return false;
+  if (L.W_nbits != 4 && !gemm_tc2_supported(L, M)) return false;
   if (L.wq_stride1 != 1 || L.wq_stride0 != L.N) return false;
   if (L.channel_scale_mode != 0) return false;
   if (!(L.W_group_mode == 2 || L.W_group_mode == 3 || L.W_group_mode == 4)) return false;
@@ -698,10 +702,11 @@ bool gemm_tc_supported(const glb_linear& L, int64_t M) {
 // which A16W4 / MXFP4 launches go to the CTA-pair kernel (gl_gemm_tc2.cu): MXFP4 always; INT4 above the decode range
 // (GLB_PREFILL_VARIANT=1 keeps the single-CTA kernel for A/B comparisons)
 static bool use_pair_kernel(const glb_linear& L, int64_t M) {
-  if (gemm_mx_tc2_supported(L, M)) return true;
+  if (gemm_mx_tc2_supported(L, M) || gemm_w8_tc2_supported(L, M)) return true;
   static int variant = -1;
   if (variant < 0) { const char* e = getenv("GLB_PREFILL_VARIANT"); variant = e ? atoi(e) : 2; }
   if (a8w8_tc_supported(L, M)) return false;
+  if (L.W_nbits != 4) return true;                        // the single-CTA kernel unpacks 4-bit words only
   return variant != 1 && M > 16 && gemm_tc2_supported(L, M);
 }
 

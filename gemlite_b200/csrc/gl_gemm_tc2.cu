@@ -67,6 +67,7 @@ struct Tc2Params {
   int M, N, K;
   int group_size;
   int mode;
+  int post_scale;         // 8-bit weight-only: multiply the accumulator by the per-feature fp32 scale (channel_scale_mode 1)
   int tiles_m;            // 256-token blocks
   int tiles_n;            // 256-feature blocks
   int prefetch;           // x stages of L2 prefetch distance (0 = off)
@@ -113,6 +114,47 @@ template <bool BF16> __device__ __forceinline__ void unpack8_nat(uint32_t q, uin
   o[1] = __byte_perm(h[2], h[3], 0x5410);   // (k2,k3)
   o[2] = __byte_perm(h[0], h[1], 0x7632);   // (k4,k5)
   o[3] = __byte_perm(h[2], h[3], 0x7632);   // (k6,k7)
+}
+
+// Packed int32 words of other widths (A16W8 / A16W2 / A16W1 HQQ layers, packing_bitwidth 32; bitpack.py): element j of a
+// word sits at bits [NBITS j, NBITS (j+1)).  One word -> 16 / NBITS pairs of exact integers in natural k order.
+template <bool BF16, int NBITS> __device__ __forceinline__ void unpack_word_nat(uint32_t q, uint32_t (&o)[16 / NBITS]) {
+  if (NBITS == 8) {
+    uint32_t m0, m1;
+    asm("prmt.b32 %0, %1, %2, 0x5140;" : "=r"(m0) : "r"(q), "r"(0x64646464u));     // (1024 + u0, 1024 + u1)
+    asm("prmt.b32 %0, %1, %2, 0x7362;" : "=r"(m1) : "r"(q), "r"(0x64646464u));     // (1024 + u2, 1024 + u3)
+    const __half2 k1024 = __half2half2(__ushort_as_half((unsigned short)0x6400));
+    __half2 r0 = __hsub2(*reinterpret_cast<const __half2*>(&m0), k1024), r1 = __hsub2(*reinterpret_cast<const __half2*>(&m1), k1024);
+    if (BF16) {                                              // 0..255 needs 8 significand bits: exact in bf16
+      const float2 a = __half22float2(r0), b = __half22float2(r1);
+      __nv_bfloat162 c0 = __floats2bfloat162_rn(a.x, a.y), c1 = __floats2bfloat162_rn(b.x, b.y);
+      o[0] = *reinterpret_cast<uint32_t*>(&c0); o[1] = *reinterpret_cast<uint32_t*>(&c1);
+    } else {
+      o[0] = *reinterpret_cast<uint32_t*>(&r0); o[1] = *reinterpret_cast<uint32_t*>(&r1);
+    }
+  } else {
+    constexpr int H = 16 / NBITS;                            // elements per 16-bit half of the word
+    constexpr uint32_t MASK = ((1u << NBITS) - 1u) * 0x00010001u;
+    uint32_t h[H];
+#pragma unroll
+    for (int i = 0; i < H; ++i) {                            // h[i] = (k_i, k_{i+H})
+      uint32_t v;
+      if (!BF16) {
+        asm("lop3.b32 %0, %1, %2, 0x64006400, 0xEA;" : "=r"(v) : "r"(q >> (NBITS * i)), "r"(MASK));
+        __half2 r = __hsub2(*reinterpret_cast<__half2*>(&v), __half2half2(__ushort_as_half((unsigned short)0x6400)));
+        h[i] = *reinterpret_cast<uint32_t*>(&r);
+      } else {
+        asm("lop3.b32 %0, %1, %2, 0x43004300, 0xEA;" : "=r"(v) : "r"(q >> (NBITS * i)), "r"(MASK));
+        __nv_bfloat162 r = __hsub2(*reinterpret_cast<__nv_bfloat162*>(&v), __bfloat162bfloat162(__ushort_as_bfloat16((unsigned short)0x4300)));
+        h[i] = *reinterpret_cast<uint32_t*>(&r);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < H / 2; ++j) {
+      o[j] = __byte_perm(h[2 * j], h[2 * j + 1], 0x5410);            // (k_{2j}, k_{2j+1})
+      o[H / 2 + j] = __byte_perm(h[2 * j], h[2 * j + 1], 0x7632);    // (k_{H+2j}, k_{H+2j+1})
+    }
+  }
 }
 
 template <bool BF16> __device__ __forceinline__ uint32_t dequant2_ref(uint32_t q2, uint32_t s2, uint32_t z2, int mode) {
@@ -163,9 +205,44 @@ template <bool BF16> __device__ __forceinline__ uint32_t mx_scale_pair(uint32_t 
   }
 }
 
-constexpr int WFMT_INT4 = 0, WFMT_MXFP4 = 1;
+constexpr int WFMT_INT4 = 0, WFMT_MXFP4 = 1, WFMT_W8I = 2, WFMT_W8F = 3;
+// 8-bit weight-only layers (A16W8 int8 / e4m3, helper.py:88-170): storage (N, K) bytes K-contiguous, one fp32 scale per
+// feature.  A stage is 128 rows x 128 bytes (16 KB, TMA 128B swizzle: a thread's two 16-byte chunks land on distinct
+// banks across 8 consecutive rows), 4-deep ring.  Pre-scaling (W_group_mode 2): w = round16(float(q) * s), the
+// reference's rounding point (b.to(fp32) * scales -> compute dtype); post-scaling (channel_scale_mode 1): the exact
+// integer / e4m3 value goes to the tensor core and the accumulator is multiplied by s in the epilogue.
+constexpr int T2_P8_BYTES = T2_BK * T2_BM;                 // 16 KB
+constexpr int T2_P8_STAGES = 4;
+static_assert(T2_P8_STAGES * T2_P8_BYTES == T2_PSTAGES * T2_P_BYTES, "both packed rings fill the same 64 KB");
 
-template <bool BF16, int WFMT>
+// 4 weight bytes (k .. k+3) -> two 16-bit-float pairs (k, k+1), (k+2, k+3): exact values, optionally pre-scaled in fp32
+template <bool BF16, int WFMT> __device__ __forceinline__ void widen4_w8(uint32_t w, float sc, bool prescale, uint32_t& lo, uint32_t& hi) {
+  uint32_t l16, h16;                                         // fp16 pairs holding the exact weight values
+  if (WFMT == WFMT_W8I) {
+    const uint32_t u = w ^ 0x80808080u;                      // signed -> offset-128
+    uint32_t m0, m1;
+    asm("prmt.b32 %0, %1, %2, 0x5140;" : "=r"(m0) : "r"(u), "r"(0x64646464u));     // (1024 + u0, 1024 + u1)
+    asm("prmt.b32 %0, %1, %2, 0x7362;" : "=r"(m1) : "r"(u), "r"(0x64646464u));     // (1024 + u2, 1024 + u3)
+    const __half2 k1152 = __half2half2(__ushort_as_half((unsigned short)0x6480));
+    __half2 r0 = __hsub2(*reinterpret_cast<const __half2*>(&m0), k1152), r1 = __hsub2(*reinterpret_cast<const __half2*>(&m1), k1152);
+    l16 = *reinterpret_cast<uint32_t*>(&r0); h16 = *reinterpret_cast<uint32_t*>(&r1);
+  } else {
+    asm("{\n\t.reg .b16 t;\n\tcvt.u16.u32 t, %1;\n\tcvt.rn.f16x2.e4m3x2 %0, t;\n\t}" : "=r"(l16) : "r"(w & 0xffffu));
+    asm("{\n\t.reg .b16 t;\n\tcvt.u16.u32 t, %1;\n\tcvt.rn.f16x2.e4m3x2 %0, t;\n\t}" : "=r"(h16) : "r"(w >> 16));
+  }
+  if (!BF16 && !prescale) { lo = l16; hi = h16; return; }
+  float2 a = __half22float2(*reinterpret_cast<__half2*>(&l16)), b = __half22float2(*reinterpret_cast<__half2*>(&h16));
+  if (prescale) { a.x *= sc; a.y *= sc; b.x *= sc; b.y *= sc; }
+  if (BF16) {
+    __nv_bfloat162 r0 = __floats2bfloat162_rn(a.x, a.y), r1 = __floats2bfloat162_rn(b.x, b.y);
+    lo = *reinterpret_cast<uint32_t*>(&r0); hi = *reinterpret_cast<uint32_t*>(&r1);
+  } else {
+    __half2 r0 = __floats2half2_rn(a.x, a.y), r1 = __floats2half2_rn(b.x, b.y);
+    lo = *reinterpret_cast<uint32_t*>(&r0); hi = *reinterpret_cast<uint32_t*>(&r1);
+  }
+}
+
+template <bool BF16, int WFMT, int NBITS>
 __global__ void __launch_bounds__(T2_THREADS, 1)
 gemm_a16w4_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const Tc2Params P) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -185,6 +262,12 @@ gemm_a16w4_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
   const bool leader = (rank == 0);
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   const int kblocks = P.kb_per_split;                 // stages per work item
+  constexpr bool W8 = (WFMT == WFMT_W8I || WFMT == WFMT_W8F);
+  // packed ring depth / stage bytes of this weight format: packed int32 words hold 32 / NBITS elements -> 4 NBITS word
+  // rows of 128 features per 128-k stage (NBITS = 4: the 8 KB of T2_P_BYTES)
+  constexpr int PBYTES = W8 ? T2_P8_BYTES : ((WFMT == WFMT_INT4) ? 4 * NBITS * T2_BM * 4 : T2_P_BYTES);
+  constexpr int PSTAGES = (PBYTES > T2_P_BYTES) ? T2_P8_STAGES : T2_PSTAGES;
+  static_assert(PSTAGES * PBYTES <= T2_PSTAGES * T2_P_BYTES, "packed ring overflows its 64 KB");
   const int ntiles = P.tiles_m * P.tiles_n * P.splits;   // work items; item w = (tile w / splits, split w % splits)
 
   if (warp == T2_XPROD_WARP && lane == 0) {
@@ -194,7 +277,7 @@ gemm_a16w4_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       ptx::mbar_init(&ready[s], 1 + 2 * T2_DEQ_WARPS);   // the leader producer's expect_tx arrival + 32 dequant warps
       ptx::mbar_init(&empty[s], 1);
     }
-    for (int s = 0; s < T2_PSTAGES; ++s) {
+    for (int s = 0; s < PSTAGES; ++s) {
       ptx::mbar_init(&pfull[s], 1);
       ptx::mbar_init(&pfree[s], T2_DEQ_WARPS);
     }
@@ -245,10 +328,11 @@ gemm_a16w4_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         const int kb0 = (t % P.splits) * kblocks;
         for (int kb = kb0; kb < kb0 + kblocks; ++kb) {
           ptx::mbar_wait(&pfree[s], ph ^ 1u);
-          ptx::mbar_arrive_expect_tx(&pfull[s], T2_P_BYTES);
-          if (WFMT == WFMT_INT4) ptx::tma_load_2d(smem + T2_P_OFF + s * T2_P_BYTES, &tmap_w, &pfull[s], feat0, kb * (T2_BK / 8));
-          else ptx::tma_load_2d(smem + T2_P_OFF + s * T2_P_BYTES, &tmap_w, &pfull[s], kb * (T2_BK / 2), feat0);   // [64 B of codes][128 rows]
-          if (++s == T2_PSTAGES) { s = 0; ph ^= 1u; }
+          ptx::mbar_arrive_expect_tx(&pfull[s], PBYTES);
+          if (WFMT == WFMT_INT4) ptx::tma_load_2d(smem + T2_P_OFF + s * PBYTES, &tmap_w, &pfull[s], feat0, kb * (4 * NBITS));
+          else if (W8) ptx::tma_load_2d(smem + T2_P_OFF + s * PBYTES, &tmap_w, &pfull[s], kb * T2_BK, feat0);   // [128 B][128 rows], swizzled
+          else ptx::tma_load_2d(smem + T2_P_OFF + s * PBYTES, &tmap_w, &pfull[s], kb * (T2_BK / 2), feat0);   // [64 B of codes][128 rows]
+          if (++s == PSTAGES) { s = 0; ph ^= 1u; }
         }
       }
     }
@@ -292,7 +376,7 @@ gemm_a16w4_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     const int kq = d >> 2;                                  // which 32-k quarter of the 128-k stage
     const uint32_t taddr0 = tmem_base + ((uint32_t)(q4 * 32) << 16) + T2_ACOL0 + (uint32_t)kq * 16u;
     const uint32_t ready_leader = ptx::mapa(ptx::smem_u32(&ready[0]), 0u);
-    const uint32_t* pk0 = reinterpret_cast<const uint32_t*>(smem + T2_P_OFF) + (kq * 4) * T2_BM + row;
+    const uint32_t* pk0 = reinterpret_cast<const uint32_t*>(smem + T2_P_OFF) + (kq * NBITS) * T2_BM + row;   // this thread's NBITS words of the stage
     auto dup = [](uint16_t v) { return (uint32_t)v | ((uint32_t)v << 16); };
     uint32_t s = 0, ph = 0;                                 // x / A ring position
     uint32_t ps = 0, pph = 0;                               // packed ring position
@@ -313,7 +397,10 @@ gemm_a16w4_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       // ---------------- MXFP4 metadata state: one e8m0 byte per stage, row stride N, requested one stage ahead ----------------
       const uint8_t* mxp = nullptr;
       uint8_t mxraw = 0;
-      if (WFMT == WFMT_INT4) {
+      float w8_scale = 1.f;                                 // 8-bit weight-only: the feature's fp32 scale (pre-scaling only)
+      if (W8) {
+        if (P.mode == 2) w8_scale = reinterpret_cast<const float*>(P.scales)[n];
+      } else if (WFMT == WFMT_INT4) {
         g = (kstage0 * T2_BK + kq * 32) / P.group_size; rem = (kstage0 * T2_BK + kq * 32) % P.group_size;
         sp = reinterpret_cast<const uint16_t*>(P.scales) + (size_t)g * P.N + n;
         zp = (P.mode != 2) ? reinterpret_cast<const uint16_t*>(P.zeros) + (size_t)g * P.N + n : sp;
@@ -325,7 +412,8 @@ gemm_a16w4_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       for (int kb = 0; kb < kblocks; ++kb) {
         float mx_sf = 0.f;
         uint32_t mx_s16 = 0u;
-        if (WFMT == WFMT_INT4) {
+        if (W8) {
+        } else if (WFMT == WFMT_INT4) {
           if (fresh) { s2 = dup(sraw); z2 = dup(zraw); fresh = false; }
           // where the next stage lands; if it is another group, request its metadata now and expand it next iteration
           rem += T2_BK;
@@ -346,17 +434,28 @@ gemm_a16w4_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         }
         // 1. packed words (landed long ago in steady state) -> dequantised pairs in registers; release the ring slot
         ptx::mbar_wait(&pfull[ps], pph);
-        if (WFMT == WFMT_INT4) {
-          const uint32_t* pk = pk0 + ps * (uint32_t)(T2_P_BYTES / 4);
-          uint32_t w[4];
+        if (W8) {
+          // row r of the tile is 128 bytes (k .. k+127) in 16-byte chunks, chunk c stored at c ^ (r & 7); this thread's
+          // 32 k are chunks 2 kq and 2 kq + 1
+          const unsigned char* rb = smem + T2_P_OFF + ps * PBYTES + row * 128;
+          const uint4 w0 = *reinterpret_cast<const uint4*>(rb + (((2 * kq) ^ (row & 7)) << 4));
+          const uint4 w1 = *reinterpret_cast<const uint4*>(rb + (((2 * kq + 1) ^ (row & 7)) << 4));
+          const uint32_t w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-          for (int cc = 0; cc < 4; ++cc) w[cc] = pk[cc * T2_BM];
+          for (int cc = 0; cc < 8; ++cc) widen4_w8<BF16, WFMT>(w[cc], w8_scale, P.mode == 2, o[2 * cc], o[2 * cc + 1]);
+        } else if (WFMT == WFMT_INT4) {
+          const uint32_t* pk = pk0 + ps * (uint32_t)(PBYTES / 4);
+          constexpr int PPW = 16 / NBITS;                       // pairs per word
+          uint32_t w[NBITS];
 #pragma unroll
-          for (int cc = 0; cc < 4; ++cc) {
-            uint32_t q[4];
-            unpack8_nat<BF16>(w[cc], q);
+          for (int cc = 0; cc < NBITS; ++cc) w[cc] = pk[cc * T2_BM];
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) o[cc * 4 + jj] = dequant2_ref<BF16>(q[jj], s2, z2, P.mode);
+          for (int cc = 0; cc < NBITS; ++cc) {
+            uint32_t q[PPW];
+            if (NBITS == 4) unpack8_nat<BF16>(w[cc], reinterpret_cast<uint32_t (&)[4]>(q));
+            else unpack_word_nat<BF16, NBITS>(w[cc], q);
+#pragma unroll
+            for (int jj = 0; jj < PPW; ++jj) o[cc * PPW + jj] = dequant2_ref<BF16>(q[jj], s2, z2, P.mode);
           }
         } else {
           // row r of the tile is 64 bytes (128 codes); this thread's 32 codes are bytes kq*16 .. kq*16+15
@@ -371,7 +470,7 @@ gemm_a16w4_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         }
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&pfree[ps]);          // every lane's LDS results have been consumed above
-        if (++ps == T2_PSTAGES) { ps = 0; pph ^= 1u; }
+        if (++ps == PSTAGES) { ps = 0; pph ^= 1u; }
         // 2. A slot s is free once the MMAs of its previous use completed; store, publish
         ptx::mbar_wait(&empty[s], ph ^ 1u);
         ptx::tc_fence_after_sync();
@@ -397,6 +496,7 @@ gemm_a16w4_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       tile_coords(tile, P.tiles_m, P.tiles_n, tm, tn);
       const int n = tn * 2 * T2_BM + (int)rank * T2_BM + row;
       float bv = 0.f;
+      const float es = (W8 && P.post_scale) ? reinterpret_cast<const float*>(P.scales)[n] : 1.f;   // channel_scale_mode 1
       if (P.bias) bv = BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(P.bias)[n])
                             : __half2float(reinterpret_cast<const __half*>(P.bias)[n]);
       ptx::mbar_wait_sleep(tfull, (uint32_t)(it & 1));     // a whole main loop away: do not burn issue slots spinning
@@ -405,6 +505,7 @@ gemm_a16w4_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       unsigned char* ybase = reinterpret_cast<unsigned char*>(P.y) + ((int64_t)(tm * T2_BT) * P.N + n) * 2;
       const int64_t ystride = (int64_t)P.N * 2;
       auto store_out = [&](int c, float v) {                              // one output element (token c of the tile, this row)
+        if (W8) v *= es;
         if (BF16) {
           if (P.bias) v = __bfloat162float(__float2bfloat16_rn(v)) + bv;
           *reinterpret_cast<__nv_bfloat16*>(ybase + c * ystride) = __float2bfloat16_rn(v);
@@ -515,14 +616,16 @@ Tc2Plan make_plan(const glb_linear& L, int64_t M) {
   return p;
 }
 
-template <bool BF16, int WFMT>
+template <bool BF16, int WFMT, int NBITS = 4>
 int launch_tc2(const glb_linear& L, const void* x, void* y, int64_t M, void* workspace, size_t ws_bytes, const void* bias,
                cudaStream_t stream) {
   CUtensorMap tx, tw;
   int rc = make_tmap_2d(&tx, BF16 ? GLB_BF16 : GLB_FP16, x, (uint64_t)L.K, (uint64_t)M, (uint64_t)L.K * 2, 64, T2_BT / 2, 1);
   if (rc != GLB_OK) return rc;
   if (WFMT == WFMT_INT4)
-    rc = make_tmap_2d(&tw, GLB_INT32, L.W_q, (uint64_t)L.N, (uint64_t)(L.K / 8), (uint64_t)L.N * 4, T2_BM, T2_BK / 8, 0);
+    rc = make_tmap_2d(&tw, GLB_INT32, L.W_q, (uint64_t)L.N, (uint64_t)(L.K * NBITS / 32), (uint64_t)L.N * 4, T2_BM, 4 * NBITS, 0);
+  else if (WFMT == WFMT_W8I || WFMT == WFMT_W8F)   // (N, K) bytes, K contiguous: box = 128 bytes x 128 feature rows, 128B swizzle
+    rc = make_tmap_2d(&tw, GLB_UINT8, L.W_q, (uint64_t)L.K, (uint64_t)L.N, (uint64_t)L.K, T2_BK, T2_BM, 1);
   else   // (N, K/2) bytes, K contiguous: box = 64 bytes of codes x 128 feature rows
     rc = make_tmap_2d(&tw, GLB_UINT8, L.W_q, (uint64_t)(L.K / 2), (uint64_t)L.N, (uint64_t)(L.K / 2), T2_BK / 2, T2_BM, 0);
   if (rc != GLB_OK) return rc;
@@ -531,6 +634,7 @@ int launch_tc2(const glb_linear& L, const void* x, void* y, int64_t M, void* wor
   P.scales = L.scales; P.zeros = (L.W_group_mode == 2) ? nullptr : L.zeros;
   P.y = y; P.bias = bias; P.M = (int)M; P.N = (int)L.N; P.K = (int)L.K;
   P.group_size = L.group_size; P.mode = L.W_group_mode;
+  P.post_scale = (L.channel_scale_mode == 1) ? 1 : 0;
   P.tiles_m = plan.tiles_m; P.tiles_n = plan.tiles_n;
   P.splits = plan.splits; P.kb_per_split = plan.kb_per_split; P.n_mma = plan.n_mma;
   P.ws_counter = nullptr; P.ws_partial = nullptr;
@@ -546,7 +650,7 @@ int launch_tc2(const glb_linear& L, const void* x, void* y, int64_t M, void* wor
     if (pf < 0) { const char* e = getenv("GLB_PREFILL_PREFETCH"); pf = e ? atoi(e) : 0; }
     P.prefetch = pf;
   }
-  auto kern = gemm_a16w4_tc2_kernel<BF16, WFMT>;
+  auto kern = gemm_a16w4_tc2_kernel<BF16, WFMT, NBITS>;
   GLB_ENSURE_SMEM(kern, T2_SMEM);
   const int pairs = std::min(num_sms() / 2, P.tiles_m * P.tiles_n * P.splits);
   cudaLaunchConfig_t cfg = {};
@@ -590,6 +694,20 @@ bool gemm_mx_tc2_supported(const glb_linear& L, int64_t M) {
   return true;
 }
 
+// 8-bit weight-only layers (A16W8 int8 / e4m3 with fp16 / bf16 activations; helper.py:88-170)
+bool gemm_w8_tc2_supported(const glb_linear& L, int64_t M) {
+  if (M < 1) return false;
+  if (!(L.input_dtype == GLB_FP16 || L.input_dtype == GLB_BF16) || L.output_dtype != L.input_dtype) return false;
+  if (L.W_nbits != 8 || L.elements_per_sample != 1) return false;
+  if (!(L.wq_dtype == GLB_INT8 || L.wq_dtype == GLB_FP8E4)) return false;
+  if (L.wq_stride0 != 1 || L.wq_stride1 != L.K) return false;                     // (K, N) view of (N, K)
+  if (!((L.W_group_mode == 2 && L.channel_scale_mode == 0) || (L.W_group_mode == 0 && L.channel_scale_mode == 1))) return false;
+  if (L.scales_dtype != GLB_FP32 || L.scales_numel != L.N || L.group_size != L.K) return false;
+  if (L.N % (2 * T2_BM) != 0 || L.K % T2_BK != 0) return false;
+  if (reinterpret_cast<uintptr_t>(L.W_q) & 15) return false;
+  return true;
+}
+
 // bytes of zero-initialised workspace launch_gemm_tc2 needs for (L, M): per-slice counters + fp32 partials (0 without split-K)
 size_t gemm_tc2_workspace(const glb_linear& L, int64_t M) {
   const Tc2Plan p = make_plan(L, M);
@@ -604,9 +722,25 @@ int launch_gemm_tc2(const glb_linear& L, const void* x, void* y, int64_t M, void
                                          : launch_tc2<false, WFMT_MXFP4>(L, x, y, M, workspace, ws_bytes, bias, stream);
   }
   const bool bf = (L.input_dtype == GLB_BF16);
+  if (gemm_w8_tc2_supported(L, M)) {
+    const bool f8 = (L.wq_dtype == GLB_FP8E4);
+    set_kernel_name(f8 ? "gemm_a16w8_fp8_tcgen05_2cta" : "gemm_a16w8_int8_tcgen05_2cta");
+    if (f8) return bf ? launch_tc2<true, WFMT_W8F>(L, x, y, M, workspace, ws_bytes, bias, stream)
+                      : launch_tc2<false, WFMT_W8F>(L, x, y, M, workspace, ws_bytes, bias, stream);
+    return bf ? launch_tc2<true, WFMT_W8I>(L, x, y, M, workspace, ws_bytes, bias, stream)
+              : launch_tc2<false, WFMT_W8I>(L, x, y, M, workspace, ws_bytes, bias, stream);
+  }
+#define GLB_TC2_INT(NB) (bf ? launch_tc2<true, WFMT_INT4, NB>(L, x, y, M, workspace, ws_bytes, bias, stream) \
+                           : launch_tc2<false, WFMT_INT4, NB>(L, x, y, M, workspace, ws_bytes, bias, stream))
+  switch (L.W_nbits) {
+    case 8: set_kernel_name("gemm_a16w8_packed_tcgen05_2cta"); return GLB_TC2_INT(8);
+    case 2: set_kernel_name("gemm_a16w2_tcgen05_2cta"); return GLB_TC2_INT(2);
+    case 1: set_kernel_name("gemm_a16w1_tcgen05_2cta"); return GLB_TC2_INT(1);
+    default: break;
+  }
   set_kernel_name("gemm_a16w4_tcgen05_2cta");
-  return bf ? launch_tc2<true, WFMT_INT4>(L, x, y, M, workspace, ws_bytes, bias, stream)
-            : launch_tc2<false, WFMT_INT4>(L, x, y, M, workspace, ws_bytes, bias, stream);
+  return GLB_TC2_INT(4);
+#undef GLB_TC2_INT
 }
 
 }  // namespace glb

@@ -812,8 +812,8 @@ def test_a8w8_batched_decode_kernel(kind, shape):
 @pytest.mark.parametrize("post_scale", [False, True])
 def test_a16w8_weight_only_decode_kernel(kind, post_scale):
     """helper.A16W8_INT8 / A16W8_FP8 at M <= 16 on the streaming kernel of gl_gemv_a8.cu (fp16 activations, weights
-    widened to fp16 in registers, per-channel scale on the fp32 accumulator) against the oracle; larger batches stay on
-    the general kernel.  Pre-scale mode differs from the oracle by the fp16 rounding of every q * s (decode tolerance)."""
+    widened to fp16 in registers, per-channel scale on the fp32 accumulator) against the oracle; larger batches run on
+    the CTA-pair tcgen05 kernel.  Pre-scale mode differs from the oracle by the fp16 rounding of every q * s (decode tolerance)."""
     N, K = 512, 2048
     W = (torch.randn(N, K, generator=torch.Generator().manual_seed(77)) / 10).half()
     bias = (torch.randn(N, generator=torch.Generator().manual_seed(3)) / 10).half()
@@ -824,7 +824,78 @@ def test_a16w8_weight_only_decode_kernel(kind, post_scale):
         for M in (1, 3, 8, 16, 40):
             x = xgen(M, K, torch.float16, 60 + M)
             y = layer(x.to(DEV))
-            want = f"gemv_a16w8_{kind}" if M <= 16 else "generic_cuda_core"
+            want = f"gemv_a16w8_{kind}" if M <= 16 else f"gemm_a16w8_{kind}_tcgen05_2cta"
             assert _cabi.last_kernel() == want, (M, _cabi.last_kernel())
             e = relerr(y, O.forward(p, x))
             assert e <= REL_DECODE[torch.float16], (kind, post_scale, b is not None, M, e)
+
+
+@pytest.mark.parametrize("kind", ["int8", "fp8"])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("post_scale", [False, True])
+def test_a16w8_weight_only_pair_kernel(kind, dtype, post_scale):
+    """helper.A16W8_INT8 / A16W8_FP8 above the decode range (and bf16 at every M) on the CTA-pair tcgen05 kernel: the
+    8-bit weights are widened by the dequant warps straight into tensor memory (pre-scaling: round16(float(q) * s), the
+    reference's rounding point; post-scaling: exact values, accumulator x s in the epilogue) -- against the oracle,
+    split-K range included, and bit for bit through one-hot activations."""
+    N, K = 768, 2048
+    W = (torch.randn(N, K, generator=torch.Generator().manual_seed(78)) / 10).to(dtype)
+    bias = (torch.randn(N, generator=torch.Generator().manual_seed(4)) / 10).to(dtype)
+    cls = A16W8_INT8 if kind == "int8" else A16W8_FP8
+    for b in (None, bias):
+        layer = cls(device=DEV, dtype=dtype, post_scale=post_scale).from_weights(W.clone().to(DEV), bias=None if b is None else b.to(DEV))
+        p = oracle_from_layer(layer)
+        for M in (17, 64, 129, 300, 1000):
+            if dtype == torch.bfloat16 or M > 16:
+                x = xgen(M, K, dtype, 90 + M)
+                y = layer(x.to(DEV))
+                assert _cabi.last_kernel() == f"gemm_a16w8_{kind}_tcgen05_2cta", (M, _cabi.last_kernel())
+                e = relerr(y, O.forward(p, x))
+                assert e <= REL[dtype], (kind, dtype, post_scale, b is not None, M, e)
+                assert torch.equal(layer(x.to(DEV)), y)
+    if dtype == torch.bfloat16:
+        x1 = xgen(1, K, dtype, 5)
+        y1 = layer(x1.to(DEV))
+        assert _cabi.last_kernel() == f"gemm_a16w8_{kind}_tcgen05_2cta"
+        assert relerr(y1, O.forward(p, x1)) <= REL[dtype]
+    # one-hot activations: every output is one dequantised weight (times 1, plus bias) -> the oracle's bits
+    layer = cls(device=DEV, dtype=dtype, post_scale=post_scale).from_weights(W.clone().to(DEV))
+    p = oracle_from_layer(layer)
+    eye = torch.eye(K, dtype=dtype)[:512]
+    y = layer(eye.to(DEV)).cpu()
+    ref = O.forward(p, eye)
+    assert torch.equal(y, ref.to(y.dtype)), (kind, dtype, post_scale, (y != ref.to(y.dtype)).sum().item())
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("nbits", [8, 2, 1])
+@pytest.mark.parametrize("mode", ["fma", "nofma", "sym"])
+def test_packed_8_2_1_bit_layers_on_the_pair_kernel(dtype, nbits, mode):
+    """A16W8 / A16W2 / A16W1 grouped layers (packing_bitwidth 32; helper.py:344-400) take the same TMA -> unpack ->
+    tensor-memory -> tcgen05 path as 4-bit ones at every M: against the oracle, and through one-hot activations bit for
+    bit (the tensor-memory operand holds exactly the reference's dequantize() values)."""
+    N, K, gs = 512, 1024, 64
+    W_q, scales, zeros = gen_int(N, K, nbits, gs, dtype, seed=nbits + (31 if mode == "fma" else 37))
+    gd = gemlite_b200.dtypes.TORCH_TO_DTYPE[dtype]
+    bias = (torch.randn(N, generator=torch.Generator().manual_seed(4)) / 10).to(dtype)
+    z_in = None if mode == "sym" else zeros
+    name = {8: "gemm_a16w8_packed_tcgen05_2cta", 2: "gemm_a16w2_tcgen05_2cta", 1: "gemm_a16w1_tcgen05_2cta"}[nbits]
+    for b in (None, bias):
+        layer = GemLiteLinear(nbits, gs, K, N, gd, gd)
+        layer.pack(W_q.to(DEV), scales.to(DEV), None if z_in is None else z_in.to(DEV), None if b is None else b.to(DEV),
+                   fma_mode=(mode == "fma"), packing_bitwidth=32)
+        p = O.prepare(W_q, scales, z_in, W_nbits=nbits, group_size=gs, in_features=K, out_features=N,
+                      input_dtype=O.DTYPE_OF[dtype], output_dtype=O.DTYPE_OF[dtype], bias=b, fma_mode=(mode == "fma"),
+                      packing_bitwidth=32)
+        for M in (1, 16, 64, 129, 300):
+            x = xgen(M, K, dtype, 90 + M)
+            y = layer(x.to(DEV))
+            assert _cabi.last_kernel() == name, (M, _cabi.last_kernel())
+            e = relerr(y, O.forward(p, x))
+            assert e <= REL[dtype], (dtype, nbits, mode, b is not None, M, e)
+    layer = GemLiteLinear(nbits, gs, K, N, gd, gd)
+    layer.pack(W_q.to(DEV), scales.to(DEV), None if z_in is None else z_in.to(DEV), None, fma_mode=(mode == "fma"), packing_bitwidth=32)
+    p = O.prepare(W_q, scales, z_in, W_nbits=nbits, group_size=gs, in_features=K, out_features=N,
+                  input_dtype=O.DTYPE_OF[dtype], output_dtype=O.DTYPE_OF[dtype], fma_mode=(mode == "fma"), packing_bitwidth=32)
+    eye = torch.eye(K, dtype=dtype)
+    assert torch.equal(layer(eye.to(DEV)).cpu(), O.forward(p, eye))

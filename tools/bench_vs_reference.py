@@ -23,6 +23,9 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 I4 = dict(kind="pack_int", nbits=4, gs=128, dtype="float16", seed=100)
 A8I = dict(kind="helper_w", cls="A8W8_INT8_dynamic", dtype="float16", seed=200, N=4096, K=4096)
 A8F = dict(kind="helper_w", cls="A8W8_FP8_dynamic", dtype="float16", seed=300, N=4096, K=4096)
+W8 = dict(kind="helper_w", cls="A16W8_INT8", dtype="float16", seed=500, N=4096, K=4096)
+W8F = dict(kind="helper_w", cls="A16W8_FP8", dtype="bfloat16", seed=510, N=4096, K=4096)
+W2 = dict(kind="hqq_int", cls="A16W2_HQQ_INT", nbits=2, gs=64, dtype="float16", seed=520, N=4096, K=4096)
 MX = dict(kind="mx_random", cls="A16W4_MXFP", dtype="bfloat16", seed=400, N=16384, K=16384)
 TIMING = [
     dict(name="c2_decode_M1", build=dict(I4, N=4096, K=4096), M=1, n_layers=64, chained=True, rep=300,
@@ -37,6 +40,13 @@ TIMING = [
     dict(name="c4_int8_M64", build=A8I, M=64, n_layers=16, rep=100),
     dict(name="c4_int8_M4096", build=A8I, M=4096, n_layers=8, rep=50, flops=2 * 4096 ** 3),
     dict(name="c4_fp8_M4096", build=A8F, M=4096, n_layers=8, rep=50, flops=2 * 4096 ** 3),
+    dict(name="a16w8_int8_M1", build=W8, M=1, n_layers=16, rep=100, bytes=4096 * 4096),
+    dict(name="a16w8_int8_M64", build=W8, M=64, n_layers=16, rep=100),
+    dict(name="a16w8_int8_M4096", build=W8, M=4096, n_layers=8, rep=50, flops=2 * 4096 ** 3),
+    dict(name="a16w8_fp8_M4096", build=W8F, M=4096, n_layers=8, rep=50, flops=2 * 4096 ** 3),
+    dict(name="a16w2_hqq_M1", build=W2, M=1, n_layers=16, rep=100),
+    dict(name="a16w2_hqq_M64", build=W2, M=64, n_layers=16, rep=100),
+    dict(name="a16w2_hqq_M4096", build=W2, M=4096, n_layers=8, rep=50, flops=2 * 4096 ** 3),
     dict(name="c5_mxfp4_M1", build=MX, M=1, n_layers=1, rep=50, bytes=142606336),
     dict(name="c5_mxfp4_M4096", build=MX, M=4096, n_layers=1, rep=20, flops=2 * 4096 * 16384 ** 2),
 ]
