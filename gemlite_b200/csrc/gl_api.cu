@@ -185,6 +185,15 @@ static int validate(const glb_linear* L, int64_t M) {
 // (gl_actquant.cu) into the workspace and the layer then runs as the MXFP4 weight-only layer it also is -- on the
 // tcgen05 / streaming MXFP4 kernels instead of the CUDA-core general kernel.  Same products as tl.dot_scaled, fp32
 // accumulation.  (Native block-scaled tcgen05.mma would skip the expansion; not built yet.)
+static bool mx_expand_view(const glb_linear& L, glb_linear* as_weight_only);
+// Native block-scaled tcgen05 kernel (gl_gemm_bs.cu) for the dynamic MX / NV layers it takes -- except at M <= 4 where an
+// MXFP4 layer has the streaming kernel behind the expansion (weights read once at HBM speed, no 256-token tile to fill)
+static bool use_block_scaled(const glb_linear& L, int64_t M) {
+  if (!gemm_bs_supported(L, M)) return false;
+  glb_linear W;
+  if (mx_expand_view(L, &W) && gemv_mx_supported(W, M)) return false;
+  return true;
+}
 static bool mx_expand_view(const glb_linear& L, glb_linear* as_weight_only) {
   if (!(L.input_dtype == GLB_MXFP8 || L.input_dtype == GLB_MXFP4) || L.channel_scale_mode != 4) return false;
   if (L.output_dtype != GLB_BF16) return false;
@@ -242,6 +251,7 @@ extern "C" unsigned long long glb_stream_capture_id(void* stream_) {
 
 extern "C" size_t glb_workspace_bytes(const glb_linear* L, int64_t M, int matmul_type) {
   if (!L || M <= 0) return 0;
+  if (use_block_scaled(*L, M)) return 0;
   {
     glb_linear W;
     if (mx_expand_view(*L, &W) && (gemm_mx_tc2_supported(W, M) || gemv_mx_supported(W, M)))
@@ -253,7 +263,7 @@ extern "C" size_t glb_workspace_bytes(const glb_linear* L, int64_t M, int matmul
   const bool gemv_name = (matmul_type <= GLB_MM_GEMV_SPLITK);
   const bool can_gemv = gemv_supported(*L, M), can_tc = gemm_tc_supported(*L, M);
   if (can_gemv && (gemv_name || (was_auto && M <= 16) || !can_tc)) return gemv_workspace(*L, M);
-  if ((was_auto || matmul_type != GLB_MM_GEMM) && gemm_mid_supported(*L, M)) return 0;
+  if ((was_auto || matmul_type != GLB_MM_GEMM) && (gemm_mid_supported(*L, M) || gemm_w8_mid_supported(*L, M))) return 0;
   if (can_tc) return gemm_tc_workspace(*L, M);
   return 0;
 }
@@ -267,6 +277,7 @@ extern "C" int glb_matmul(const glb_linear* L, const void* x, const void* scales
   GLB_REQUIRE(matmul_type >= GLB_MM_AUTO && matmul_type <= GLB_MM_GEMM, GLB_ERR_INVALID, "bad matmul_type %d", matmul_type);
   if (L->channel_scale_mode >= 2)
     GLB_REQUIRE(scales_x != nullptr, GLB_ERR_INVALID, "channel_scale_mode %d needs activation scales", L->channel_scale_mode);
+  if (use_block_scaled(*L, M)) return launch_gemm_bs(*L, x, scales_x, y, M, bias, stream);
   {
     glb_linear W;
     if (mx_expand_view(*L, &W) && (gemm_mx_tc2_supported(W, M) || gemv_mx_supported(W, M))) {
@@ -297,6 +308,8 @@ extern "C" int glb_matmul(const glb_linear* L, const void* x, const void* scales
   // 0a. A8W8 at 16 < M <= 128: clustered streaming kernel (gl_gemm_a8_mid.cu); "GEMM" by name keeps the tcgen05 tile
   if ((was_auto || matmul_type != GLB_MM_GEMM) && gemm_a8_mid_supported(*L, M))
     return launch_gemm_a8_mid(*L, x, sx, y, M, bias, stream);
+  // 0d. A16W8 weight-only at 16 < M <= 128: clustered streaming kernel with in-register widening (gl_gemm_a8_mid.cu)
+  if ((was_auto || matmul_type != GLB_MM_GEMM) && gemm_w8_mid_supported(*L, M)) return launch_gemm_w8_mid(*L, x, y, M, bias, stream);
   // 0c. A16W8 weight-only (fp16 x int8 / e4m3) at M <= 16: streaming kernel with in-register widening (gl_gemv_a8.cu)
   if (matmul_type != GLB_MM_GEMM && gemv_a16w8_supported(*L, M)) return launch_gemv_a16w8(*L, x, y, M, bias, stream);
   // 0b. A8W8 at M <= 16: 16-feature-row streaming kernel (gl_gemv_a8.cu) (validated in round 2)

@@ -85,6 +85,10 @@ int launch_gemm_tc(const glb_linear& L, const void* x, const float* scales_x, vo
 bool gemm_tc2_supported(const glb_linear& L, int64_t M);
 bool gemm_mx_tc2_supported(const glb_linear& L, int64_t M);
 bool gemm_w8_tc2_supported(const glb_linear& L, int64_t M);
+bool gemm_w8_mid_supported(const glb_linear& L, int64_t M);
+bool gemm_bs_supported(const glb_linear& L, int64_t M);
+int launch_gemm_bs(const glb_linear& L, const void* x, const void* scales_x, void* y, int64_t M, const void* bias, cudaStream_t stream);
+int launch_gemm_w8_mid(const glb_linear& L, const void* x, void* y, int64_t M, const void* bias, cudaStream_t stream);
 bool gemv_mx_supported(const glb_linear& L, int64_t M);
 int launch_gemv_mx(const glb_linear& L, const void* x, void* y, int64_t M, const void* bias, cudaStream_t stream);
 bool gemm_a8_tc2_supported(const glb_linear& L, int64_t M);

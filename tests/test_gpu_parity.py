@@ -518,6 +518,11 @@ def test_mx_dynamic_layers_vs_oracle():
                 expanded = (dt == torch.bfloat16 and layer.channel_scale_mode == 4 and layer.W_nbits == 4
                             and cls is not A4W4_NVFP_dynamic)
                 want = ("gemv_mxfp4" if M <= 4 else "gemm_a16w4_mxfp4_tcgen05_2cta") if expanded else "generic_cuda_core"
+                # both operands of one element type: the tensor core applies the group scales itself (gl_gemm_bs.cu)
+                native = {A8W8_MXFP_dynamic: "gemm_mxfp8_block_scaled_tcgen05_2cta", A4W4_MXFP_dynamic: "gemm_mxfp4_block_scaled_tcgen05_2cta",
+                          A4W4_NVFP_dynamic: "gemm_nvfp4_block_scaled_tcgen05_2cta"}.get(cls)
+                if native and not (expanded and M <= 4):
+                    want = native
                 assert _cabi.last_kernel() == want, (cls.__name__, kw, dt, M, _cabi.last_kernel())
                 if layer.channel_scale_mode == 2:
                     # per-token fp8 activations: the GPU quantiser divides with div.full.f32 like the reference's Triton
@@ -812,8 +817,8 @@ def test_a8w8_batched_decode_kernel(kind, shape):
 @pytest.mark.parametrize("post_scale", [False, True])
 def test_a16w8_weight_only_decode_kernel(kind, post_scale):
     """helper.A16W8_INT8 / A16W8_FP8 at M <= 16 on the streaming kernel of gl_gemv_a8.cu (fp16 activations, weights
-    widened to fp16 in registers, per-channel scale on the fp32 accumulator) against the oracle; larger batches run on
-    the CTA-pair tcgen05 kernel.  Pre-scale mode differs from the oracle by the fp16 rounding of every q * s (decode tolerance)."""
+    widened to fp16 in registers, per-channel scale on the fp32 accumulator) against the oracle; 16 < M <= 128 runs on
+    the clustered batched-decode kernel of gl_gemm_a8_mid.cu (same arithmetic).  Pre-scale mode differs from the oracle by the fp16 rounding of every q * s (decode tolerance)."""
     N, K = 512, 2048
     W = (torch.randn(N, K, generator=torch.Generator().manual_seed(77)) / 10).half()
     bias = (torch.randn(N, generator=torch.Generator().manual_seed(3)) / 10).half()
@@ -824,7 +829,7 @@ def test_a16w8_weight_only_decode_kernel(kind, post_scale):
         for M in (1, 3, 8, 16, 40):
             x = xgen(M, K, torch.float16, 60 + M)
             y = layer(x.to(DEV))
-            want = f"gemv_a16w8_{kind}" if M <= 16 else f"gemm_a16w8_{kind}_tcgen05_2cta"
+            want = f"gemv_a16w8_{kind}" if M <= 16 else f"gemm_a16w8_{kind}_mma_mid"
             assert _cabi.last_kernel() == want, (M, _cabi.last_kernel())
             e = relerr(y, O.forward(p, x))
             assert e <= REL_DECODE[torch.float16], (kind, post_scale, b is not None, M, e)
@@ -849,10 +854,15 @@ def test_a16w8_weight_only_pair_kernel(kind, dtype, post_scale):
             if dtype == torch.bfloat16 or M > 16:
                 x = xgen(M, K, dtype, 90 + M)
                 y = layer(x.to(DEV))
-                assert _cabi.last_kernel() == f"gemm_a16w8_{kind}_tcgen05_2cta", (M, _cabi.last_kernel())
+                mid = 16 < M <= 128                    # batched-decode kernel (scale on the accumulator: decode tolerance)
+                assert _cabi.last_kernel() == (f"gemm_a16w8_{kind}_mma_mid" if mid else f"gemm_a16w8_{kind}_tcgen05_2cta"), (M, _cabi.last_kernel())
                 e = relerr(y, O.forward(p, x))
-                assert e <= REL[dtype], (kind, dtype, post_scale, b is not None, M, e)
+                assert e <= (REL_DECODE if mid else REL)[dtype], (kind, dtype, post_scale, b is not None, M, e)
                 assert torch.equal(layer(x.to(DEV)), y)
+                if mid:                                # the tcgen05 kernel by name, same layer
+                    y2 = layer.forward_manual(x.to(DEV), "GEMM")
+                    assert _cabi.last_kernel() == f"gemm_a16w8_{kind}_tcgen05_2cta"
+                    assert relerr(y2, O.forward(p, x)) <= REL[dtype]
     if dtype == torch.bfloat16:
         x1 = xgen(1, K, dtype, 5)
         y1 = layer(x1.to(DEV))

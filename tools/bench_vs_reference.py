@@ -26,6 +26,9 @@ A8F = dict(kind="helper_w", cls="A8W8_FP8_dynamic", dtype="float16", seed=300, N
 W8 = dict(kind="helper_w", cls="A16W8_INT8", dtype="float16", seed=500, N=4096, K=4096)
 W8F = dict(kind="helper_w", cls="A16W8_FP8", dtype="bfloat16", seed=510, N=4096, K=4096)
 W2 = dict(kind="hqq_int", cls="A16W2_HQQ_INT", nbits=2, gs=64, dtype="float16", seed=520, N=4096, K=4096)
+MX8D = dict(kind="mx_dynamic", cls="A8W8_MXFP_dynamic", dtype="bfloat16", seed=600, N=4096, K=4096, kwargs={"post_scale": False})
+MX4D = dict(kind="mx_dynamic", cls="A4W4_MXFP_dynamic", dtype="bfloat16", seed=610, N=8192, K=8192)
+NV4D = dict(kind="mx_dynamic", cls="A4W4_NVFP_dynamic", dtype="bfloat16", seed=620, N=8192, K=8192)
 MX = dict(kind="mx_random", cls="A16W4_MXFP", dtype="bfloat16", seed=400, N=16384, K=16384)
 TIMING = [
     dict(name="c2_decode_M1", build=dict(I4, N=4096, K=4096), M=1, n_layers=64, chained=True, rep=300,
@@ -47,6 +50,11 @@ TIMING = [
     dict(name="a16w2_hqq_M1", build=W2, M=1, n_layers=16, rep=100),
     dict(name="a16w2_hqq_M64", build=W2, M=64, n_layers=16, rep=100),
     dict(name="a16w2_hqq_M4096", build=W2, M=4096, n_layers=8, rep=50, flops=2 * 4096 ** 3),
+    dict(name="mxdyn_a8w8_M64", build=MX8D, M=64, n_layers=8, rep=50),
+    dict(name="mxdyn_a8w8_M4096", build=MX8D, M=4096, n_layers=8, rep=30, flops=2 * 4096 ** 3),
+    dict(name="mxdyn_a4w4_M64", build=MX4D, M=64, n_layers=4, rep=50),
+    dict(name="mxdyn_a4w4_M4096", build=MX4D, M=4096, n_layers=4, rep=20, flops=2 * 4096 * 8192 ** 2),
+    dict(name="mxdyn_nvfp4_M4096", build=NV4D, M=4096, n_layers=4, rep=20, flops=2 * 4096 * 8192 ** 2),
     dict(name="c5_mxfp4_M1", build=MX, M=1, n_layers=1, rep=50, bytes=142606336),
     dict(name="c5_mxfp4_M4096", build=MX, M=4096, n_layers=1, rep=20, flops=2 * 4096 * 16384 ** 2),
 ]

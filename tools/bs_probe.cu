@@ -254,9 +254,9 @@ int main() {
     run<KIND_MXFP8>(enc, 128, 512, v, "mxf8f6f4 e4m3 x e4m3 /32");
     run<KIND_MXFP8>(enc, 256, 512, v, "mxf8f6f4 e4m3 x e4m3 /32");
   }
-  for (int v = 0; v < 4; ++v) {
+  for (int v = 0; v < 2; ++v) {      // (variant bit 1 -- pair index instead of byte index as the scale id -- is an illegal instruction)
     run<KIND_MXFP4>(enc, 128, 256, v, "mxf4 e2m1 x e2m1 /32");
-    if (v < 2) run<KIND_MXFP4>(enc, 256, 256, v, "mxf4 e2m1 x e2m1 /32");
+    run<KIND_MXFP4>(enc, 256, 256, v, "mxf4 e2m1 x e2m1 /32");
   }
   for (int v = 0; v < 2; ++v) {
     run<KIND_NVFP4>(enc, 128, 256, v, "mxf4nvf4 e2m1 x e2m1 /16 ue4m3");
