@@ -186,9 +186,15 @@ __device__ __forceinline__ uint32_t next_pow2_exponent(float val) {          // 
   return min(max(e, 97u), 254u);
 }
 
-__device__ __forceinline__ uint32_t e2m1_code(float wq) {                    // quant_utils.py:806-808
-  const float a = fabsf(wq);
-  uint32_t idx = (a > 0.25f) + (a > 0.75f) + (a > 1.25f) + (a > 1.75f) + (a > 2.5f) + (a > 3.5f) + (a > 5.0f) + (a > 7.0f);
+// e2m1 index of |wq| = number of the thresholds {0.25, 0.75, 1.25, 1.75, 2.5, 3.5, 5, 7} strictly below it (quant_utils.py:806-808;
+// 8 = beyond the grid, kept: the reference's byte packing lets it carry).  All eight thresholds have zero low 21 bits, so
+// |wq| > T  <=>  (bits(|wq|) - 1) >> 21 >= bits(T) >> 21 = {500, 506, 509, 511, 513, 515, 517, 519}: one subtraction and a
+// few selects instead of eight compares (the chain made the quantiser instruction-bound: 380 instructions per thread).
+__device__ __forceinline__ uint32_t e2m1_code(float wq) {
+  const uint32_t a = __float_as_uint(wq) & 0x7fffffffu;
+  const int d = (int)((a - 1u) >> 21) - 500;
+  uint32_t idx = (d >= 9) ? min(3u + ((uint32_t)(d - 9) >> 1), 8u) : ((d >= 6) ? 2u : ((d >= 0) ? 1u : 0u));
+  if (a == 0u || a > 0x7f800000u) idx = 0u;          // zero (a - 1 wraps) and NaN (every comparison false)
   return (wq >= 0.f) ? idx : idx + 8u;
 }
 
@@ -198,10 +204,11 @@ __global__ void __launch_bounds__(256) act_quant_mx_kernel(const XT* __restrict_
                                                            uint8_t* __restrict__ scales, int64_t M, int64_t M_pad, int64_t K) {
   constexpr int GS = (KIND == GLB_NVFP4) ? 16 : 32;
   constexpr int LANES = GS / 8;                       // threads per group
-  const int64_t per_row = K >> 3;
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = i < M_pad * per_row;              // whole groups are live or dead together (per_row % LANES == 0)
-  const int64_t r = live ? i / per_row : 0, t = live ? i - r * per_row : 0;
+  const uint32_t per_row = (uint32_t)(K >> 3);        // 32-bit index math (the host checks the range): a 64-bit division costs ~100 instructions
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i < (uint32_t)M_pad * per_row;    // whole groups are live or dead together (per_row % LANES == 0)
+  const uint32_t r32 = live ? i / per_row : 0u;
+  const int64_t r = r32, t = live ? (int64_t)(i - r32 * per_row) : 0;
   float v[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) v[j] = 0.f;
@@ -237,11 +244,22 @@ __global__ void __launch_bounds__(256) act_quant_mx_kernel(const XT* __restrict_
     inv_den = __uint_as_float(e << 23);
   }
   if (r >= M) return;
+  // The MX scale is a power of two 2^(e-127): dividing by it and multiplying by 2^(127-e) round the same real number the
+  // same way (both exact unless the result is subnormal, and then both round it once) -- eight IEEE divisions per thread
+  // made this kernel instruction-bound (58 us for 4096 x 8192 bf16).  e = 254 needs the subnormal 2^-127; 0 and 255 keep
+  // the division (0 / 0 and NaN propagation as before).  NVFP4 divides by an arbitrary e4m3 x 0.05: IEEE division stays.
+  float mul = 0.f;
+  bool use_mul = false;
+  if (KIND != GLB_NVFP4) {
+    const uint32_t e = __float_as_uint(inv_den) >> 23;
+    if (e >= 1u && e <= 254u) { mul = (e <= 253u) ? __uint_as_float((254u - e) << 23) : __uint_as_float(0x00400000u); use_mul = true; }
+  }
   if (KIND == GLB_MXFP8) {
     uint32_t w[2] = {0u, 0u};
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float o = fminf(fmaxf(__fdiv_rn(v[j], inv_den), -448.f), 448.f);
+      const float qv = use_mul ? __fmul_rn(v[j], mul) : __fdiv_rn(v[j], inv_den);
+      const float o = fminf(fmaxf(qv, -448.f), 448.f);
       w[j >> 2] |= (uint32_t)float_to_fp8e4(o) << (8 * (j & 3));
     }
     *reinterpret_cast<uint2*>(q + r * K + t * 8) = make_uint2(w[0], w[1]);
@@ -253,7 +271,9 @@ __global__ void __launch_bounds__(256) act_quant_mx_kernel(const XT* __restrict_
     uint32_t w = 0u;
 #pragma unroll
     for (int j = 0; j < 8; j += 2) {
-      const uint32_t lo = e2m1_code(__fdiv_rn(v[j], inv_den)), hi = e2m1_code(__fdiv_rn(v[j + 1], inv_den));
+      const float q0 = use_mul ? __fmul_rn(v[j], mul) : __fdiv_rn(v[j], inv_den);
+      const float q1 = use_mul ? __fmul_rn(v[j + 1], mul) : __fdiv_rn(v[j + 1], inv_den);
+      const uint32_t lo = e2m1_code(q0), hi = e2m1_code(q1);
       w |= ((lo | (hi << 4)) & 0xffu) << (4 * j);
     }
     *reinterpret_cast<uint32_t*>(q + r * (K >> 1) + t * 4) = w;
@@ -331,7 +351,7 @@ extern "C" int glb_quant_act_mx(const void* x, int64_t M, int64_t K, int x_dtype
   cudaStream_t stream = (cudaStream_t)stream_;
   GLB_REQUIRE(x && q && scales && M > 0 && K > 0, GLB_ERR_INVALID, "quant_act_mx: bad arguments");
   GLB_REQUIRE(K % 32 == 0, GLB_ERR_UNSUPPORTED, "quant_act_mx: K must be a multiple of 32 (got %lld)", (long long)K);
-  GLB_REQUIRE(M <= 0x7fffffffLL && (M + 32) * (K >> 3) / 256 < 0x7fffffffLL, GLB_ERR_UNSUPPORTED, "quant_act_mx: too large");
+  GLB_REQUIRE(M <= 0x7fffffffLL && (M + 32) * (K >> 3) < 0xffffff00LL, GLB_ERR_UNSUPPORTED, "quant_act_mx: too large");
   GLB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(q) & 7) == 0, GLB_ERR_INVALID,
               "quant_act_mx: x must be 16-byte and q 8-byte aligned");
   set_kernel_name("act_quant_mx");

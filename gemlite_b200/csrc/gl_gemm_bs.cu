@@ -15,8 +15,8 @@
 //     tokens (N = 256) take 8 columns per word.  tcgen05.cp.32x128b.warpx4 copies one 512-byte block
 //     (byte (r % 32) * 16 + (r / 32) * 4 + j) from shared memory into those 4 columns;
 //   * four "scale" warps per CTA gather the words from the layouts the reference keeps -- weights (K / gs, N) bytes
-//     N-contiguous, activations (M, K / gs) bytes row-major -- into that block layout, a few stages ahead of the MMAs
-//     (register prefetch, they share the operand ring's barriers);
+//     N-contiguous, activations (M, K / gs) bytes row-major -- into that block layout, each warp a whole stage of every
+//     fourth stage (they share the operand ring's barriers);
 //   * per MMA the instruction descriptor selects the scale byte(s) inside the word: mxf8f6f4 (K = 32): byte k-step;
 //     mxf4 (K = 64, 2 scales): byte 0 or 2 of word k-step / 2; nvf4 (K = 64, 4 scales): word k-step;
 //   * tcgen05.cp and tcgen05.mma of one thread execute in issue order, so the scale columns are single buffered.
@@ -47,7 +47,6 @@ constexpr int BS_BAR_OFF = BS_STAGES * BS_STAGE;
 constexpr int BS_SMEM = BS_BAR_OFF + 1024;
 constexpr int BS_GROUP_M = 4;
 constexpr uint32_t BS_SFA_COL = 256, BS_SFB_COL = 256 + 16;         // scale words behind the accumulator
-constexpr int BS_PF = 4;              // stages of scale words a scale warp keeps in registers
 
 struct BsParams {
   const uint8_t* scales_w;   // (K / gs, N) bytes, N contiguous
@@ -59,6 +58,7 @@ struct BsParams {
   int nsf;                   // scale bytes per row = K / gs
   int out_dtype;
   int tiles_m, tiles_n;
+  int debug;                 // diagnostics (GLB_BS_DEBUG): 1 no scale copies, 2 scale warps arrive without writing, 4 scale warps do not take part
 };
 
 __device__ __forceinline__ void bs_tile_coords(int t, int tiles_m, int tiles_n, int& tm, int& tn) {
@@ -132,7 +132,7 @@ gemm_mx_bs_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_x);
     ptx::prefetch_tmap(&tmap_w);
-    for (int s = 0; s < BS_STAGES; ++s) { ptx::mbar_init(&full[s], 1 + 2 * BS_SF_WARPS); ptx::mbar_init(&empty[s], 1); }
+    for (int s = 0; s < BS_STAGES; ++s) { ptx::mbar_init(&full[s], (P.debug & 4) ? 1 : 1 + 2); ptx::mbar_init(&empty[s], 1); }
     ptx::mbar_init(tfull, 1);
     ptx::mbar_init(tempty, 2 * BS_EPI_WARPS);
     ptx::fence_mbar_init();
@@ -163,66 +163,69 @@ gemm_mx_bs_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       }
     }
   } else if (warp >= BS_SF_WARP0 && warp < BS_SF_WARP0 + BS_SF_WARPS) {
-    // ================= scale warps: thread r = feature r of this CTA and tokens r, r + 128 of the pair tile =================
-    const int r = (warp - BS_SF_WARP0) * 32 + lane;
+    // ================= scale warps: warp sw owns every 4th stage of this pair's sequence and fills ALL its scale blocks =================
+    // A stage's scale words are gathered by ONE warp: it issues its loads (weights: 32-bit words = 4 consecutive features of
+    // one group, coalesced; activations: the NW words of a token, one vector load), waits for them, waits for the ring
+    // slot, writes the blocks (weights: bytes of 4 groups re-packed into per-feature words; activations: the four tokens
+    // lane, lane + 32, lane + 64, lane + 96 of a block are ONE 16-byte row) and arrives.  Four warps work on four
+    // different stages, so the memory latency of one stage is hidden behind the other three.
+    // (History, profiles/block_scaled_r2.txt: (1) all four warps on every stage, words assembled right after the byte
+    // loads: every stage sat out the memory latency, 40 % of the unscaled fp8 kernel; (2) register prefetch 4 stages ahead:
+    // fence.proxy.async waits for the OUTSTANDING prefetch loads, same stall; with the scale warps switched off the same
+    // kernel ran 1.5x (MXFP8) / 2.5x (NVFP4) faster.)
+    const int sw = warp - BS_SF_WARP0;
     const uint32_t full_leader = ptx::mapa(ptx::smem_u32(&full[0]), 0u);
     const int my_tiles = (ntiles > pair) ? (ntiles - pair + npairs - 1) / npairs : 0;
-    const int total = my_tiles * kblocks;
-    const uint32_t boff = (uint32_t)((r & 31) * 16 + (r >> 5) * 4);          // this row's word inside a 512-byte block
-    uint32_t wf[BS_PF][NW], wt0[BS_PF][NW], wt1[BS_PF][NW];
-    auto fetch = [&](int i, uint32_t (&f)[NW], uint32_t (&t0)[NW], uint32_t (&t1)[NW]) {
+    const int total = (P.debug & 4) ? 0 : my_tiles * kblocks;
+    // this lane's 32-bit stores on the weight side: feature f = 4 lane + b -> byte offset (f % 32) * 16 + (f / 32) * 4
+    const uint32_t foff0 = (uint32_t)((4 * (lane & 7)) * 16 + (lane >> 3) * 4);
+    for (int i = sw; i < total; i += BS_SF_WARPS) {
       const int j = i / kblocks, kb = i - j * kblocks;
+      const int s = i % BS_STAGES;
+      const uint32_t ph = (uint32_t)((i / BS_STAGES) & 1);
       int tm, tn;
       bs_tile_coords(pair + j * npairs, P.tiles_m, P.tiles_n, tm, tn);
-      const int n = tn * 2 * BS_BM + (int)rank * BS_BM + r;
-      const uint8_t* ws = P.scales_w + (size_t)(kb * 4 * NW) * P.N + n;      // group g of feature n at g * N + n
+      // ---- loads ----
+      uint32_t wfv[NW][4];                                              // [word][group inside the word]: features 4 lane .. 4 lane + 3
+      const uint8_t* ws = P.scales_w + (size_t)(kb * 4 * NW) * P.N + (tn * 2 * BS_BM + (int)rank * BS_BM + 4 * lane);
 #pragma unroll
-      for (int w = 0; w < NW; ++w) {
-        uint32_t v = 0;
+      for (int w = 0; w < NW; ++w)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) v |= (uint32_t)__ldg(ws + (size_t)(4 * w + b) * P.N) << (8 * b);
-        f[w] = v;
-      }
-      const int tok = tm * BS_BT + r;
+        for (int g = 0; g < 4; ++g) wfv[w][g] = __ldg(reinterpret_cast<const uint32_t*>(ws + (size_t)(4 * w + g) * P.N));
+      uint32_t wtv[8][NW];                                              // [token lane + 32 q][word]
 #pragma unroll
-      for (int w = 0; w < NW; ++w) { t0[w] = 0x7f7f7f7fu; t1[w] = 0x7f7f7f7fu; }          // e8m0 1.0 (post-scaled MXFP8 activations)
-      if (P.scales_x) {
-        if (tok < P.M) {
-          const uint32_t* p = reinterpret_cast<const uint32_t*>(P.scales_x + (size_t)tok * P.nsf + kb * 4 * NW);
+      for (int q = 0; q < 8; ++q) {
+        const int tok = tm * BS_BT + lane + 32 * q;
 #pragma unroll
-          for (int w = 0; w < NW; ++w) t0[w] = __ldg(p + w);
-        }
-        if (tok + 128 < P.M) {
-          const uint32_t* p = reinterpret_cast<const uint32_t*>(P.scales_x + (size_t)(tok + 128) * P.nsf + kb * 4 * NW);
-#pragma unroll
-          for (int w = 0; w < NW; ++w) t1[w] = __ldg(p + w);
+        for (int w = 0; w < NW; ++w) wtv[q][w] = P.scales_x ? 0u : 0x7f7f7f7fu;       // e8m0 1.0 for post-scaled MXFP8 activations
+        if (P.scales_x && tok < P.M) {
+          const uint8_t* p = P.scales_x + (size_t)tok * P.nsf + kb * 4 * NW;
+          if (NW == 1) wtv[q][0] = __ldg(reinterpret_cast<const uint32_t*>(p));
+          else if (NW == 2) { const uint2 v = __ldg(reinterpret_cast<const uint2*>(p)); wtv[q][0] = v.x; wtv[q][NW - 1] = v.y; }
+          else { const uint4 v = __ldg(reinterpret_cast<const uint4*>(p)); wtv[q][0] = v.x; wtv[q][1 % NW] = v.y; wtv[q][2 % NW] = v.z; wtv[q][3 % NW] = v.w; }
         }
       }
-    };
+      // ---- the ring slot ----
+      ptx::mbar_wait(&empty[s], ph ^ 1u);
+      unsigned char* sf = smem + s * BS_STAGE + BS_W_BYTES + BS_X_BYTES;
+      if (!(P.debug & 2)) {
 #pragma unroll
-    for (int u = 0; u < BS_PF; ++u)
-      if (u < total) fetch(u, wf[u], wt0[u], wt1[u]);
-    uint32_t s = 0, ph = 0;
-    for (int i0 = 0; i0 < total; i0 += BS_PF) {
-#pragma unroll
-      for (int u = 0; u < BS_PF; ++u) {
-        const int i = i0 + u;
-        if (i < total) {
-          ptx::mbar_wait(&empty[s], ph ^ 1u);
-          unsigned char* sf = smem + s * BS_STAGE + BS_W_BYTES + BS_X_BYTES;
-#pragma unroll
-          for (int w = 0; w < NW; ++w) {
-            *reinterpret_cast<uint32_t*>(sf + (3 * w + 0) * 512 + boff) = wf[u][w];
-            *reinterpret_cast<uint32_t*>(sf + (3 * w + 1) * 512 + boff) = wt0[u][w];
-            *reinterpret_cast<uint32_t*>(sf + (3 * w + 2) * 512 + boff) = wt1[u][w];
-          }
-          ptx::fence_proxy_async_smem();                 // generic-proxy stores before the tensor core's (async proxy) read
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive_cluster(full_leader + s * 8u);
-          if (i + BS_PF < total) fetch(i + BS_PF, wf[u], wt0[u], wt1[u]);
-          if (++s == BS_STAGES) { s = 0; ph ^= 1u; }
+        for (int w = 0; w < NW; ++w) {
+          unsigned char* fa = sf + (3 * w + 0) * 512 + foff0;
+          // feature 4 lane + b: its word = byte b of the four group words
+          const uint32_t lo01 = __byte_perm(wfv[w][0], wfv[w][1], 0x5140), hi01 = __byte_perm(wfv[w][0], wfv[w][1], 0x7362);   // (b0g0,b0g1,b1g0,b1g1) / (b2.., b3..)
+          const uint32_t lo23 = __byte_perm(wfv[w][2], wfv[w][3], 0x5140), hi23 = __byte_perm(wfv[w][2], wfv[w][3], 0x7362);
+          *reinterpret_cast<uint32_t*>(fa + 0 * 16) = __byte_perm(lo01, lo23, 0x5410);    // b = 0: g0 g1 g2 g3
+          *reinterpret_cast<uint32_t*>(fa + 1 * 16) = __byte_perm(lo01, lo23, 0x7632);    // b = 1
+          *reinterpret_cast<uint32_t*>(fa + 2 * 16) = __byte_perm(hi01, hi23, 0x5410);    // b = 2
+          *reinterpret_cast<uint32_t*>(fa + 3 * 16) = __byte_perm(hi01, hi23, 0x7632);    // b = 3
+          *reinterpret_cast<uint4*>(sf + (3 * w + 1) * 512 + lane * 16) = make_uint4(wtv[0][w], wtv[1][w], wtv[2][w], wtv[3][w]);
+          *reinterpret_cast<uint4*>(sf + (3 * w + 2) * 512 + lane * 16) = make_uint4(wtv[4][w], wtv[5][w], wtv[6][w], wtv[7][w]);
         }
       }
+      ptx::fence_proxy_async_smem();                 // generic-proxy stores before the tensor core's (async proxy) read
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_cluster(full_leader + (uint32_t)s * 8u);
     }
   } else if (warp == BS_MMA_WARP) {
     // ================= MMA issuer (leader CTA): per stage NW x 3 scale copies, 4 MMAs, one multicast commit =================
@@ -242,7 +245,7 @@ gemm_mx_bs_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           if (ptx::elect_one()) {
             const uint32_t sfs = sf_smem0 + s * (uint32_t)BS_STAGE;
 #pragma unroll
-            for (int w = 0; w < NW; ++w) {
+            for (int w = 0; w < ((P.debug & 1) ? 0 : NW); ++w) {
               sf_copy_2cta(tmem_base + BS_SFA_COL + 4u * w, make_sf_desc(sfs + (3 * w + 0) * 512));
               sf_copy_2cta(tmem_base + BS_SFB_COL + 8u * w, make_sf_desc(sfs + (3 * w + 1) * 512));
               sf_copy_2cta(tmem_base + BS_SFB_COL + 8u * w + 4u, make_sf_desc(sfs + (3 * w + 2) * 512));
@@ -293,6 +296,29 @@ gemm_mx_bs_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         float sxl = 1.f;
         if (P.post_x && c0 + lane < mrem) sxl = P.post_x[tm * BS_BT + c0 + lane];
         ptx::tmem_ld_wait();
+        if (!P.post_x && P.out_dtype != GLB_FP32) {
+          // micro-scaled activations, 16-bit output: the accumulator is single buffered, so this drain is exposed -- one
+          // cvt, one address add and one 2-byte store per element, no per-element branches but the edge mask
+          unsigned char* yp = reinterpret_cast<unsigned char*>(P.y) + ((int64_t)(tm * BS_BT + c0) * P.N + n) * 2;
+          const int64_t ystride = (int64_t)P.N * 2;
+          const bool f16 = (P.out_dtype == GLB_FP16), hb = (P.bias != nullptr);
+          const int cnt = mrem - c0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float v = __uint_as_float(r[j]);
+            if (KIND == BS_NVFP4) v *= alpha;
+            unsigned short o;
+            if (f16) {
+              if (hb) v = __half2float(__float2half_rn(v)) + bv;
+              o = __half_as_ushort(__float2half_rn(v));
+            } else {
+              if (hb) v = __bfloat162float(__float2bfloat16_rn(v)) + bv;
+              o = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+            }
+            if (j < cnt) *reinterpret_cast<unsigned short*>(yp + j * ystride) = o;
+          }
+          continue;
+        }
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const float sx = __shfl_sync(0xffffffffu, sxl, j);
@@ -348,6 +374,11 @@ int launch_bs(const glb_linear& L, const void* x, const void* scales_x, void* y,
   P.y = y; P.bias = bias; P.M = (int)M; P.N = (int)L.N; P.kbytes = (int)kbytes; P.nsf = (int)(L.K / L.group_size);
   P.out_dtype = act_storage_dtype(L.output_dtype);
   P.tiles_m = (int)((M + BS_BT - 1) / BS_BT); P.tiles_n = (int)(L.N / (2 * BS_BM));
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("GLB_BS_DEBUG"); dbg = e ? atoi(e) : 0; }
+    P.debug = dbg;
+  }
   auto kern = gemm_mx_bs_kernel<KIND>;
   GLB_ENSURE_SMEM(kern, BS_SMEM);
   const int pairs = std::min(num_sms() / 2, P.tiles_m * P.tiles_n);
