@@ -16,6 +16,7 @@ Other keys of the line:
   isolated_call        one eager call, cold L2 (the reference's own timing protocol, examples/benchmark_triton.py:44-60)
   prefill              second half of the metric: M=4096 TFLOP/s at K=N=4096 (the metric's shape) and 8192 (configs[2])
   independent_launches supplementary: same 64 layers, same x for every call, 4 streams in one graph
+  mx_block_scaled      supplementary: A4W4 MXFP4 / A8W8 MXFP8 dynamic layers (M=4096, K=N=8192) on the block-scaled tcgen05 kernel
   reference_triton     the UNMODIFIED reference (baseline/_ref, Triton kernels) timed on this GPU on the same shapes by
                        tools/ref_runner.py (child process): decode chained / flush, prefill -- the comparison
                        `north_star` asks for.  {"unavailable": ...} when baseline/_ref is absent.
@@ -305,6 +306,47 @@ def time_prefill(dev, pk, pn, pm=4096):
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops (cuBLAS burst)" if "bf16_tflops" in peaks else "fallback 1590",
                 "l2": "256 MB flush between iterations"}
     except Exception as e:  # keep the decode line alive, but say why
+        return {"available": False, "error": repr(e)[:200]}
+
+
+def mx_block_scaled_leg(dev, n=8192, m=4096):
+    """Supplementary: the dynamic MX layers of SURVEY 8f item 1 on the block-scaled tcgen05 kernel (gl_gemm_bs.cu) --
+    A4W4_MXFP_dynamic and A8W8_MXFP_dynamic, M tokens through one K = N = n layer: the whole call (activation quantiser +
+    GEMM, what GemLiteLinear.__call__ costs) and the quantiser alone, events around 10 calls, 4 distinct layers > L2."""
+    try:
+        from gemlite_b200 import _cabi
+        from gemlite_b200 import helper as H
+        from gemlite_b200.quant_utils import scale_activations_mxfp4, scale_activations_mxfp8
+        out = {}
+        for cls, kw, quant, tag in (("A4W4_MXFP_dynamic", {}, scale_activations_mxfp4, "a4w4_mxfp4"),
+                                    ("A8W8_MXFP_dynamic", {"post_scale": False}, scale_activations_mxfp8, "a8w8_mxfp8")):
+            layers = []
+            for i in range(4):
+                lin = torch.nn.Linear(n, n, bias=False, dtype=torch.bfloat16, device=dev)
+                lin.weight.requires_grad = False
+                layers.append(getattr(H, cls)(device=dev, dtype=torch.bfloat16, **kw).from_linear(lin))
+                del lin
+            xs = [(torch.randn(m, n, device=dev) / 10).to(torch.bfloat16) for _ in range(4)]
+
+            def timed(fn, rep=3):
+                fn(); torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(rep):
+                    fn()
+                b.record(); torch.cuda.synchronize()
+                return a.elapsed_time(b) / rep / 4
+            call_ms = timed(lambda: [l(x) for l, x in zip(layers, xs)])
+            kern = _cabi.last_kernel()
+            quant_ms = timed(lambda: [quant(x) for x in xs])
+            flops = 2.0 * m * n * n
+            out[tag] = {"kernel": kern, "workload": f"{cls} M={m} K=N={n} bf16", "call_ms": call_ms, "quantiser_ms": quant_ms,
+                        "call_tflops": flops / call_ms / 1e9, "gemm_tflops": flops / max(call_ms - quant_ms, 1e-6) / 1e9}
+            del layers, xs
+            torch.cuda.empty_cache()
+        out["peaks"] = "profiles/tensor_peaks_r2.json: cuBLASLt fp8 e4m3 8192^3 2883-2985 TFLOP/s on this pool (no fp4 entry: no library fp4 GEMM in the image)"
+        return out
+    except Exception as e:
         return {"available": False, "error": repr(e)[:200]}
 
 
@@ -602,12 +644,15 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(n_warm):
         one_step()
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    # NVML is initialised BEFORE the barrier: done after it (as in the first 2- and 4-GPU runs of this round) the ranks left
+    # the barrier aligned and then spent different milliseconds in nvmlInit, and the early ranks waited for the late one in
+    # the first step's device-side barrier -- one ~1 ms step out of 20 (profiles/bench_r2_n4_visit21.json)
     with ClockSampler(local_rank, threaded=False) as clocks:
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
         ev0.record()
         marks[0].record()
         for i in range(args.steps):
@@ -725,6 +770,7 @@ def run_ours(args, rank, world, local_rank):
         prefill["at_4096"] = time_prefill(dev, 4096, 4096)
     independent = independent_leg(layers, x0, dev, peak) if (world == 1 and not skip and not ALIAS) else None
     isolated = isolated_call(layers[0], x0, dev) if (world == 1 and not skip) else None
+    mx_bs = mx_block_scaled_leg(dev) if (world == 1 and not skip) else None
     ref_triton = reference_triton_leg() if (world == 1 and not skip and os.environ.get("BENCH_SKIP_REFERENCE_TRITON", "0") != "1") else None
     cfg = workload_config(world)
     handoff = {"handoff": "griddepcontrol.wait (programmatic dependent launch); a device-side arrival counter was measured slower (DESIGN.md 3.3)"}
@@ -756,6 +802,7 @@ def run_ours(args, rank, world, local_rank):
         "independent_launches": independent,
         "reference_triton": ref_triton,
         "mxfp4_sharded": mx_sharded,
+        "mx_block_scaled": mx_bs,
     }
     print(json.dumps(line), flush=True)
 

@@ -3,6 +3,7 @@
 // the same div.full.f32 the reference's Triton `/` lowers to, clamp to [min, max], INT8 rounds half
 // away from zero (libdevice.round, :255-257), FP8 converts round-to-nearest-even (saturating).
 // HBM-bound: the row is read once with 128-bit loads into registers, reduced, and written once.
+#include <type_traits>
 #include "gl_common.cuh"
 
 namespace glb {
@@ -280,10 +281,103 @@ __global__ void __launch_bounds__(256) act_quant_mx_kernel(const XT* __restrict_
   }
 }
 
+// 16-bit inputs, 16 consecutive k per thread (two 128-bit loads): the 8-per-thread kernel above is instruction-bound
+// (profiles/mx_dynamic_breakdown_r2.txt: 45 us for 4096 x 8192 bf16 -> e2m1, a quarter of an A4W4 layer call) -- index
+// arithmetic, the group reduction and the scale computation are per thread, so twice the elements per thread halves them;
+// an MX group is 2 threads, an NV group 1.  Same arithmetic, same outputs (bit for bit: tests/test_gpu_parity.py).
+template <typename XT, int KIND>
+__global__ void __launch_bounds__(256) act_quant_mx16_kernel(const XT* __restrict__ x, uint8_t* __restrict__ q,
+                                                             uint8_t* __restrict__ scales, uint32_t M, uint32_t M_pad, uint32_t K) {
+  static_assert(sizeof(XT) == 2, "16-bit activations only");
+  constexpr int GS = (KIND == GLB_NVFP4) ? 16 : 32;
+  constexpr int LANES = GS / 16;
+  const uint32_t per_row = K >> 4;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i < M_pad * per_row;              // whole groups are live or dead together (per_row % LANES == 0)
+  const uint32_t r = live ? i / per_row : 0u;
+  const uint32_t t = live ? i - r * per_row : 0u;
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = 0.f;
+  if (live && r < M) {
+    const uint4* src = reinterpret_cast<const uint4*>(x + (size_t)r * K + (size_t)t * 16);
+    const uint4 a = __ldg(src), b = __ldg(src + 1);
+    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (sizeof(XT) == 2 && std::is_same<XT, __nv_bfloat16>::value) {
+        v[2 * j] = __uint_as_float(w[j] << 16);
+        v[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+      } else {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+        v[2 * j] = f.x; v[2 * j + 1] = f.y;
+      }
+    }
+  }
+  float amax = 0.f;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) amax = fmaxf(amax, fabsf(v[j]));
+#pragma unroll
+  for (int o = 1; o < LANES; o <<= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  if (!live) return;
+  const uint32_t g = t / LANES;
+  float mul = 0.f, inv_den = 1.f;
+  if (KIND == GLB_NVFP4) {
+    float sc = __fdiv_rn(amax, (float)(6.0 * 0.05));
+    sc = fminf(sc, 448.f);
+    const uint8_t s8 = float_to_fp8e4(sc);
+    scales[(size_t)r * (K / GS) + g] = s8;
+    inv_den = fmaxf(__fmul_rn(fp8e4_to_float(s8), 0.05f), 1e-6f);
+  } else {
+    const uint32_t e = next_pow2_exponent(__fdiv_rn(amax, (KIND == GLB_MXFP8) ? 448.f : 6.f));     // 97 .. 254
+    if ((t % LANES) == 0) scales[(size_t)r * (K / GS) + g] = (uint8_t)e;
+    mul = (e <= 253u) ? __uint_as_float((254u - e) << 23) : __uint_as_float(0x00400000u);           // exact reciprocal of 2^(e-127)
+  }
+  if (r >= M) return;
+  float qv[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) qv[j] = (KIND == GLB_NVFP4) ? __fdiv_rn(v[j], inv_den) : __fmul_rn(v[j], mul);
+  if (KIND == GLB_MXFP8) {
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float o = fminf(fmaxf(qv[j], -448.f), 448.f);
+      w[j >> 2] |= (uint32_t)float_to_fp8e4(o) << (8 * (j & 3));
+    }
+    *reinterpret_cast<uint4*>(q + (size_t)r * K + (size_t)t * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+  } else {
+    uint32_t w[2] = {0u, 0u};
+#pragma unroll
+    for (int j = 0; j < 16; j += 2) {
+      const uint32_t lo = e2m1_code(qv[j]), hi = e2m1_code(qv[j + 1]);
+      w[j >> 3] |= ((lo | (hi << 4)) & 0xffu) << (4 * (j & 7));      // uint8 arithmetic of the reference (see above)
+    }
+    *reinterpret_cast<uint2*>(q + (size_t)r * (K >> 1) + (size_t)t * 8) = make_uint2(w[0], w[1]);
+  }
+}
+
 template <typename XT>
 int launch_aq_mx(const void* x, int64_t M, int64_t K, int mx_dtype, void* q, void* scales, cudaStream_t stream) {
   const int gs = (mx_dtype == GLB_NVFP4) ? 16 : 32;
   const int64_t M_pad = (M + gs - 1) / gs * gs;
+  if (sizeof(XT) == 2 && (reinterpret_cast<uintptr_t>(q) & 15) == 0 && M_pad * (K >> 4) < 0xffffff00LL && K < 0x7fffffffLL) {
+    // 16 elements per thread (see act_quant_mx16_kernel)
+    static int v16 = -1;
+    if (v16 < 0) { const char* e = getenv("GLB_AQ_MX16"); v16 = e ? atoi(e) : 1; }
+    if (v16) {
+      const unsigned grid16 = (unsigned)((M_pad * (K >> 4) + 255) / 256);
+      using X16 = typename std::conditional<sizeof(XT) == 2, XT, __half>::type;
+      switch (mx_dtype) {
+        case GLB_MXFP8: act_quant_mx16_kernel<X16, GLB_MXFP8><<<grid16, 256, 0, stream>>>((const X16*)x, (uint8_t*)q, (uint8_t*)scales, (uint32_t)M, (uint32_t)M_pad, (uint32_t)K); break;
+        case GLB_MXFP4: act_quant_mx16_kernel<X16, GLB_MXFP4><<<grid16, 256, 0, stream>>>((const X16*)x, (uint8_t*)q, (uint8_t*)scales, (uint32_t)M, (uint32_t)M_pad, (uint32_t)K); break;
+        case GLB_NVFP4: act_quant_mx16_kernel<X16, GLB_NVFP4><<<grid16, 256, 0, stream>>>((const X16*)x, (uint8_t*)q, (uint8_t*)scales, (uint32_t)M, (uint32_t)M_pad, (uint32_t)K); break;
+        default: set_error("quant_act_mx: unsupported mx_dtype %d", mx_dtype); return GLB_ERR_UNSUPPORTED;
+      }
+      count_launch();
+      GLB_CHECK_CUDA(cudaGetLastError());
+      return GLB_OK;
+    }
+  }
   const int64_t threads = M_pad * (K >> 3);
   const unsigned grid = (unsigned)((threads + 255) / 256);
   switch (mx_dtype) {

@@ -215,8 +215,9 @@ gemm_a8w8_mid_kernel(const A8MidParams P) {
 // skeleton: the 8-bit weights stay resident (128 features x 1024 k per CTA), the activation tile is 32 tokens x 1024 k of
 // 16-bit values (pitch 2064 B: conflict-free 128-bit loads), the weights are widened to the compute type in registers
 // (prmt + hsub2 / cvt.f16x2.e4m3x2, bf16 through fp32) and fed to mma.sync.m16n8k16 with the k permutation both operands
-// share.  The per-feature fp32 scale multiplies the fp32 accumulator (pre- and post-scaling alike: pre-scaling differs
-// from the reference's round16(q * s) by weight-rounding noise, same bound as the decode kernel).  M > 32: further passes
+// share.  Pre-scaling (W_group_mode 2) reproduces the reference's rounding point round16(float(q) * s) in the widening
+// (a first version scaled the accumulator instead and sat 1e-4 .. 8e-4 away from the live reference's outputs -- its
+// weight-rounding noise); post-scaling (channel_scale_mode 1) multiplies the fp32 accumulator.  M > 32: further passes
 // over the resident weights.
 constexpr int WM_TOK = 32, WM_NT = 4;
 constexpr int WM_XPITCH = 2 * AM_KC + 16;          // 129 x 16 B
@@ -226,7 +227,7 @@ static_assert(2 * WM_TOK * AM_ROWS * 4 <= WM_XBYTES, "reduction buffer must fit 
 
 struct W8MidParams {
   const uint8_t* W; const void* x; const float* scales_w; void* y; const void* bias;
-  int M, N, K, ks;
+  int M, N, K, ks, prescale;
 };
 
 template <bool BF16> __device__ __forceinline__ void mma_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
@@ -237,8 +238,9 @@ template <bool BF16> __device__ __forceinline__ void mma_16816(float (&d)[4], ui
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
-// 4 weight bytes (k .. k+3) -> two 16-bit-float pairs (k, k+1), (k+2, k+3), exact
-template <bool BF16, bool F8> __device__ __forceinline__ void widen4_mid(uint32_t w, uint32_t& lo, uint32_t& hi) {
+// 4 weight bytes (k .. k+3) -> two 16-bit-float pairs (k, k+1), (k+2, k+3): exact values, or -- pre-scaling, W_group_mode 2 --
+// round16(float(q) * s), the reference's rounding point (b.to(fp32) * scales -> compute dtype)
+template <bool BF16, bool F8> __device__ __forceinline__ void widen4_mid(uint32_t w, float sc, bool prescale, uint32_t& lo, uint32_t& hi) {
   uint32_t l16, h16;
   if (!F8) {
     const uint32_t u = w ^ 0x80808080u;
@@ -252,10 +254,16 @@ template <bool BF16, bool F8> __device__ __forceinline__ void widen4_mid(uint32_
     asm("{\n\t.reg .b16 t;\n\tcvt.u16.u32 t, %1;\n\tcvt.rn.f16x2.e4m3x2 %0, t;\n\t}" : "=r"(l16) : "r"(w & 0xffffu));
     asm("{\n\t.reg .b16 t;\n\tcvt.u16.u32 t, %1;\n\tcvt.rn.f16x2.e4m3x2 %0, t;\n\t}" : "=r"(h16) : "r"(w >> 16));
   }
-  if (!BF16) { lo = l16; hi = h16; return; }
-  const float2 a = __half22float2(*reinterpret_cast<__half2*>(&l16)), b = __half22float2(*reinterpret_cast<__half2*>(&h16));
-  __nv_bfloat162 r0 = __floats2bfloat162_rn(a.x, a.y), r1 = __floats2bfloat162_rn(b.x, b.y);
-  lo = *reinterpret_cast<uint32_t*>(&r0); hi = *reinterpret_cast<uint32_t*>(&r1);
+  if (!BF16 && !prescale) { lo = l16; hi = h16; return; }
+  float2 a = __half22float2(*reinterpret_cast<__half2*>(&l16)), b = __half22float2(*reinterpret_cast<__half2*>(&h16));
+  if (prescale) { a.x *= sc; a.y *= sc; b.x *= sc; b.y *= sc; }
+  if (BF16) {
+    __nv_bfloat162 r0 = __floats2bfloat162_rn(a.x, a.y), r1 = __floats2bfloat162_rn(b.x, b.y);
+    lo = *reinterpret_cast<uint32_t*>(&r0); hi = *reinterpret_cast<uint32_t*>(&r1);
+  } else {
+    __half2 r0 = __floats2half2_rn(a.x, a.y), r1 = __floats2half2_rn(b.x, b.y);
+    lo = *reinterpret_cast<uint32_t*>(&r0); hi = *reinterpret_cast<uint32_t*>(&r1);
+  }
 }
 
 template <bool BF16, bool F8>
@@ -291,6 +299,8 @@ gemm_a16w8_mid_kernel(const W8MidParams P) {
   const unsigned char* wb = wa + (size_t)8 * AM_PITCH;
   const unsigned char* xa = xbuf + (size_t)g * WM_XPITCH + (size_t)kh * 1024 + 32 * t;
   const unsigned char* xg = reinterpret_cast<const unsigned char*>(P.x);
+  const bool pre = (P.prescale != 0);                                  // W_group_mode 2: scale inside the dequantisation
+  const float s_lo = pre ? P.scales_w[feat0 + fb * 16 + g] : 1.f, s_hi = pre ? P.scales_w[feat0 + fb * 16 + g + 8] : 1.f;
 
   int pass = 0;
   for (int tok0 = 0; tok0 < P.M; tok0 += TOK, ++pass) {
@@ -311,10 +321,10 @@ gemm_a16w8_mid_kernel(const W8MidParams P) {
       const uint4 p = *reinterpret_cast<const uint4*>(wa + o);          // 16 weights of row g
       const uint4 q = *reinterpret_cast<const uint4*>(wb + o);          // 16 weights of row g + 8
       uint32_t pl[4], ph[4], ql[4], qh[4];
-      widen4_mid<BF16, F8>(p.x, pl[0], ph[0]); widen4_mid<BF16, F8>(p.y, pl[1], ph[1]);
-      widen4_mid<BF16, F8>(p.z, pl[2], ph[2]); widen4_mid<BF16, F8>(p.w, pl[3], ph[3]);
-      widen4_mid<BF16, F8>(q.x, ql[0], qh[0]); widen4_mid<BF16, F8>(q.y, ql[1], qh[1]);
-      widen4_mid<BF16, F8>(q.z, ql[2], qh[2]); widen4_mid<BF16, F8>(q.w, ql[3], qh[3]);
+      widen4_mid<BF16, F8>(p.x, s_lo, pre, pl[0], ph[0]); widen4_mid<BF16, F8>(p.y, s_lo, pre, pl[1], ph[1]);
+      widen4_mid<BF16, F8>(p.z, s_lo, pre, pl[2], ph[2]); widen4_mid<BF16, F8>(p.w, s_lo, pre, pl[3], ph[3]);
+      widen4_mid<BF16, F8>(q.x, s_hi, pre, ql[0], qh[0]); widen4_mid<BF16, F8>(q.y, s_hi, pre, ql[1], qh[1]);
+      widen4_mid<BF16, F8>(q.z, s_hi, pre, ql[2], qh[2]); widen4_mid<BF16, F8>(q.w, s_hi, pre, ql[3], qh[3]);
 #pragma unroll
       for (int n = 0; n < NT; ++n) {
         const unsigned char* xr = xa + (size_t)n * 8 * WM_XPITCH + 2 * o;
@@ -364,7 +374,7 @@ gemm_a16w8_mid_kernel(const W8MidParams P) {
         const int i = reg & 3, n = reg >> 2;
         const int f = feat0 + blk * 16 + gq + ((i & 2) ? 8 : 0);
         const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
-        const float sb = P.scales_w[f];
+        const float sb = pre ? 1.f : P.scales_w[f];                   // post-scaling: channel_scale_mode 1
         float bv = 0.f;
         if (P.bias) bv = BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(P.bias)[f]) : __half2float(reinterpret_cast<const __half*>(P.bias)[f]);
 #pragma unroll
@@ -372,7 +382,7 @@ gemm_a16w8_mid_kernel(const W8MidParams P) {
           const int m = tok0 + n * 8 + 2 * tq + (i & 1);
           if (m >= P.M) continue;
           const int64_t oi = (int64_t)m * P.N + f;
-          float o = __fmul_rn(__uint_as_float(vv[tq]), sb);
+          float o = pre ? __uint_as_float(vv[tq]) : __fmul_rn(__uint_as_float(vv[tq]), sb);
           if (BF16) {
             if (P.bias) o = __bfloat162float(__float2bfloat16_rn(o)) + bv;
             reinterpret_cast<__nv_bfloat16*>(P.y)[oi] = __float2bfloat16_rn(o);
@@ -412,6 +422,7 @@ int launch_gemm_w8_mid(const glb_linear& L, const void* x, void* y, int64_t M, c
   W8MidParams P;
   P.W = reinterpret_cast<const uint8_t*>(L.W_q); P.x = x; P.scales_w = reinterpret_cast<const float*>(L.scales);
   P.y = y; P.bias = bias; P.M = (int)M; P.N = (int)L.N; P.K = (int)L.K; P.ks = (int)(L.K / AM_KC);
+  P.prescale = (L.W_group_mode == 2) ? 1 : 0;
   const bool bf = (L.input_dtype == GLB_BF16), f8 = (L.wq_dtype == GLB_FP8E4);
   auto kern = bf ? (f8 ? gemm_a16w8_mid_kernel<true, true> : gemm_a16w8_mid_kernel<true, false>)
                  : (f8 ? gemm_a16w8_mid_kernel<false, true> : gemm_a16w8_mid_kernel<false, false>);

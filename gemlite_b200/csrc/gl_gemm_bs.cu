@@ -7,7 +7,7 @@
 // is fp32, like tl.dot_scaled's.
 //
 // Structure = gl_gemm_a8_tc2.cu (CTA pair, tcgen05.mma.cta_group::2, M = 256 features x N = 256 tokens, each CTA stages
-// its 128 feature rows of W and its 128 tokens of x by TMA with the 128-byte swizzle, 128 BYTES of K per stage = 4 MMAs)
+// its 128 feature rows of W and its 128 tokens of x by TMA with the 128-byte swizzle, 128 BYTES of K per stage = 4 MMAs, 5-stage ring)
 // plus the scale plumbing, whose encodings were probed on hardware first (tools/bs_probe.cu,
 // profiles/block_scaled_probe_r2.txt):
 //   * scale factors live in TENSOR MEMORY next to the accumulator: for 128 rows one 32-bit word (4 consecutive group
@@ -36,15 +36,18 @@ constexpr int BS_MXFP8 = 0, BS_MXFP4 = 1, BS_NVFP4 = 2;
 constexpr int BS_BM = 128;            // features per CTA (256 per pair)
 constexpr int BS_BT = 256;            // tokens per pair tile (128 staged per CTA)
 constexpr int BS_BK = 128;            // BYTES of K per row and stage
-constexpr int BS_STAGES = 5;
-constexpr int BS_THREADS = 512;       // w0 producer, w1 TMEM alloc, w2-9 epilogue, w10 idle, w11 MMA issuer, w12-15 scale warps
-constexpr int BS_EPI_WARPS = 8, BS_MMA_WARP = 11, BS_SF_WARP0 = 12, BS_SF_WARPS = 4;
+// ring geometry: a stage = 32 KB of operands + 6 KB of scale blocks (3 x 512 B per scale word, up to 4 words), 5 stages.
+// (A 6-stage ring with the scale region trimmed per kind -- 34 / 35 KB stages for MXFP8 / MXFP4 -- measured 13-15 % SLOWER
+// on two visits: MXFP8 8192^2 2743 -> 2377 TFLOP/s, MXFP4 16384^2 5622 -> 4787; not understood, reverted.)
+constexpr int bs_sf_bytes(int) { return 3 * 4 * 512; }
+constexpr int bs_stages(int) { return 5; }
+constexpr int BS_THREADS = 512;       // w0 producer, w1 TMEM alloc, w2-9 epilogue, w11 MMA issuer, w10 + w12-15 scale warps
+constexpr int BS_EPI_WARPS = 8, BS_MMA_WARP = 11, BS_SF_WARPS = 5;     // scale warps: 10, 12, 13, 14, 15
 constexpr int BS_W_BYTES = BS_BM * BS_BK;            // 16 KB
 constexpr int BS_X_BYTES = (BS_BT / 2) * BS_BK;      // 16 KB
-constexpr int BS_SF_BYTES = 3 * 4 * 512;             // per stage: up to 4 words x (features | tokens 0-127 | tokens 128-255) blocks
-constexpr int BS_STAGE = BS_W_BYTES + BS_X_BYTES + BS_SF_BYTES;     // 38 KB
-constexpr int BS_BAR_OFF = BS_STAGES * BS_STAGE;
-constexpr int BS_SMEM = BS_BAR_OFF + 1024;
+constexpr int bs_stage_bytes(int nw) { return BS_W_BYTES + BS_X_BYTES + bs_sf_bytes(nw); }
+constexpr int bs_smem_bytes(int nw) { return bs_stages(nw) * bs_stage_bytes(nw) + 1024; }
+static_assert(bs_smem_bytes(1) <= 227 * 1024 && bs_smem_bytes(2) <= 227 * 1024 && bs_smem_bytes(4) <= 227 * 1024, "ring too large");
 constexpr int BS_GROUP_M = 4;
 constexpr uint32_t BS_SFA_COL = 256, BS_SFB_COL = 256 + 16;         // scale words behind the accumulator
 
@@ -112,6 +115,7 @@ template <int KIND>
 __global__ void __launch_bounds__(BS_THREADS, 1)
 gemm_mx_bs_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const BsParams P) {
   constexpr int NW = (KIND == BS_MXFP8) ? 1 : ((KIND == BS_MXFP4) ? 2 : 4);     // 32-bit scale words per row and stage
+  constexpr int BS_STAGES = bs_stages(NW), BS_STAGE = bs_stage_bytes(NW), BS_BAR_OFF = BS_STAGES * BS_STAGE;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = smem_raw;
   if ((ptx::smem_u32(smem_raw) & 1023u) != 0u) __trap();
@@ -162,18 +166,18 @@ gemm_mx_bs_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         }
       }
     }
-  } else if (warp >= BS_SF_WARP0 && warp < BS_SF_WARP0 + BS_SF_WARPS) {
-    // ================= scale warps: warp sw owns every 4th stage of this pair's sequence and fills ALL its scale blocks =================
+  } else if (warp == 10 || warp >= 12) {
+    // ================= scale warps: warp sw owns every 5th stage of this pair's sequence and fills ALL its scale blocks =================
     // A stage's scale words are gathered by ONE warp: it issues its loads (weights: 32-bit words = 4 consecutive features of
     // one group, coalesced; activations: the NW words of a token, one vector load), waits for them, waits for the ring
     // slot, writes the blocks (weights: bytes of 4 groups re-packed into per-feature words; activations: the four tokens
-    // lane, lane + 32, lane + 64, lane + 96 of a block are ONE 16-byte row) and arrives.  Four warps work on four
-    // different stages, so the memory latency of one stage is hidden behind the other three.
+    // lane, lane + 32, lane + 64, lane + 96 of a block are ONE 16-byte row) and arrives.  Five warps work on five
+    // different stages, so the memory latency of one stage is hidden behind the other four.
     // (History, profiles/block_scaled_r2.txt: (1) all four warps on every stage, words assembled right after the byte
     // loads: every stage sat out the memory latency, 40 % of the unscaled fp8 kernel; (2) register prefetch 4 stages ahead:
     // fence.proxy.async waits for the OUTSTANDING prefetch loads, same stall; with the scale warps switched off the same
     // kernel ran 1.5x (MXFP8) / 2.5x (NVFP4) faster.)
-    const int sw = warp - BS_SF_WARP0;
+    const int sw = (warp == 10) ? 0 : warp - 11;
     const uint32_t full_leader = ptx::mapa(ptx::smem_u32(&full[0]), 0u);
     const int my_tiles = (ntiles > pair) ? (ntiles - pair + npairs - 1) / npairs : 0;
     const int total = (P.debug & 4) ? 0 : my_tiles * kblocks;
@@ -225,6 +229,8 @@ gemm_mx_bs_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       }
       ptx::fence_proxy_async_smem();                 // generic-proxy stores before the tensor core's (async proxy) read
       __syncwarp();
+      // plain arrive (.release.cta), as everywhere in these kernels: a cluster-scope release was tried for the peer's
+      // arrivals and cost 25-30 % of the GEMM (MXFP8 8192^2 2743 -> 2082 TFLOP/s: the fence sits on every stage's path)
       if (lane == 0) ptx::mbar_arrive_cluster(full_leader + (uint32_t)s * 8u);
     }
   } else if (warp == BS_MMA_WARP) {
@@ -380,6 +386,8 @@ int launch_bs(const glb_linear& L, const void* x, const void* scales_x, void* y,
     P.debug = dbg;
   }
   auto kern = gemm_mx_bs_kernel<KIND>;
+  constexpr int NW = (KIND == BS_MXFP8) ? 1 : ((KIND == BS_MXFP4) ? 2 : 4);
+  constexpr int BS_SMEM = bs_smem_bytes(NW);
   GLB_ENSURE_SMEM(kern, BS_SMEM);
   const int pairs = std::min(num_sms() / 2, P.tiles_m * P.tiles_n);
   cudaLaunchConfig_t cfg = {};

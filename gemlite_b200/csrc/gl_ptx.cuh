@@ -157,6 +157,11 @@ __device__ __forceinline__ uint32_t mapa(uint32_t cta_addr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// same with cluster-scope release: what the arriving thread wrote to ITS OWN shared memory (and ordered with
+// fence.proxy.async) is consumed by its own tensor core on an instruction the LEADER issues after observing this arrival
+__device__ __forceinline__ void mbar_arrive_cluster_release(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 // TMA load issued by either CTA of a pair: data lands in THIS CTA's shared memory, the transaction bytes are
 // reported to the barrier at `cluster_bar_addr` (the leader's) -- cute SM100_TMA_2SM_LOAD_2D.
 __device__ __forceinline__ void tma_load_2d_2cta(void* smem_dst, const CUtensorMap* m, uint32_t cluster_bar_addr, int32_t c0,
