@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgemlite_b200.so")
 STAMP = os.path.join(HERE, "csrc", ".build_stamp")
-SOURCES = ["gl_api.cu", "gl_pack.cu", "gl_actquant.cu", "gl_generic.cu", "gl_gemv.cu", "gl_gemm_tc.cu", "gl_gemm_tc2.cu", "gl_gemm_a8_tc2.cu", "gl_gemv_mx.cu", "gl_gemv_a8.cu", "gl_gemm_mid.cu", "gl_gemm_a8_mid.cu", "gl_gemm_bs.cu"]
+SOURCES = ["gl_api.cu", "gl_pack.cu", "gl_actquant.cu", "gl_generic.cu", "gl_gemv.cu", "gl_gemm_tc.cu", "gl_gemm_tc2.cu", "gl_gemm_a8_tc2.cu", "gl_gemv_mx.cu", "gl_gemv_a8.cu", "gl_gemm_mid.cu", "gl_gemm_a8_mid.cu", "gl_gemm_bs.cu", "gl_gemv_packed.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",

@@ -263,6 +263,7 @@ extern "C" size_t glb_workspace_bytes(const glb_linear* L, int64_t M, int matmul
   const bool gemv_name = (matmul_type <= GLB_MM_GEMV_SPLITK);
   const bool can_gemv = gemv_supported(*L, M), can_tc = gemm_tc_supported(*L, M);
   if (can_gemv && (gemv_name || (was_auto && M <= 16) || !can_tc)) return gemv_workspace(*L, M);
+  if (matmul_type != GLB_MM_GEMM && gemv_packed_supported(*L, M)) return 0;
   if ((was_auto || matmul_type != GLB_MM_GEMM) && (gemm_mid_supported(*L, M) || gemm_w8_mid_supported(*L, M))) return 0;
   if (can_tc) return gemm_tc_workspace(*L, M);
   return 0;
@@ -317,6 +318,8 @@ extern "C" int glb_matmul(const glb_linear* L, const void* x, const void* scales
     return launch_gemv_a8(*L, x, sx, y, M, bias, stream);
   const bool prefer_gemv = can_gemv && (gemv_name || (was_auto && M <= 16) || !can_tc);
   if (prefer_gemv) return launch_gemv(*L, x, sx, y, M, bias, workspace, workspace_bytes, stream);
+  // 1a. packed 8 / 2 / 1-bit grouped layers at M <= 8: streaming CUDA-core kernel (gl_gemv_packed.cu); "GEMM" by name keeps tcgen05
+  if (matmul_type != GLB_MM_GEMM && gemv_packed_supported(*L, M)) return launch_gemv_packed(*L, x, y, M, bias, stream);
   // 1b. batched decode, 16 < M <= 128 (the reference's GEMM_SPLITK range and the bottom of its GEMM range): streaming
   //     mma.sync kernel (gl_gemm_mid.cu); an explicit "GEMM" request keeps the tcgen05 kernel
   if ((was_auto || matmul_type != GLB_MM_GEMM) && gemm_mid_supported(*L, M)) return launch_gemm_mid(*L, x, y, M, bias, stream);

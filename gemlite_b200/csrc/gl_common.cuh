@@ -86,6 +86,8 @@ bool gemm_tc2_supported(const glb_linear& L, int64_t M);
 bool gemm_mx_tc2_supported(const glb_linear& L, int64_t M);
 bool gemm_w8_tc2_supported(const glb_linear& L, int64_t M);
 bool gemm_w8_mid_supported(const glb_linear& L, int64_t M);
+bool gemv_packed_supported(const glb_linear& L, int64_t M);
+int launch_gemv_packed(const glb_linear& L, const void* x, void* y, int64_t M, const void* bias, cudaStream_t stream);
 bool gemm_bs_supported(const glb_linear& L, int64_t M);
 int launch_gemm_bs(const glb_linear& L, const void* x, const void* scales_x, void* y, int64_t M, const void* bias, cudaStream_t stream);
 int launch_gemm_w8_mid(const glb_linear& L, const void* x, void* y, int64_t M, const void* bias, cudaStream_t stream);
