@@ -56,12 +56,24 @@ __global__ void __launch_bounds__(PV_COLS, 4) gemv_packed_kernel(const PvParams 
   float* xs = reinterpret_cast<float*>(smem);                        // [MT][kslice]
   float* sx = xs + (size_t)MT * kslice;                              // [MT][gslice]
   float* red = sx + (size_t)MT * gslice;                             // [MT][128] partial outputs of this CTA
+  float* meta = red + (size_t)MT * PV_COLS;                          // [gslice][2][128] scale, zero of (group, column) as fp32
 
   // ---- weights of the first chunk: independent of the previous kernel ----
   const uint32_t* wp = P.W + (size_t)row0 * P.N + col;
   uint32_t w[PV_CHUNK];
 #pragma unroll
   for (int i = 0; i < PV_CHUNK; ++i) w[i] = (i < rows) ? __ldg(wp + (size_t)i * P.N) : 0u;
+  // ---- this column's scales / zeros of the slice: also before the hand-off, parked in the thread's own shared-memory
+  //      slots (loading them at each group boundary put two dependent global loads per group on the critical path:
+  //      12 us per call for a 4 MB layer) ----
+  {
+    const uint16_t* sp0 = reinterpret_cast<const uint16_t*>(P.scales) + (size_t)g0 * P.N + col;
+    const uint16_t* zp0 = P.zeros ? reinterpret_cast<const uint16_t*>(P.zeros) + (size_t)g0 * P.N + col : nullptr;
+    for (int gg = 0; gg < gslice; ++gg) {
+      meta[(2 * gg) * PV_COLS + threadIdx.x] = pv_to_float<BF16>(__ldg(sp0 + (size_t)gg * P.N));
+      meta[(2 * gg + 1) * PV_COLS + threadIdx.x] = zp0 ? pv_to_float<BF16>(__ldg(zp0 + (size_t)gg * P.N)) : 0.f;
+    }
+  }
   pdl_wait_prior_grids();
   pdl_launch_dependents();
 
@@ -89,8 +101,6 @@ __global__ void __launch_bounds__(PV_COLS, 4) gemv_packed_kernel(const PvParams 
   __syncthreads();
 
   // ---- main loop: chunks of PV_CHUNK packed rows, groups closed as they complete ----
-  const uint16_t* sp = reinterpret_cast<const uint16_t*>(P.scales) + (size_t)g0 * P.N + col;
-  const uint16_t* zp = P.zeros ? reinterpret_cast<const uint16_t*>(P.zeros) + (size_t)g0 * P.N + col : nullptr;
   float out[MT], acc[MT];
 #pragma unroll
   for (int m = 0; m < MT; ++m) { out[m] = 0.f; acc[m] = 0.f; }
@@ -119,8 +129,7 @@ __global__ void __launch_bounds__(PV_COLS, 4) gemv_packed_kernel(const PvParams 
           }
         }
         if (++in_group == wpg) {                       // group complete: apply its scale / zero once
-          const float s = pv_to_float<BF16>(sp[(size_t)g * P.N]);
-          const float z = zp ? pv_to_float<BF16>(zp[(size_t)g * P.N]) : 0.f;
+          const float s = meta[(2 * g) * PV_COLS + threadIdx.x], z = meta[(2 * g + 1) * PV_COLS + threadIdx.x];
 #pragma unroll
           for (int m = 0; m < MT; ++m) {
             const float sxm = sx[(size_t)m * gslice + g];
@@ -172,7 +181,7 @@ int pv_ks(const glb_linear& L) {
 }
 size_t pv_smem(const glb_linear& L, int mt) {
   const int ks = pv_ks(L), kslice = (int)(L.K / ks), gslice = kslice / L.group_size;
-  return (size_t)mt * (kslice + gslice + PV_COLS) * sizeof(float);
+  return ((size_t)mt * (kslice + gslice + PV_COLS) + (size_t)2 * gslice * PV_COLS) * sizeof(float);
 }
 
 template <bool BF16, int NBITS, int MT>
