@@ -189,3 +189,31 @@ def test_mx_dynamic_descriptor_validation_without_gpu():
               _mx_desc(256, 512, DType.NVFP4.value, 4, 32, 4, DType.FP8.value)):   # NVFP4 groups are 16 wide
         rc, msg = call(d, fake)
         assert rc == -2, (rc, msg)
+
+
+def test_workspace_plan_of_the_round2_routes_without_gpu():
+    """Host-side routing of the kernels added in round 2 (glb_workspace_bytes mirrors glb_matmul's dispatch): the
+    block-scaled MX kernel, the packed-width decode kernel and the A16W8 batched-decode kernel need no scratch; the
+    expansion path (A8W4, or A4W4 MXFP4 at M <= 4) needs room for the expanded activations behind the 64 KB counter region;
+    packed 2-bit layers above the decode range take the pair kernel's split-K plan."""
+    lib = _cabi.load()
+    u8 = DType.UINT8.value
+    ws = lambda d, M, mt=-1: lib.glb_workspace_bytes(ctypes.byref(d), M, mt)   # noqa: E731
+    # A8W8 MXFP8 and A4W4 NVFP4: block-scaled kernel at every M
+    for d in (_mx_desc(4096, 4096, DType.MXFP8.value, 8, 32, 4, u8), _mx_desc(4096, 4096, DType.NVFP4.value, 4, 16, 4, DType.FP8.value)):
+        assert [ws(d, M) for M in (1, 64, 4096)] == [0, 0, 0]
+    # A4W4 MXFP4 (bf16): streaming kernel behind the bf16 expansion at M <= 4, block-scaled above
+    a4 = _mx_desc(4096, 4096, DType.MXFP4.value, 4, 32, 4, u8)
+    # (the expanded activations sit behind the inner launch's own scratch, never inside the first 64 KB: the split-K counters)
+    for M in (1, 4):
+        assert ws(a4, M) >= 65536 + M * 4096 * 2 and (ws(a4, M) - M * 4096 * 2) % 256 == 0, (M, ws(a4, M))
+    assert ws(a4, 5) == 0 and ws(a4, 4096) == 0
+    # a width the block-scaled kernel does not take (N % 256 != 0) stays on the expansion path
+    odd = _mx_desc(4096 + 128, 4096, DType.MXFP4.value, 4, 32, 4, u8)
+    assert ws(odd, 64) == 0 or ws(odd, 64) >= 65536
+    # packed 2-bit grouped layer: decode kernel (no scratch) to M = 8, pair kernel + split-K plan above
+    w2 = _a16w4_desc(4096, 4096, gs=64)
+    w2.W_nbits, w2.elements_per_sample, w2.unpack_mask, w2.wq_rows = 2, 16, 3, 4096 // 16
+    assert ws(w2, 1) == 0 and ws(w2, 8) == 0
+    assert ws(w2, 16) == 65536 + 16 * 4 * 2 * 128 * 64 * 4        # same plan as the 4-bit layer by name (tests above)
+    assert ws(w2, 4096) == 0
