@@ -157,7 +157,7 @@ GLB_API size_t glb_workspace_bytes(const glb_linear* layer, int64_t M, int matmu
 /* y(M, N) = epilogue( x(M, K) . dequant(W_q)(K, N) ) [+ bias]
  *   x        : (M, K) row-major, dtype = storage type of layer->input_dtype
  *              (already quantised when layer->scaled_activations != 0)
- *   scales_x : (M) fp32 per-token activation scales, or NULL
+ *   scales_x : (M) fp32 per-token activation scales; MX / NV layers with channel_scale_mode 4: (M, K / group) e8m0 / e4m3 bytes; or NULL
  *   y        : (M, N) row-major, layer->output_dtype
  *   bias     : (N) in the output dtype, or NULL
  *   workspace: >= glb_workspace_bytes(...) bytes, 16-byte aligned, zero-initialised once (may be NULL when that is 0);
